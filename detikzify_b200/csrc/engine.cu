@@ -1,0 +1,864 @@
+// C-ABI implementation (see include/detikzify_b200.h). Host-side orchestration only: weight-arena
+// layout, KV sequence slots, workspaces, CUDA-graph capture of the decode+sample step and the launch
+// sequences for ViT encode / projector / prefill / decode. All arithmetic is in the .cu kernels.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/detikzify_b200.h"
+#include "launch.h"
+
+using namespace dtk;
+
+namespace {
+
+struct WEntry {
+  std::string name;
+  int rows, cols;
+  uint64_t offset, nbytes;
+};
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+inline int patch_k_padded(const dtk_config& c) { return (int)align_up((uint64_t)3 * c.v_patch * c.v_patch, 64); }
+inline int v_tokens(const dtk_config& c) { int g = c.v_image / c.v_patch; return g * g; }
+inline int img_tokens(const dtk_config& c) { return v_tokens(c) / c.concat; }
+
+std::vector<WEntry> build_table(const dtk_config& c) {
+  std::vector<WEntry> t;
+  uint64_t off = 0;
+  auto add = [&](const std::string& n, int rows, int cols) {
+    WEntry e{n, rows, cols, off, (uint64_t)rows * cols * 2};
+    off = align_up(off + e.nbytes, 256);
+    t.push_back(e);
+  };
+  const int H = c.hidden, I = c.inter, V = c.vocab, qd = c.heads * c.head_dim, kd = c.kv_heads * c.head_dim;
+  add("dec.embed", V, H);
+  for (int l = 0; l < c.layers; ++l) {
+    std::string p = "dec.L" + std::to_string(l) + ".";
+    add(p + "norm1", 1, H);
+    add(p + "wqkv", qd + 2 * kd, H);
+    add(p + "wo", H, qd);
+    add(p + "norm2", 1, H);
+    add(p + "wgu", 2 * I, H);  // interleaved rows: 2i = gate_i, 2i+1 = up_i
+    add(p + "wd", H, I);
+  }
+  add("dec.norm", 1, H);
+  add("dec.lm_head", V, H);
+  const int D = c.v_hidden, VI = c.v_inter, N = v_tokens(c);
+  add("proj.w", H, D * c.concat);
+  add("proj.b", 1, H);
+  add("vit.patch_w", D, patch_k_padded(c));
+  add("vit.patch_b", 1, D);
+  add("vit.pos", N, D);
+  for (int l = 0; l < c.v_layers; ++l) {
+    std::string p = "vit.L" + std::to_string(l) + ".";
+    add(p + "ln1_w", 1, D); add(p + "ln1_b", 1, D);
+    add(p + "wqkv", 3 * D, D); add(p + "bqkv", 1, 3 * D);
+    add(p + "wo", D, D); add(p + "bo", 1, D);
+    add(p + "ln2_w", 1, D); add(p + "ln2_b", 1, D);
+    add(p + "w1", VI, D); add(p + "b1", 1, VI);
+    add(p + "w2", D, VI); add(p + "b2", 1, D);
+  }
+  add("vit.post_w", 1, D); add("vit.post_b", 1, D);
+  add("vit.head.probe", 1, D);
+  add("vit.head.wq", D, D); add("vit.head.bq", 1, D);
+  add("vit.head.wkv", 2 * D, D); add("vit.head.bkv", 1, 2 * D);
+  add("vit.head.wo", D, D); add("vit.head.bo", 1, D);
+  add("vit.head.ln_w", 1, D); add("vit.head.ln_b", 1, D);
+  add("vit.head.w1", VI, D); add("vit.head.b1", 1, VI);
+  add("vit.head.w2", D, VI); add("vit.head.b2", 1, D);
+  return t;
+}
+
+bool config_ok(const dtk_config& c, std::string& why) {
+  auto bad = [&](const char* m) { why = m; return false; };
+  if (c.hidden <= 0 || c.inter <= 0 || c.layers <= 0 || c.heads <= 0 || c.kv_heads <= 0 || c.vocab <= 0) return bad("non-positive decoder dims");
+  if (c.head_dim != 128) return bad("decoder head_dim must be 128");
+  if (c.heads % c.kv_heads) return bad("heads % kv_heads != 0");
+  if ((c.hidden & 7) || (c.inter & 7)) return bad("hidden/inter must be multiples of 8");
+  if (c.max_len <= 0 || c.max_seqs <= 0 || c.max_batch <= 0 || c.max_batch > 64) return bad("bad max_len/max_seqs/max_batch (max_batch <= 64)");
+  if (c.v_hidden <= 0 || c.v_heads <= 0 || c.v_hidden % c.v_heads) return bad("bad vision dims");
+  if (c.v_hidden / c.v_heads != 72) return bad("vision head_dim must be 72 (SigLIP so400m)");
+  if ((c.v_hidden & 7) || (c.v_inter & 7)) return bad("vision dims must be multiples of 8");
+  if (c.v_patch <= 0 || c.v_image < c.v_patch) return bad("bad image/patch size");  // conv stride P, no padding: floor(S/P) patches
+  if (c.concat <= 0 || img_tokens(c) <= 0) return bad("bad concat");
+  return true;
+}
+
+}  // namespace
+
+struct dtk_engine {
+  dtk_config cfg;
+  int device = 0;
+  std::string err;
+  uint64_t launches = 0;
+  const uint8_t* arena = nullptr;
+  std::map<std::string, const bf16*> w;
+
+  // KV slots: [slot][layer][2][kv_head][max_len][128] bf16
+  bf16* kv = nullptr;
+  int64_t kv_layer_stride = 0, kv_v_offset = 0, kv_slot_stride = 0;
+  std::vector<char> slot_used;
+  float* rope_cs = nullptr;  // [max_len, 64, 2]
+
+  // prefill workspace (max_len rows)
+  float *p_x = nullptr, *p_qkv = nullptr;
+  bf16 *p_xn = nullptr, *p_q = nullptr, *p_att = nullptr, *p_h = nullptr;
+  // decode workspace (max_batch rows)
+  float *d_x = nullptr, *d_q = nullptr, *d_att = nullptr, *d_h = nullptr, *d_logits = nullptr, *d_scratch = nullptr;
+  float *d_part_o = nullptr, *d_part_ml = nullptr;
+  unsigned int* d_counters = nullptr;  // [max_batch*heads] + 1 (sampler done counter)
+  int *d_slots = nullptr, *d_pos = nullptr, *d_tok = nullptr;
+  unsigned long long* d_gen = nullptr;  // [0] = step counter
+  // ViT workspace (grows with batch)
+  int vit_cap = 0;
+  float *v_x = nullptr, *v_small_f = nullptr, *v_pq = nullptr;
+  bf16 *v_xn = nullptr, *v_qkv = nullptr, *v_att = nullptr, *v_h = nullptr, *v_small_b = nullptr;
+  bool pq_ready = false;
+
+  // generation loop
+  int gen_B = 0;
+  dtk_sampling gen_params{};
+  int* host_ring = nullptr;          // pinned, mapped
+  long long* host_flag = nullptr;    // pinned, mapped
+  int* dev_ring = nullptr;
+  long long* dev_flag = nullptr;
+  int ring = 256;
+  std::map<std::string, cudaGraphExec_t> graphs;
+  cudaGraphExec_t gen_graph = nullptr;
+  cudaStream_t gen_stream = nullptr;
+};
+
+namespace {
+
+#define DTK_CK(expr)                                                                          \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      eng->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+      return DTK_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define DTK_REQUIRE(cond, msg)                                                                \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      eng->err = std::string("invalid argument: ") + msg;                                     \
+      return DTK_ERR_INVALID;                                                                 \
+    }                                                                                         \
+  } while (0)
+
+template <typename T>
+int dev_alloc(dtk_engine* eng, T** p, uint64_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) {
+    eng->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return DTK_ERR_OOM;
+  }
+  *p = (T*)q;
+  return DTK_OK;
+}
+#define DTK_ALLOC(ptr, count)                         \
+  do {                                                \
+    int _r = dev_alloc(eng, &(ptr), (uint64_t)(count)); \
+    if (_r != DTK_OK) return _r;                      \
+  } while (0)
+
+const bf16* W(dtk_engine* eng, const std::string& n) { return eng->w.at(n); }
+std::string LN(const char* prefix, int l, const char* s) { return std::string(prefix) + std::to_string(l) + "." + s; }
+
+struct StateArgs {
+  int n;
+  int slots[64], pos[64];
+  long long tok[64];
+  int have_tok;
+};
+__global__ void set_state_kernel(StateArgs a, int* slots, int* pos, int* tok) {
+  int i = threadIdx.x;
+  if (i < a.n) {
+    slots[i] = a.slots[i];
+    pos[i] = a.pos[i];
+    if (a.have_tok) tok[i] = (int)a.tok[i];
+  }
+}
+__global__ void reset_gen_kernel(unsigned long long* gen, unsigned int* done) {
+  gen[0] = 0ull;
+  *done = 0u;
+}
+
+int ensure_vit_ws(dtk_engine* eng, int B) {
+  if (B <= eng->vit_cap) return DTK_OK;
+  const dtk_config& c = eng->cfg;
+  const int64_t rows = (int64_t)B * v_tokens(c);
+  cudaFree(eng->v_x); cudaFree(eng->v_xn); cudaFree(eng->v_qkv); cudaFree(eng->v_att); cudaFree(eng->v_h);
+  cudaFree(eng->v_small_f); cudaFree(eng->v_small_b);
+  eng->v_x = nullptr; eng->v_xn = eng->v_qkv = eng->v_att = eng->v_h = eng->v_small_b = nullptr; eng->v_small_f = nullptr;
+  eng->vit_cap = 0;
+  DTK_ALLOC(eng->v_x, rows * c.v_hidden);
+  DTK_ALLOC(eng->v_xn, rows * c.v_hidden);
+  DTK_ALLOC(eng->v_qkv, rows * 3 * c.v_hidden);
+  DTK_ALLOC(eng->v_att, rows * c.v_hidden);
+  int64_t hcols = c.v_inter > patch_k_padded(c) ? c.v_inter : patch_k_padded(c);
+  DTK_ALLOC(eng->v_h, rows * hcols);
+  DTK_ALLOC(eng->v_small_f, (int64_t)B * c.v_hidden * 2);
+  DTK_ALLOC(eng->v_small_b, (int64_t)B * (c.v_hidden * 2 + c.v_inter));
+  eng->vit_cap = B;
+  return DTK_OK;
+}
+
+// ViT blocks for B images already resident as fp32 pixels; leaves post-LN tokens (bf16) in v_xn.
+int vit_forward(dtk_engine* eng, const float* pixels, int B, float* tokens_out, float* pooled_out, cudaStream_t s) {
+  const dtk_config& c = eng->cfg;
+  const int D = c.v_hidden, VI = c.v_inter, N = v_tokens(c), KP = patch_k_padded(c);
+  const int M = B * N;
+  const int act = c.v_act == 1 ? ACT_GELU_ERF : ACT_GELU_TANH;
+  uint64_t* lc = &eng->launches;
+  bf16* col = eng->v_h;  // alias: v_h is free until the first MLP
+  DTK_CK(launch_im2col(pixels, B, c.v_image, c.v_patch, KP, col, s, lc));
+  {
+    GemmArgs g{};
+    g.A = col; g.lda = KP; g.W = W(eng, "vit.patch_w"); g.ldw = KP; g.M = M; g.N = D; g.K = KP;
+    g.bias = W(eng, "vit.patch_b"); g.rowbias = W(eng, "vit.pos"); g.rowbias_mod = N;
+    g.out_f32 = eng->v_x; g.ldo = D;
+    DTK_CK(launch_gemm(g, s, lc));
+  }
+  for (int l = 0; l < c.v_layers; ++l) {
+    DTK_CK(launch_layernorm(eng->v_x, W(eng, LN("vit.L", l, "ln1_w")), W(eng, LN("vit.L", l, "ln1_b")), c.v_eps, M, D, eng->v_xn, nullptr, s, lc));
+    {
+      GemmArgs g{};
+      g.A = eng->v_xn; g.lda = D; g.W = W(eng, LN("vit.L", l, "wqkv")); g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+      g.bias = W(eng, LN("vit.L", l, "bqkv")); g.out_bf16 = eng->v_qkv; g.ldo = 3 * D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    {
+      AttnArgs a{};
+      a.q = eng->v_qkv; a.k = eng->v_qkv + D; a.v = eng->v_qkv + 2 * D; a.o = eng->v_att;
+      a.q_bs = a.k_bs = a.v_bs = (int64_t)N * 3 * D; a.q_hs = a.k_hs = a.v_hs = 72; a.q_rs = a.k_rs = a.v_rs = 3 * D;
+      a.o_bs = (int64_t)N * D; a.o_hs = 72; a.o_rs = D;
+      a.B = B; a.heads = c.v_heads; a.kv_group = 1; a.Tq = N; a.Tk = N; a.q_pos0 = 0; a.causal = 0; a.head_dim = 72;
+      a.scale = 1.0f / sqrtf(72.f);
+      DTK_CK(launch_flash_attn(a, s, lc));
+    }
+    {
+      GemmArgs g{};
+      g.A = eng->v_att; g.lda = D; g.W = W(eng, LN("vit.L", l, "wo")); g.ldw = D; g.M = M; g.N = D; g.K = D;
+      g.bias = W(eng, LN("vit.L", l, "bo")); g.resid = eng->v_x; g.ldr = D; g.out_f32 = eng->v_x; g.ldo = D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    DTK_CK(launch_layernorm(eng->v_x, W(eng, LN("vit.L", l, "ln2_w")), W(eng, LN("vit.L", l, "ln2_b")), c.v_eps, M, D, eng->v_xn, nullptr, s, lc));
+    {
+      GemmArgs g{};
+      g.A = eng->v_xn; g.lda = D; g.W = W(eng, LN("vit.L", l, "w1")); g.ldw = D; g.M = M; g.N = VI; g.K = D;
+      g.bias = W(eng, LN("vit.L", l, "b1")); g.act = act; g.out_bf16 = eng->v_h; g.ldo = VI;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    {
+      GemmArgs g{};
+      g.A = eng->v_h; g.lda = VI; g.W = W(eng, LN("vit.L", l, "w2")); g.ldw = VI; g.M = M; g.N = D; g.K = VI;
+      g.bias = W(eng, LN("vit.L", l, "b2")); g.resid = eng->v_x; g.ldr = D; g.out_f32 = eng->v_x; g.ldo = D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+  }
+  DTK_CK(launch_layernorm(eng->v_x, W(eng, "vit.post_w"), W(eng, "vit.post_b"), c.v_eps, M, D, eng->v_xn, tokens_out, s, lc));
+
+  if (pooled_out) {
+    if (!eng->pq_ready) {  // probe query is input independent: q = probe Wq^T + bq
+      GemmArgs g{};
+      g.A = W(eng, "vit.head.probe"); g.lda = D; g.W = W(eng, "vit.head.wq"); g.ldw = D; g.M = 1; g.N = D; g.K = D;
+      g.bias = W(eng, "vit.head.bq"); g.out_f32 = eng->v_pq; g.ldo = D;
+      DTK_CK(launch_gemm(g, s, lc));
+      eng->pq_ready = true;
+    }
+    bf16* kvb = eng->v_qkv;  // [M, 2D]
+    {
+      GemmArgs g{};
+      g.A = eng->v_xn; g.lda = D; g.W = W(eng, "vit.head.wkv"); g.ldw = D; g.M = M; g.N = 2 * D; g.K = D;
+      g.bias = W(eng, "vit.head.bkv"); g.out_bf16 = kvb; g.ldo = 2 * D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    bf16* pa = eng->v_small_b;               // [B, D] attention output
+    bf16* pn = eng->v_small_b + (int64_t)B * D;      // [B, D] LN output
+    bf16* ph = eng->v_small_b + (int64_t)B * 2 * D;  // [B, VI]
+    float* pr = eng->v_small_f;              // [B, D] residual
+    DTK_CK(launch_pool_attn(eng->v_pq, kvb, B, N, D, c.v_heads, 1.0f / sqrtf(72.f), pa, s, lc));
+    {
+      GemmArgs g{};
+      g.A = pa; g.lda = D; g.W = W(eng, "vit.head.wo"); g.ldw = D; g.M = B; g.N = D; g.K = D;
+      g.bias = W(eng, "vit.head.bo"); g.out_f32 = pr; g.ldo = D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    DTK_CK(launch_layernorm(pr, W(eng, "vit.head.ln_w"), W(eng, "vit.head.ln_b"), c.v_eps, B, D, pn, nullptr, s, lc));
+    {
+      GemmArgs g{};
+      g.A = pn; g.lda = D; g.W = W(eng, "vit.head.w1"); g.ldw = D; g.M = B; g.N = VI; g.K = D;
+      g.bias = W(eng, "vit.head.b1"); g.act = act; g.out_bf16 = ph; g.ldo = VI;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    {
+      GemmArgs g{};
+      g.A = ph; g.lda = VI; g.W = W(eng, "vit.head.w2"); g.ldw = VI; g.M = B; g.N = D; g.K = VI;
+      g.bias = W(eng, "vit.head.b2"); g.resid = pr; g.ldr = D; g.out_f32 = pooled_out; g.ldo = D;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+  }
+  return DTK_OK;
+}
+
+// concat-3 projector on bf16 tokens [B, N, D] -> fp32 [B, P, H]
+int project_bf16(dtk_engine* eng, const bf16* tokens, int B, float* out, cudaStream_t s) {
+  const dtk_config& c = eng->cfg;
+  const int D = c.v_hidden, N = v_tokens(c), P = img_tokens(c), K = D * c.concat;
+  GemmArgs g{};
+  g.A = tokens + (int64_t)(N - P * c.concat) * D;  // drop the first patches when N % concat != 0
+  g.lda = K; g.a_rows_per_batch = P; g.a_batch_stride = (int64_t)N * D;
+  g.W = W(eng, "proj.w"); g.ldw = K; g.M = B * P; g.N = c.hidden; g.K = K;
+  g.bias = W(eng, "proj.b"); g.out_f32 = out; g.ldo = c.hidden;
+  DTK_CK(launch_gemm(g, s, &eng->launches));
+  return DTK_OK;
+}
+
+bf16* kv_layer(dtk_engine* eng, int slot, int layer) {
+  return eng->kv + (int64_t)slot * eng->kv_slot_stride + (int64_t)layer * eng->kv_layer_stride;
+}
+
+int nsplit_for(const dtk_config& c, int B) {
+  int n = (2 * 148 + c.heads * B - 1) / (c.heads * B);
+  if (n < 1) n = 1;
+  if (n > 16) n = 16;
+  return n;
+}
+
+// one decode step for the B sequences whose (slot, pos, tok) live in d_slots / d_pos / d_tok (or tok64)
+int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits, cudaStream_t s) {
+  const dtk_config& c = eng->cfg;
+  const int H = c.hidden, I = c.inter, qd = c.heads * 128, kd = c.kv_heads * 128;
+  uint64_t* lc = &eng->launches;
+  DTK_CK(launch_embed_tokens(tok64 ? nullptr : eng->d_tok, tok64, B, W(eng, "dec.embed"), H, c.vocab, eng->d_x, s, lc));
+  const int nsplit = nsplit_for(c, B);
+  for (int l = 0; l < c.layers; ++l) {
+    {
+      GemvArgs g{};
+      g.mode = GEMV_QKV; g.W = W(eng, LN("dec.L", l, "wqkv")); g.N = qd + 2 * kd; g.K = H;
+      g.x = eng->d_x; g.x_stride = H; g.norm_w = W(eng, LN("dec.L", l, "norm1")); g.eps = c.rms_eps;
+      g.out = eng->d_q; g.out_stride = qd; g.B = B;
+      g.slots = eng->d_slots; g.pos = eng->d_pos; g.rope_cs = eng->rope_cs;
+      g.kv_base = kv_layer(eng, 0, l); g.kv_slot_stride = eng->kv_slot_stride; g.kv_v_offset = eng->kv_v_offset;
+      g.q_dim = qd; g.kv_dim = kd; g.max_len = c.max_len;
+      DTK_CK(launch_gemv(g, s, lc));
+    }
+    {
+      DecodeAttnArgs a{};
+      a.q = eng->d_q; a.q_stride = qd; a.kv_base = kv_layer(eng, 0, l); a.kv_slot_stride = eng->kv_slot_stride;
+      a.kv_v_offset = eng->kv_v_offset; a.slots = eng->d_slots; a.pos = eng->d_pos;
+      a.B = B; a.heads = c.heads; a.kv_group = c.heads / c.kv_heads; a.max_len = c.max_len; a.nsplit = nsplit;
+      a.scale = 1.0f / sqrtf(128.f);
+      a.part_o = eng->d_part_o; a.part_ml = eng->d_part_ml; a.counters = eng->d_counters;
+      a.out = eng->d_att; a.out_stride = qd;
+      DTK_CK(launch_decode_attn(a, s, lc));
+    }
+    {
+      GemvArgs g{};
+      g.mode = GEMV_ADD; g.W = W(eng, LN("dec.L", l, "wo")); g.N = H; g.K = qd;
+      g.x = eng->d_att; g.x_stride = qd; g.out = eng->d_x; g.out_stride = H; g.B = B;
+      DTK_CK(launch_gemv(g, s, lc));
+    }
+    {
+      GemvArgs g{};
+      g.mode = GEMV_GLU; g.W = W(eng, LN("dec.L", l, "wgu")); g.N = 2 * I; g.K = H;
+      g.x = eng->d_x; g.x_stride = H; g.norm_w = W(eng, LN("dec.L", l, "norm2")); g.eps = c.rms_eps;
+      g.out = eng->d_h; g.out_stride = I; g.B = B;
+      DTK_CK(launch_gemv(g, s, lc));
+    }
+    {
+      GemvArgs g{};
+      g.mode = GEMV_ADD; g.W = W(eng, LN("dec.L", l, "wd")); g.N = H; g.K = I;
+      g.x = eng->d_h; g.x_stride = I; g.out = eng->d_x; g.out_stride = H; g.B = B;
+      DTK_CK(launch_gemv(g, s, lc));
+    }
+  }
+  {
+    GemvArgs g{};
+    g.mode = GEMV_STORE; g.W = W(eng, "dec.lm_head"); g.N = c.vocab; g.K = H;
+    g.x = eng->d_x; g.x_stride = H; g.norm_w = W(eng, "dec.norm"); g.eps = c.rms_eps;
+    g.out = logits; g.out_stride = c.vocab; g.B = B;
+    DTK_CK(launch_gemv(g, s, lc));
+  }
+  return DTK_OK;
+}
+
+void fill_sample_args(dtk_engine* eng, SampleArgs& a, const float* logits, int B, const dtk_sampling& p) {
+  std::memset(&a, 0, sizeof(a));
+  a.logits = logits; a.B = B; a.V = eng->cfg.vocab;
+  a.temperature = (float)p.temperature; a.top_p = (float)p.top_p; a.top_p_limit = (float)(1.0 - p.top_p); a.top_k = p.top_k;
+  a.max_pos = eng->cfg.max_len - 1;
+  a.do_sample = (p.do_sample && p.temperature >= 1e-5) ? 1 : 0;
+  a.bad_token = p.bad_token; a.bs_token = p.begin_suppress_token; a.seed = p.seed;
+  a.scratch = eng->d_scratch;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int dtk_abi_version(void) { return DTK_ABI_VERSION; }
+
+int dtk_weight_count(const dtk_config* cfg) {
+  if (!cfg) return DTK_ERR_INVALID;
+  std::string why;
+  if (!config_ok(*cfg, why)) return DTK_ERR_INVALID;
+  return (int)build_table(*cfg).size();
+}
+
+int dtk_weight_get(const dtk_config* cfg, int index, dtk_weight_info* out) {
+  if (!cfg || !out) return DTK_ERR_INVALID;
+  std::string why;
+  if (!config_ok(*cfg, why)) return DTK_ERR_INVALID;
+  auto t = build_table(*cfg);
+  if (index < 0 || index >= (int)t.size()) return DTK_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  std::snprintf(out->name, sizeof(out->name), "%s", t[index].name.c_str());
+  out->offset = t[index].offset; out->nbytes = t[index].nbytes; out->rows = t[index].rows; out->cols = t[index].cols;
+  return DTK_OK;
+}
+
+uint64_t dtk_arena_bytes(const dtk_config* cfg) {
+  if (!cfg) return 0;
+  std::string why;
+  if (!config_ok(*cfg, why)) return 0;
+  auto t = build_table(*cfg);
+  return align_up(t.back().offset + t.back().nbytes, 256);
+}
+
+uint64_t dtk_decode_bytes(const dtk_config* c, int T) {
+  if (!c) return 0;
+  const uint64_t H = c->hidden, I = c->inter, V = c->vocab, qd = (uint64_t)c->heads * c->head_dim, kd = (uint64_t)c->kv_heads * c->head_dim;
+  uint64_t wbytes = 2 * ((uint64_t)c->layers * ((qd + 2 * kd) * H + H * qd + 3 * H * I) + V * H);
+  uint64_t kv = 2 * (uint64_t)c->layers * 2 * kd;  // bytes per cached position (K and V, bf16)
+  return wbytes + (uint64_t)T * kv;
+}
+
+int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_bytes, int device, dtk_engine** out) {
+  if (!cfg || !weight_arena || !out) return DTK_ERR_INVALID;
+  std::string why;
+  if (!config_ok(*cfg, why)) return DTK_ERR_INVALID;
+  if (arena_bytes < dtk_arena_bytes(cfg)) return DTK_ERR_INVALID;
+  dtk_engine* eng = new (std::nothrow) dtk_engine();
+  if (!eng) return DTK_ERR_OOM;
+  eng->cfg = *cfg;
+  eng->device = device;
+  *out = eng;  // returned even on failure so the caller can read dtk_last_error, then dtk_destroy
+  DTK_CK(cudaSetDevice(device));
+  eng->arena = (const uint8_t*)weight_arena;
+  for (auto& e : build_table(*cfg)) eng->w[e.name] = (const bf16*)(eng->arena + e.offset);
+
+  const dtk_config& c = eng->cfg;
+  const int64_t H = c.hidden, I = c.inter, V = c.vocab, qd = c.heads * 128, kd = c.kv_heads * 128, T = c.max_len, MB = c.max_batch;
+  eng->kv_v_offset = (int64_t)c.kv_heads * c.max_len * 128;
+  eng->kv_layer_stride = 2 * eng->kv_v_offset;
+  eng->kv_slot_stride = eng->kv_layer_stride * c.layers;
+  DTK_ALLOC(eng->kv, eng->kv_slot_stride * c.max_seqs);
+  eng->slot_used.assign(c.max_seqs, 0);
+
+  // RoPE table (HF modeling_llama.py:83-121: inv_freq = theta^(-2i/d) / factor, fp32; angle = pos * inv_freq)
+  {
+    std::vector<float> tab((size_t)T * 64 * 2);
+    for (int i = 0; i < 64; ++i) {
+      float inv = 1.0f / powf(c.rope_theta, (float)(2 * i) / 128.0f);
+      inv = inv / c.rope_factor;
+      for (int64_t p = 0; p < T; ++p) {
+        float ang = (float)p * inv;
+        tab[((size_t)p * 64 + i) * 2] = (float)cos((double)ang);
+        tab[((size_t)p * 64 + i) * 2 + 1] = (float)sin((double)ang);
+      }
+    }
+    DTK_ALLOC(eng->rope_cs, tab.size());
+    DTK_CK(cudaMemcpy(eng->rope_cs, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  DTK_ALLOC(eng->p_x, T * H);
+  DTK_ALLOC(eng->p_qkv, T * (qd + 2 * kd));
+  DTK_ALLOC(eng->p_xn, T * H);
+  DTK_ALLOC(eng->p_q, T * qd);
+  DTK_ALLOC(eng->p_att, T * qd);
+  DTK_ALLOC(eng->p_h, T * I);
+  DTK_ALLOC(eng->d_x, MB * H);
+  DTK_ALLOC(eng->d_q, MB * qd);
+  DTK_ALLOC(eng->d_att, MB * qd);
+  DTK_ALLOC(eng->d_h, MB * I);
+  DTK_ALLOC(eng->d_logits, MB * V);
+  DTK_ALLOC(eng->d_scratch, MB * V);
+  DTK_ALLOC(eng->d_part_o, MB * c.heads * 16 * 128);
+  DTK_ALLOC(eng->d_part_ml, MB * c.heads * 16 * 2);
+  DTK_ALLOC(eng->d_counters, MB * c.heads + 1);
+  DTK_CK(cudaMemset(eng->d_counters, 0, (MB * c.heads + 1) * sizeof(unsigned int)));
+  DTK_ALLOC(eng->d_slots, MB);
+  DTK_ALLOC(eng->d_pos, MB);
+  DTK_ALLOC(eng->d_tok, MB);
+  DTK_ALLOC(eng->d_gen, 2);
+  DTK_CK(cudaMemset(eng->d_gen, 0, 2 * sizeof(unsigned long long)));
+  DTK_ALLOC(eng->v_pq, c.v_hidden);
+  DTK_CK(cudaHostAlloc((void**)&eng->host_ring, (size_t)eng->ring * 64 * sizeof(int), cudaHostAllocMapped));
+  DTK_CK(cudaHostAlloc((void**)&eng->host_flag, sizeof(long long), cudaHostAllocMapped));
+  *eng->host_flag = 0;
+  DTK_CK(cudaHostGetDevicePointer((void**)&eng->dev_ring, eng->host_ring, 0));
+  DTK_CK(cudaHostGetDevicePointer((void**)&eng->dev_flag, eng->host_flag, 0));
+  DTK_CK(cudaDeviceSynchronize());
+  return DTK_OK;
+}
+
+int dtk_destroy(dtk_engine* eng) {
+  if (!eng) return DTK_ERR_INVALID;
+  cudaSetDevice(eng->device);
+  cudaDeviceSynchronize();
+  for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
+  void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
+                  eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (eng->host_ring) cudaFreeHost(eng->host_ring);
+  if (eng->host_flag) cudaFreeHost(eng->host_flag);
+  cudaGetLastError();
+  delete eng;
+  return DTK_OK;
+}
+
+const char* dtk_last_error(const dtk_engine* eng) { return eng ? eng->err.c_str() : "null engine"; }
+uint64_t dtk_launch_count(const dtk_engine* eng) { return eng ? eng->launches : 0; }
+
+int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_out, float* pooled_out, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(pixels && B > 0, "pixels/B");
+  DTK_CK(cudaSetDevice(eng->device));
+  const dtk_config& c = eng->cfg;
+  const int CH = 64;
+  int r = ensure_vit_ws(eng, B < CH ? B : CH);
+  if (r != DTK_OK) return r;
+  const int64_t pix_per = (int64_t)3 * c.v_image * c.v_image, N = v_tokens(c), D = c.v_hidden;
+  for (int b0 = 0; b0 < B; b0 += CH) {
+    int nb = B - b0 < CH ? B - b0 : CH;
+    r = vit_forward(eng, pixels + b0 * pix_per, nb, tokens_out ? tokens_out + b0 * N * D : nullptr,
+                    pooled_out ? pooled_out + (int64_t)b0 * D : nullptr, (cudaStream_t)stream);
+    if (r != DTK_OK) return r;
+  }
+  return DTK_OK;
+}
+
+int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(tokens && out && B > 0, "tokens/out/B");
+  DTK_CK(cudaSetDevice(eng->device));
+  const dtk_config& c = eng->cfg;
+  const int CH = 64;
+  int r = ensure_vit_ws(eng, B < CH ? B : CH);
+  if (r != DTK_OK) return r;
+  const int64_t per = (int64_t)v_tokens(c) * c.v_hidden;
+  for (int b0 = 0; b0 < B; b0 += CH) {
+    int nb = B - b0 < CH ? B - b0 : CH;
+    DTK_CK(launch_cast_f32_bf16(tokens + b0 * per, eng->v_xn, nb * per, (cudaStream_t)stream, &eng->launches));
+    r = project_bf16(eng, eng->v_xn, nb, out + (int64_t)b0 * img_tokens(c) * c.hidden, (cudaStream_t)stream);
+    if (r != DTK_OK) return r;
+  }
+  return DTK_OK;
+}
+
+int dtk_seq_alloc(dtk_engine* eng, int* slot) {
+  if (!eng || !slot) return DTK_ERR_INVALID;
+  for (size_t i = 0; i < eng->slot_used.size(); ++i)
+    if (!eng->slot_used[i]) {
+      eng->slot_used[i] = 1;
+      *slot = (int)i;
+      return DTK_OK;
+    }
+  eng->err = "no free KV sequence slot";
+  return DTK_ERR_NOSLOT;
+}
+
+int dtk_seq_free(dtk_engine* eng, int slot) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(slot >= 0 && slot < (int)eng->slot_used.size() && eng->slot_used[slot], "slot");
+  eng->slot_used[slot] = 0;
+  return DTK_OK;
+}
+
+int dtk_seq_fork(dtk_engine* eng, int src, int dst, int len, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  const dtk_config& c = eng->cfg;
+  DTK_REQUIRE(src >= 0 && src < c.max_seqs && dst >= 0 && dst < c.max_seqs && src != dst, "slots");
+  DTK_REQUIRE(len >= 0 && len <= c.max_len, "len");
+  if (len == 0) return DTK_OK;
+  DTK_CK(cudaSetDevice(eng->device));
+  // rows = layers * 2 * kv_heads segments of [max_len, 128]; copy the first len positions of each
+  const size_t pitch = (size_t)c.max_len * 128 * sizeof(bf16);
+  DTK_CK(cudaMemcpy2DAsync(kv_layer(eng, dst, 0), pitch, kv_layer(eng, src, 0), pitch, (size_t)len * 128 * sizeof(bf16),
+                           (size_t)c.layers * 2 * c.kv_heads, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return DTK_OK;
+}
+
+int dtk_prefill(dtk_engine* eng, int slot, const int64_t* ids, int T, int start_pos, const float* img_embeds,
+                int img_start, int n_img, float* last_logits, float* all_logits, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  const dtk_config& c = eng->cfg;
+  DTK_REQUIRE(ids && T > 0, "ids/T");
+  DTK_REQUIRE(slot >= 0 && slot < c.max_seqs, "slot");
+  DTK_REQUIRE(start_pos >= 0 && start_pos + T <= c.max_len, "start_pos + T exceeds max_len");
+  DTK_CK(cudaSetDevice(eng->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint64_t* lc = &eng->launches;
+  const int H = c.hidden, I = c.inter, qd = c.heads * 128, kd = c.kv_heads * 128;
+  DTK_CK(launch_embed_splice(ids, T, start_pos, W(eng, "dec.embed"), H, c.vocab, c.image_token_id, img_embeds, img_start,
+                             n_img, eng->p_x, s, lc));
+  for (int l = 0; l < c.layers; ++l) {
+    DTK_CK(launch_rmsnorm(eng->p_x, H, W(eng, LN("dec.L", l, "norm1")), c.rms_eps, T, H, eng->p_xn, s, lc));
+    {
+      GemmArgs g{};
+      g.A = eng->p_xn; g.lda = H; g.W = W(eng, LN("dec.L", l, "wqkv")); g.ldw = H; g.M = T; g.N = qd + 2 * kd; g.K = H;
+      g.out_f32 = eng->p_qkv; g.ldo = qd + 2 * kd;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    bf16* kc = kv_layer(eng, slot, l);
+    bf16* vc = kc + eng->kv_v_offset;
+    DTK_CK(launch_rope_kv_prefill(eng->p_qkv, T, start_pos, c.heads, c.kv_heads, eng->rope_cs, eng->p_q, kc, vc, c.max_len, s, lc));
+    {
+      AttnArgs a{};
+      a.q = eng->p_q; a.k = kc; a.v = vc; a.o = eng->p_att;
+      a.q_bs = 0; a.q_hs = 128; a.q_rs = qd;
+      a.k_bs = 0; a.k_hs = (int64_t)c.max_len * 128; a.k_rs = 128;
+      a.v_bs = 0; a.v_hs = (int64_t)c.max_len * 128; a.v_rs = 128;
+      a.o_bs = 0; a.o_hs = 128; a.o_rs = qd;
+      a.B = 1; a.heads = c.heads; a.kv_group = c.heads / c.kv_heads; a.Tq = T; a.Tk = start_pos + T; a.q_pos0 = start_pos;
+      a.causal = 1; a.head_dim = 128; a.scale = 1.0f / sqrtf(128.f);
+      DTK_CK(launch_flash_attn(a, s, lc));
+    }
+    {
+      GemmArgs g{};
+      g.A = eng->p_att; g.lda = qd; g.W = W(eng, LN("dec.L", l, "wo")); g.ldw = qd; g.M = T; g.N = H; g.K = qd;
+      g.resid = eng->p_x; g.ldr = H; g.out_f32 = eng->p_x; g.ldo = H;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    DTK_CK(launch_rmsnorm(eng->p_x, H, W(eng, LN("dec.L", l, "norm2")), c.rms_eps, T, H, eng->p_xn, s, lc));
+    {
+      GemmArgs g{};
+      g.A = eng->p_xn; g.lda = H; g.W = W(eng, LN("dec.L", l, "wgu")); g.ldw = H; g.M = T; g.N = 2 * I; g.K = H;
+      g.glu = 1; g.out_bf16 = eng->p_h; g.ldo = I;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+    {
+      GemmArgs g{};
+      g.A = eng->p_h; g.lda = I; g.W = W(eng, LN("dec.L", l, "wd")); g.ldw = I; g.M = T; g.N = H; g.K = I;
+      g.resid = eng->p_x; g.ldr = H; g.out_f32 = eng->p_x; g.ldo = H;
+      DTK_CK(launch_gemm(g, s, lc));
+    }
+  }
+  if (last_logits) {  // final RMSNorm + lm_head on the last row only (reference computes all T rows, v1/modeling:251-257)
+    GemvArgs g{};
+    g.mode = GEMV_STORE; g.W = W(eng, "dec.lm_head"); g.N = c.vocab; g.K = H;
+    g.x = eng->p_x + (int64_t)(T - 1) * H; g.x_stride = H; g.norm_w = W(eng, "dec.norm"); g.eps = c.rms_eps;
+    g.out = last_logits; g.out_stride = c.vocab; g.B = 1;
+    DTK_CK(launch_gemv(g, s, lc));
+  }
+  if (all_logits) {
+    DTK_CK(launch_rmsnorm(eng->p_x, H, W(eng, "dec.norm"), c.rms_eps, T, H, eng->p_xn, s, lc));
+    GemmArgs g{};
+    g.A = eng->p_xn; g.lda = H; g.W = W(eng, "dec.lm_head"); g.ldw = H; g.M = T; g.N = c.vocab; g.K = H;
+    g.out_f32 = all_logits; g.ldo = c.vocab;
+    DTK_CK(launch_gemm(g, s, lc));
+  }
+  return DTK_OK;
+}
+
+int dtk_decode(dtk_engine* eng, const int* slots, const int* positions, const int64_t* ids, int B, float* logits,
+               void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  const dtk_config& c = eng->cfg;
+  DTK_REQUIRE(slots && positions && ids && logits, "null pointer");
+  DTK_REQUIRE(B > 0 && B <= c.max_batch, "B exceeds max_batch");
+  StateArgs st{};
+  st.n = B;
+  for (int i = 0; i < B; ++i) {
+    DTK_REQUIRE(slots[i] >= 0 && slots[i] < c.max_seqs, "slot");
+    DTK_REQUIRE(positions[i] >= 0 && positions[i] < c.max_len, "position exceeds max_len");
+    st.slots[i] = slots[i];
+    st.pos[i] = positions[i];
+  }
+  DTK_CK(cudaSetDevice(eng->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok);
+  ++eng->launches;
+  DTK_CK(cudaGetLastError());
+  return decode_launches(eng, B, ids, logits, s);
+}
+
+int dtk_sample(dtk_engine* eng, const float* logits, int B, const dtk_sampling* params, const int* suppress,
+               const uint32_t* steps, const uint32_t* seq_ids, int64_t* out_ids, float* probs_out, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(logits && params && B > 0 && B <= eng->cfg.max_batch, "logits/params/B");
+  DTK_CK(cudaSetDevice(eng->device));
+  SampleArgs a;
+  fill_sample_args(eng, a, logits, B, *params);
+  if (probs_out) a.scratch = probs_out;
+  a.out_ids = out_ids;
+  for (int i = 0; i < B; ++i) {
+    a.seq[i].suppress = suppress ? suppress[i] : 0;
+    a.seq[i].step = steps ? steps[i] : 0;
+    a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i;
+  }
+  DTK_CK(launch_sample(a, (cudaStream_t)stream, &eng->launches));
+  return DTK_OK;
+}
+
+int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const int64_t* first_ids_host, int B,
+                  const dtk_sampling* params, const uint32_t* seq_ids, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  const dtk_config& c = eng->cfg;
+  DTK_REQUIRE(slots && positions && first_ids_host && params, "null pointer");
+  DTK_REQUIRE(B > 0 && B <= c.max_batch, "B exceeds max_batch");
+  DTK_CK(cudaSetDevice(eng->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  StateArgs st{};
+  st.n = B; st.have_tok = 1;
+  for (int i = 0; i < B; ++i) {
+    DTK_REQUIRE(slots[i] >= 0 && slots[i] < c.max_seqs, "slot");
+    DTK_REQUIRE(positions[i] >= 0 && positions[i] < c.max_len, "position exceeds max_len");
+    st.slots[i] = slots[i]; st.pos[i] = positions[i]; st.tok[i] = first_ids_host[i];
+  }
+  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok);
+  reset_gen_kernel<<<1, 1, 0, s>>>(eng->d_gen, eng->d_counters + (int64_t)c.max_batch * c.heads);
+  eng->launches += 2;
+  DTK_CK(cudaGetLastError());
+  DTK_CK(cudaStreamSynchronize(s));
+  *eng->host_flag = 0;
+
+  // graph key: everything baked into kernel arguments
+  char key[256];
+  std::snprintf(key, sizeof(key), "B%d|t%.9g|p%.17g|k%d|s%d|b%d|e%d|seed%llu", B, (double)params->temperature,
+                (double)params->top_p, params->top_k, params->do_sample, params->bad_token, params->begin_suppress_token,
+                (unsigned long long)params->seed);
+  std::string skey(key);
+  if (seq_ids) for (int i = 0; i < B; ++i) skey += "," + std::to_string(seq_ids[i]);
+  auto it = eng->graphs.find(skey);
+  if (it == eng->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    uint64_t before = eng->launches;
+    DTK_CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int r = decode_launches(eng, B, nullptr, eng->d_logits, s);
+    if (r == DTK_OK) {
+      SampleArgs a;
+      fill_sample_args(eng, a, eng->d_logits, B, *params);
+      for (int i = 0; i < B; ++i) { a.seq[i].suppress = 0; a.seq[i].step = 1; a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i; }
+      a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
+      a.host_ring = eng->dev_ring; a.host_flag = eng->dev_flag; a.ring = eng->ring;
+      a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
+      cudaError_t e = launch_sample(a, s, &eng->launches);
+      if (e != cudaSuccess) { eng->err = std::string("launch_sample: ") + cudaGetErrorString(e); r = DTK_ERR_CUDA; }
+    }
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    eng->launches = before;  // captured launches are counted per replay
+    if (r != DTK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess) { eng->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return DTK_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    DTK_CK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (eng->graphs.size() >= 64) {  // bound the cache
+      for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
+      eng->graphs.clear();
+    }
+    it = eng->graphs.emplace(skey, exec).first;
+  }
+  eng->gen_graph = it->second;
+  eng->gen_B = B;
+  eng->gen_params = *params;
+  eng->gen_stream = s;
+  return DTK_OK;
+}
+
+int dtk_gen_step(dtk_engine* eng, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->gen_graph != nullptr, "dtk_gen_begin not called");
+  DTK_CK(cudaGraphLaunch(eng->gen_graph, (cudaStream_t)stream));
+  eng->launches += (uint64_t)eng->cfg.layers * 5 + 3;
+  return DTK_OK;
+}
+
+int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->gen_graph != nullptr && step >= 0 && tokens_out_host, "gen state/step/out");
+  volatile long long* flag = eng->host_flag;
+  auto t0 = std::chrono::steady_clock::now();
+  uint64_t spins = 0;
+  while (*flag < step + 1) {
+    if ((++spins & 0x3ff) == 0) {
+      cudaError_t q = cudaStreamQuery(eng->gen_stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        eng->err = std::string("stream error while waiting for token: ") + cudaGetErrorString(q);
+        return DTK_ERR_CUDA;
+      }
+      if (q == cudaSuccess && *flag < step + 1) {
+        eng->err = "stream idle but requested step was never launched";
+        return DTK_ERR_INVALID;
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+        eng->err = "timeout waiting for generated token";
+        return DTK_ERR_CUDA;
+      }
+    }
+  }
+  const int* row = eng->host_ring + (size_t)(step % eng->ring) * eng->gen_B;
+  for (int i = 0; i < eng->gen_B; ++i) tokens_out_host[i] = ((volatile const int*)row)[i];
+  return DTK_OK;
+}
+
+int dtk_gen_end(dtk_engine* eng) {
+  if (!eng) return DTK_ERR_INVALID;
+  if (eng->gen_stream || eng->gen_graph) {
+    DTK_CK(cudaSetDevice(eng->device));
+    DTK_CK(cudaStreamSynchronize(eng->gen_stream));
+  }
+  eng->gen_graph = nullptr;
+  eng->gen_B = 0;
+  return DTK_OK;
+}
+
+// ---- kernel-level test hooks ---------------------------------------------------------------
+int dtk_dbg_gemm(const void* A, const void* Wm, const void* bias, const float* resid, int M, int N, int K, int act,
+                 int glu, float* out_f32, void* out_bf16, void* stream) {
+  GemmArgs g{};
+  g.A = (const bf16*)A; g.lda = K; g.W = (const bf16*)Wm; g.ldw = K; g.M = M; g.N = N; g.K = K;
+  g.bias = (const bf16*)bias; g.resid = resid; g.ldr = glu ? N / 2 : N; g.act = act; g.glu = glu;
+  g.out_f32 = out_f32; g.out_bf16 = (bf16*)out_bf16; g.ldo = glu ? N / 2 : N;
+  return launch_gemm(g, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+}
+
+int dtk_dbg_flash_attn(const void* q, const void* k, const void* v, void* o, int B, int heads, int Tq, int Tk,
+                       int head_dim, int causal, int q_pos0, float scale, void* stream) {
+  AttnArgs a{};
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.o = (bf16*)o;
+  const int64_t rs = (int64_t)heads * head_dim;
+  a.q_bs = (int64_t)Tq * rs; a.q_hs = head_dim; a.q_rs = rs;
+  a.k_bs = (int64_t)Tk * rs; a.k_hs = head_dim; a.k_rs = rs;
+  a.v_bs = (int64_t)Tk * rs; a.v_hs = head_dim; a.v_rs = rs;
+  a.o_bs = (int64_t)Tq * rs; a.o_hs = head_dim; a.o_rs = rs;
+  a.B = B; a.heads = heads; a.kv_group = 1; a.Tq = Tq; a.Tk = Tk; a.q_pos0 = q_pos0; a.causal = causal;
+  a.head_dim = head_dim; a.scale = scale;
+  return launch_flash_attn(a, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+}
+
+int dtk_dbg_gemv(const void* Wm, const float* x, const void* norm_w, float eps, int N, int K, int mode, float* out,
+                 void* stream) {
+  if (mode < 0 || mode > 2) return DTK_ERR_INVALID;
+  GemvArgs g{};
+  g.mode = mode; g.W = (const bf16*)Wm; g.N = N; g.K = K; g.x = x; g.x_stride = K; g.norm_w = (const bf16*)norm_w;
+  g.eps = eps; g.out = out; g.out_stride = N; g.B = 1;
+  return launch_gemv(g, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+}
+
+}  // extern "C"

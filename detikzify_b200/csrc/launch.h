@@ -1,0 +1,152 @@
+// Host-side launcher declarations (one per kernel family). Each launcher returns the CUDA error
+// of the launch and bumps *counter (kernel launches issued; bench.py's gpu_launches).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+namespace dtk {
+
+// ---------------------------------------------------------------- dense GEMM  C = A * W^T
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
+
+struct GemmArgs {
+  const bf16* A;              // [M, K] bf16, row stride lda (elements)
+  int64_t lda;
+  int a_rows_per_batch;       // 0 = plain; else row m lives at A + (m / rpb) * a_batch_stride + (m % rpb) * lda
+  int64_t a_batch_stride;
+  const bf16* W;              // [N, K] bf16 row-major (K contiguous), row stride ldw
+  int64_t ldw;
+  int M, N, K;                // K % 8 == 0, N % 2 == 0
+  // epilogue: v = acc (+bias[n]) ; v = act(v) ; (+ rowbias[m % rowbias_mod, n]) ; (+ resid[m, n])
+  const bf16* bias;           // [N] or null
+  const bf16* rowbias;        // [rowbias_mod, N] or null (ViT position embedding)
+  int rowbias_mod;
+  const float* resid;         // fp32 [M, ldr] or null (may alias out_f32)
+  int64_t ldr;
+  int act;
+  int glu;                    // 1: columns come in (gate, up) pairs -> out[m, n/2] = silu(gate) * up
+  float* out_f32;             // exactly one of out_f32 / out_bf16 is non-null
+  bf16* out_bf16;
+  int64_t ldo;
+};
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
+
+// ---------------------------------------------------------------- flash attention (mma.sync)
+struct AttnArgs {
+  const bf16 *q, *k, *v;
+  bf16* o;
+  int64_t q_bs, q_hs, q_rs;   // batch / head / row strides in elements
+  int64_t k_bs, k_hs, k_rs;
+  int64_t v_bs, v_hs, v_rs;
+  int64_t o_bs, o_hs, o_rs;
+  int B, heads, kv_group;     // kv head = head / kv_group
+  int Tq, Tk;
+  int q_pos0;                 // causal: query i sits at position q_pos0 + i; key j visible iff j <= pos
+  int causal;
+  int head_dim;               // 72 or 128
+  float scale;
+};
+cudaError_t launch_flash_attn(const AttnArgs& a, cudaStream_t s, uint64_t* counter);
+
+// ---------------------------------------------------------------- row-wise / elementwise
+// y = LN(x) * w + b  (fp32 stats); x fp32 [M, D]; writes bf16 and/or fp32 outputs
+cudaError_t launch_layernorm(const float* x, const bf16* w, const bf16* b, float eps, int M, int D,
+                             bf16* out_bf16, float* out_f32, cudaStream_t s, uint64_t* counter);
+// y = x * rsqrt(mean(x^2)+eps) * w ; x fp32 [M, D] row stride ldx; out bf16 [M, D]
+cudaError_t launch_rmsnorm(const float* x, int64_t ldx, const bf16* w, float eps, int M, int D, bf16* out,
+                           cudaStream_t s, uint64_t* counter);
+// pixels fp32 [B,3,S,S] -> patches bf16 [B*N, KP] (channel-major (c, py, px) like conv weight; zero pad)
+cudaError_t launch_im2col(const float* pixels, int B, int S, int P, int KP, bf16* out, cudaStream_t s,
+                          uint64_t* counter);
+cudaError_t launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s, uint64_t* counter);
+// x[t, :] = ids[t] == image_token ? img[(start_pos + t) - img_start, :] : embed[ids[t], :]
+cudaError_t launch_embed_splice(const int64_t* ids, int T, int start_pos, const bf16* embed, int H, int vocab,
+                                int image_token, const float* img, int img_start, int n_img, float* x,
+                                cudaStream_t s, uint64_t* counter);
+// prefill: qkv fp32 [T, qd+2kd] -> roped q bf16 [T, qd]; K/V bf16 into the cache at positions start_pos+t
+cudaError_t launch_rope_kv_prefill(const float* qkv, int T, int start_pos, int heads, int kv_heads,
+                                   const float* rope_cs, bf16* q_out, bf16* kcache, bf16* vcache,
+                                   int max_len, cudaStream_t s, uint64_t* counter);
+
+// ---------------------------------------------------------------- decode (batch of single tokens)
+enum { GEMV_STORE = 0, GEMV_ADD = 1, GEMV_GLU = 2, GEMV_QKV = 3 };
+struct GemvArgs {
+  int mode;
+  const bf16* W;              // [N, K]
+  int N, K;
+  const float* x;             // [B, x_stride] fp32
+  int64_t x_stride;
+  const bf16* norm_w;         // fused RMSNorm on x (null = none)
+  float eps;
+  float* out;                 // STORE/ADD: [B, out_stride]; GLU: [B, out_stride] (N/2 valid); QKV: q [B, out_stride]
+  int64_t out_stride;
+  int B;
+  // QKV mode
+  const int* slots;           // device int[B]
+  const int* pos;             // device int[B] : position of the token being processed
+  const float* rope_cs;       // fp32 [max_len, 64, 2] (cos, sin)
+  bf16* kv_base;              // cache base of this layer for slot 0: K then V
+  int64_t kv_slot_stride;     // elements between slots
+  int64_t kv_v_offset;        // elements from K to V of the same layer
+  int q_dim, kv_dim, max_len;
+};
+cudaError_t launch_gemv(const GemvArgs& a, cudaStream_t s, uint64_t* counter);
+
+// x[b, :] = embed[tok[b], :]  (fp32 out)
+cudaError_t launch_embed_tokens(const int* tok32, const int64_t* tok64, int B, const bf16* embed, int H,
+                                int vocab, float* x, cudaStream_t s, uint64_t* counter);
+
+struct DecodeAttnArgs {
+  const float* q;             // [B, q_dim] fp32 (roped)
+  int64_t q_stride;
+  const bf16* kv_base;        // layer base for slot 0
+  int64_t kv_slot_stride, kv_v_offset;
+  const int* slots;           // device int[B]
+  const int* pos;             // device int[B]; keys [0, pos] are attended
+  int B, heads, kv_group, max_len, nsplit;
+  float scale;
+  float* part_o;              // [B, heads, nsplit, 128]
+  float* part_ml;             // [B, heads, nsplit, 2]
+  unsigned int* counters;     // [B * heads], zero-initialised, self-resetting
+  float* out;                 // [B, q_dim] fp32
+  int64_t out_stride;
+};
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t s, uint64_t* counter);
+
+struct SampleSeq {
+  int suppress;
+  uint32_t step;
+  uint32_t seq_id;
+};
+struct SampleArgs {
+  const float* logits;        // [B, V]
+  int B, V;
+  float temperature, top_p;
+  float top_p_limit;              // (float)(1.0 - top_p): ascending cumulative mass <= limit is removed
+  int top_k, do_sample, bad_token, bs_token;
+  uint64_t seed;
+  float* scratch;             // [B, V] fp32 work buffer (receives the final probability vector)
+  int64_t* out_ids;           // device int64[B] or null
+  // generation-loop state (all optional, device): when gen_tok != null the sampler also advances
+  // the loop: gen_tok[b] = token, gen_pos[b] += 1, and publishes the token to the pinned host ring.
+  int* gen_tok;
+  int* gen_pos;
+  unsigned long long* gen_step;   // single counter (device); RNG counter + ring row
+  int* host_ring;                 // mapped pinned int32 [ring, B]
+  volatile long long* host_flag;  // mapped pinned: last published step + 1
+  int ring;
+  int max_pos;                    // gen_pos is clamped to this (max_len - 1)
+  unsigned int* done_counter;     // device, zero-initialised, self-resetting
+  SampleSeq seq[64];
+};
+cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s, uint64_t* counter);
+
+// single-query attention of the SigLIP attention-pool head: q fp32 [heads*72] (shared by all images),
+// kv bf16 [B*N, 2*D] -> out bf16 [B, D]
+cudaError_t launch_pool_attn(const float* q, const bf16* kv, int B, int N, int D, int heads, float scale,
+                             bf16* out, cudaStream_t s, uint64_t* counter);
+
+}  // namespace dtk

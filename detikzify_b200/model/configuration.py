@@ -1,0 +1,132 @@
+"""
+Plain configuration objects for the B200 engine (no HF dependency).
+
+Mirrors the attribute names the reference's callers read:
+  * ``config.image_token_id`` / ``config.patch_token_id`` and ``config.pooling_mode``
+    (reference: detikzify/model/v1/configuration_detikzify.py:3-13),
+  * ``config.text_config.eos_token_id`` (read at detikzify/infer/generate.py:221 for every
+    model although the v1 config is flat -> ``text_config`` is an alias to ``self``),
+  * ``config.vision_config.image_size`` (examples/refine.py:174),
+  * ``config.num_patches`` / ``concat_patches`` / ``feature_layer`` / ``mm_hidden_size``
+    (detikzify/model/v1/modeling_detikzify.py:98-107).
+
+Decoder dims of the named checkpoints are the public DeepSeek-Coder base configs
+(SURVEY.md Appendix A); they are config input, not reference source.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, asdict
+from typing import Any, Dict
+
+
+@dataclass
+class VisionConfig:
+    hidden_size: int = 1152
+    intermediate_size: int = 4304
+    num_hidden_layers: int = 27
+    num_attention_heads: int = 16
+    image_size: int = 384
+    patch_size: int = 14
+    num_channels: int = 3
+    layer_norm_eps: float = 1e-6
+    hidden_act: str = "gelu_pytorch_tanh"  # or "gelu" (exact erf); SURVEY §8c open parameter
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+    @property
+    def num_positions(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+
+@dataclass
+class DetikzifyConfig:
+    # decoder (LLaMA)
+    hidden_size: int = 2048
+    intermediate_size: int = 5504
+    num_hidden_layers: int = 24
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 16
+    head_dim: int = 128
+    vocab_size: int = 32256
+    max_position_embeddings: int = 16384
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 100000.0
+    rope_factor: float = 4.0  # linear scaling (DeepSeek-Coder)
+    model_max_length: int = 2048  # v1 tokenizer limit, detikzify/model/v1/__init__.py:28
+    # special tokens (v1: patch token := tokenizer BOS, v1/__init__.py:49)
+    bos_token_id: int = 32013
+    eos_token_id: int = 32014
+    pad_token_id: int = 32018
+    patch_token_id: int = 32013
+    # glue
+    concat_patches: int = 3
+    feature_layer: int = -1
+    projector_bias: bool = True  # v1: nn.Linear with bias (v1/modeling_detikzify.py:82)
+    model_type: str = "detikzify"
+    name_or_path: str = ""
+    vision_config: VisionConfig = field(default_factory=VisionConfig)
+
+    # --- attribute aliases the reference's callers use -------------------------------------
+    @property
+    def image_token_id(self) -> int:
+        return self.patch_token_id
+
+    @property
+    def pooling_mode(self) -> str:
+        return "cos"
+
+    @property
+    def text_config(self) -> "DetikzifyConfig":
+        return self
+
+    @property
+    def num_patches(self) -> int:
+        """image tokens fed to the decoder (243 @384px)."""
+        return self.vision_config.num_positions // self.concat_patches
+
+    @property
+    def mm_hidden_size(self) -> int:
+        return self.vision_config.hidden_size * self.concat_patches
+
+    @property
+    def use_mm_proj(self) -> bool:
+        return True
+
+    def to_dict(self) -> Dict[str, Any]:
+        d = asdict(self)
+        d["image_token_id"] = self.image_token_id
+        d["num_patches"] = self.num_patches
+        return d
+
+
+def preset(name: str) -> DetikzifyConfig:
+    """Named checkpoint shapes. ``tiny``/``tiny2`` are test shapes (ragged on purpose:
+    16 patches -> 5 image tokens drops the first patch, K=176 is not a multiple of 32)."""
+    key = name.split("/")[-1].lower()
+    if key in ("detikzify-ds-1.3b", "ds-1.3b"):
+        return DetikzifyConfig(name_or_path=name)
+    if key in ("detikzify-ds-7b", "ds-7b"):
+        return DetikzifyConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                               num_attention_heads=32, num_key_value_heads=32, name_or_path=name)
+    if key == "tiny":
+        return DetikzifyConfig(
+            hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,
+            num_key_value_heads=2, vocab_size=512, model_max_length=96,
+            bos_token_id=500, eos_token_id=501, pad_token_id=502, patch_token_id=500,
+            name_or_path=name,
+            vision_config=VisionConfig(hidden_size=144, intermediate_size=176, num_hidden_layers=2,
+                                       num_attention_heads=2, image_size=56, patch_size=14))
+    if key == "tiny2":  # more layers/heads, 3x3 patches
+        return DetikzifyConfig(
+            hidden_size=384, intermediate_size=1040, num_hidden_layers=3, num_attention_heads=3,
+            num_key_value_heads=3, vocab_size=1000, model_max_length=160,
+            bos_token_id=990, eos_token_id=991, pad_token_id=992, patch_token_id=990,
+            name_or_path=name,
+            vision_config=VisionConfig(hidden_size=216, intermediate_size=400, num_hidden_layers=3,
+                                       num_attention_heads=3, image_size=126, patch_size=14))
+    raise KeyError(f"unknown model preset {name!r}")
