@@ -134,6 +134,7 @@ struct dtk_engine {
   std::map<std::string, cudaGraphExec_t> graphs;
   cudaGraphExec_t gen_graph = nullptr;
   cudaStream_t gen_stream = nullptr;
+  cudaStream_t cap_stream = nullptr;  // engine-owned: graph capture never touches the caller's stream
 };
 
 namespace {
@@ -525,6 +526,7 @@ int dtk_destroy(dtk_engine* eng) {
                   eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
   if (eng->host_ring) cudaFreeHost(eng->host_ring);
   if (eng->host_flag) cudaFreeHost(eng->host_flag);
   cudaGetLastError();
@@ -749,8 +751,10 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
   if (it == eng->graphs.end()) {
     cudaGraph_t graph = nullptr;
     uint64_t before = eng->launches;
-    DTK_CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int r = decode_launches(eng, B, nullptr, eng->d_logits, s);
+    if (!eng->cap_stream) DTK_CK(cudaStreamCreateWithFlags(&eng->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = eng->cap_stream;
+    DTK_CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int r = decode_launches(eng, B, nullptr, eng->d_logits, cs);
     if (r == DTK_OK) {
       SampleArgs a;
       fill_sample_args(eng, a, eng->d_logits, B, *params);
@@ -758,10 +762,10 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
       a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
       a.host_ring = eng->dev_ring; a.host_flag = eng->dev_flag; a.ring = eng->ring;
       a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
-      cudaError_t e = launch_sample(a, s, &eng->launches);
+      cudaError_t e = launch_sample(a, cs, &eng->launches);
       if (e != cudaSuccess) { eng->err = std::string("launch_sample: ") + cudaGetErrorString(e); r = DTK_ERR_CUDA; }
     }
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     eng->launches = before;  // captured launches are counted per replay
     if (r != DTK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (ce != cudaSuccess) { eng->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return DTK_ERR_CUDA; }

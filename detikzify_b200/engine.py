@@ -6,13 +6,14 @@ of every call, so the streamer/consumer thread of the reference's MCTS driver ke
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import TYPE_CHECKING, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
 from ._lib import DtkConfig, DtkSampling, DtkWeightInfo
-from .model.configuration import DetikzifyConfig
+if TYPE_CHECKING:  # avoid a package-level import cycle (model/ imports this module)
+    from .model.configuration import DetikzifyConfig
 
 V = "model.vision_model.vision_model."
 
@@ -21,7 +22,7 @@ class EngineError(RuntimeError):
     pass
 
 
-def to_c_config(cfg: DetikzifyConfig, max_seqs: int = 4, max_batch: int = 1, max_len: Optional[int] = None) -> DtkConfig:
+def to_c_config(cfg: "DetikzifyConfig", max_seqs: int = 4, max_batch: int = 1, max_len: Optional[int] = None) -> DtkConfig:
     vc = cfg.vision_config
     act = {"gelu_pytorch_tanh": 0, "gelu_tanh": 0, "gelu": 1, "gelu_erf": 1}[vc.hidden_act]
     return DtkConfig(
@@ -49,7 +50,7 @@ def weight_table(ccfg: DtkConfig) -> List[DtkWeightInfo]:
     return out
 
 
-def _arena_source(name: str, sd: Dict[str, torch.Tensor], cfg: DetikzifyConfig, cols: int) -> torch.Tensor:
+def _arena_source(name: str, sd: Dict[str, torch.Tensor], cfg: "DetikzifyConfig", cols: int) -> torch.Tensor:
     """Arena tensor ``name`` as a function of the canonical (HF-named) state dict."""
     parts = name.split(".")
     if name == "dec.embed":
@@ -126,7 +127,7 @@ def _arena_source(name: str, sd: Dict[str, torch.Tensor], cfg: DetikzifyConfig, 
     raise KeyError(name)
 
 
-def pack_arena(cfg: DetikzifyConfig, sd: Dict[str, torch.Tensor], ccfg: Optional[DtkConfig] = None) -> torch.Tensor:
+def pack_arena(cfg: "DetikzifyConfig", sd: Dict[str, torch.Tensor], ccfg: Optional[DtkConfig] = None) -> torch.Tensor:
     """Pack the canonical state dict into one contiguous bf16 arena (CPU uint8 tensor)."""
     lib = _lib.load_library()
     ccfg = ccfg or to_c_config(cfg)
@@ -146,7 +147,7 @@ def pack_arena(cfg: DetikzifyConfig, sd: Dict[str, torch.Tensor], ccfg: Optional
 class Engine:
     """One engine per CUDA device. Not thread-safe: one generation thread at a time."""
 
-    def __init__(self, cfg: DetikzifyConfig, arena: torch.Tensor, device: torch.device | int | str = 0,
+    def __init__(self, cfg: "DetikzifyConfig", arena: torch.Tensor, device: torch.device | int | str = 0,
                  max_seqs: int = 4, max_batch: int = 1, max_len: Optional[int] = None):
         if not torch.cuda.is_available():
             raise EngineError("detikzify_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

@@ -1,0 +1,245 @@
+"""
+Model object with the reference's duck-typed surface, backed by the C-ABI engine.
+
+Replaces detikzify/model/v1/modeling_detikzify.py (DetikzifyVisionModel :49-72, DetikzifyModel
+:75-200, DetikzifyForCausalLM :203-305) *and* the HF ``GenerationMixin.generate/_sample`` loop the
+reference drives at detikzify/infer/generate.py:218-227. What callers rely on:
+
+  model.generate(input_ids=[1,T0], bad_words_ids=[[id]], begin_suppress_tokens=[id], pixel_values=...,
+                 streamer=..., stopping_criteria=[...], temperature, top_p, top_k, max_length,
+                 do_sample, **ignored) -> LongTensor [1,T]          (infer/generate.py:218-227)
+  model.device / model.dtype / model.name_or_path / model.config.* / model.generation_config
+  model.model.vision_model(pixel_values=...) -> .last_hidden_state, .pooler_output
+                                                               (evaluate/imagesim.py:87,101-107)
+
+Beyond the reference (results unchanged): the ViT+projector output is cached per pixel tensor and the
+KV cache of the working slot is reused across calls for the longest common token prefix, so an MCTS
+expansion prefills only the tree-path suffix instead of re-encoding the image and re-prefilling
+243 + len(prefix) tokens on every rollout (reference quirk).
+"""
+from __future__ import annotations
+
+import threading
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from ..engine import Engine, EngineError, pack_arena
+from ..util.generation import StoppingCriteriaList
+from .configuration import DetikzifyConfig
+
+
+class GenerationConfig:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def to_dict(self) -> Dict[str, Any]:
+        return dict(self.__dict__)
+
+
+class VisionOutput(SimpleNamespace):
+    pass
+
+
+class DetikzifyVisionModel:
+    """``model.model.vision_model`` — callable like the reference's wrapper (v1/modeling:63-69)."""
+
+    def __init__(self, owner: "DetikzifyForCausalLM"):
+        self._owner = owner
+        self.config = owner.config.vision_config
+
+    def __call__(self, pixel_values: torch.Tensor, **_) -> VisionOutput:
+        return self.forward(pixel_values)
+
+    def forward(self, pixel_values: torch.Tensor) -> VisionOutput:
+        o = self._owner
+        with o._lock, torch.cuda.stream(o._stream):
+            tokens, pooled = o.engine.vit_encode(pixel_values)
+            o._stream.synchronize()
+        return VisionOutput(last_hidden_state=tokens.to(o.dtype), pooler_output=pooled.to(o.dtype))
+
+    def get_intermediate_layers(self, pixel_values: torch.Tensor, n=None, norm: bool = True, **_):
+        """Only the configuration the reference uses: last layer, final norm applied
+        (v1/modeling_detikzify.py:134 with feature_layer=-1)."""
+        return [self.forward(pixel_values).last_hidden_state]
+
+
+class _Inner:
+    """``model.model`` namespace (reference: DetikzifyModel)."""
+
+    def __init__(self, owner):
+        self.vision_model = DetikzifyVisionModel(owner)
+
+
+class DetikzifyForCausalLM:
+    def __init__(self, config: DetikzifyConfig, arena: torch.Tensor, device=0, dtype=torch.bfloat16,
+                 max_seqs: int = 2, max_batch: int = 1, max_len: Optional[int] = None):
+        self.config = config
+        self.dtype = dtype
+        self.name_or_path = config.name_or_path
+        self.engine = Engine(config, arena, device=device, max_seqs=max_seqs, max_batch=max_batch, max_len=max_len)
+        self.device = self.engine.device
+        self.generation_config = GenerationConfig(
+            max_length=config.model_max_length, do_sample=False, temperature=1.0, top_p=1.0, top_k=0,
+            bos_token_id=config.bos_token_id, eos_token_id=config.eos_token_id, pad_token_id=config.pad_token_id)
+        self.model = _Inner(self)
+        self._lock = threading.Lock()
+        self._stream = torch.cuda.Stream(device=self.device)
+        self._slot = self.engine.seq_alloc()
+        self._slot_tokens: List[int] = []      # token history whose KV is valid in the working slot
+        self._slot_image_key = None
+        self._img_cache = None                  # (pixel tensor on device, image embeds [P,H])
+        self._call_counter = 0
+
+    # ---- reference-compat trivia ---------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def requires_grad_(self, *_):
+        return self
+
+    def get_model(self):
+        return self.model
+
+    # ---- image features (cached per pixel tensor) ----------------------------------------------
+    def _image_embeds(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        pix = pixel_values.to(self.device, torch.float32, non_blocking=True)
+        if pix.dim() == 3:
+            pix = pix[None]
+        if pix.shape[0] != 1:
+            raise ValueError("generate() supports a single image (batch size 1), like the reference's streamers")
+        cached = self._img_cache
+        if cached is not None and cached[0].shape == pix.shape and torch.equal(cached[0], pix):
+            return cached[1]
+        emb = self.engine.image_embeds(pix)[0]
+        self._img_cache = (pix.clone(), emb)
+        self._slot_tokens = []  # KV of the image prefix is stale for a new image
+        return emb
+
+    @staticmethod
+    def _first(seq, default=-1) -> int:
+        try:
+            v = seq[0]
+            while isinstance(v, (list, tuple)):
+                v = v[0]
+            return int(v)
+        except (TypeError, IndexError):
+            return default
+
+    # ---- generate --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor = None, pixel_values: Optional[torch.Tensor] = None,
+                 bad_words_ids=None, begin_suppress_tokens=None, streamer=None, stopping_criteria=None,
+                 temperature: Optional[float] = None, top_p: Optional[float] = None, top_k: Optional[int] = None,
+                 max_length: Optional[int] = None, max_new_tokens: Optional[int] = None,
+                 do_sample: Optional[bool] = None, seed: Optional[int] = None, eos_token_id: Optional[int] = None,
+                 **ignored) -> torch.Tensor:
+        cfg, eng = self.config, self.engine
+        gc = self.generation_config
+        temperature = gc.temperature if temperature is None else temperature
+        top_p = gc.top_p if top_p is None else top_p
+        top_k = gc.top_k if top_k is None else top_k
+        do_sample = gc.do_sample if do_sample is None else do_sample
+        eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+
+        ids2d = input_ids if input_ids.dim() == 2 else input_ids[None]
+        if ids2d.shape[0] != 1:
+            raise ValueError("generate() is batch-1 (use generate_batch for parallel rollouts)")
+        ids_host: List[int] = ids2d[0].tolist()
+        T0 = len(ids_host)
+        if max_length is None:
+            max_length = T0 + max_new_tokens if max_new_tokens is not None else gc.max_length
+        max_length = min(int(max_length), eng.max_len)
+        criteria = StoppingCriteriaList(stopping_criteria or [])
+
+        with self._lock, torch.cuda.stream(self._stream):
+            # -- splice validation (v1/modeling_detikzify.py:176-184)
+            img, img_start = None, 0
+            patch = cfg.image_token_id
+            n_patch_tokens = ids_host.count(patch)
+            if pixel_values is not None and n_patch_tokens > 0:
+                if n_patch_tokens != cfg.num_patches:
+                    raise ValueError("The number of image patch tokens should be the same as the number of image patches.")
+                img_start = ids_host.index(patch)
+                if ids_host[img_start: img_start + n_patch_tokens] != [patch] * n_patch_tokens:
+                    raise ValueError("The image patch tokens should be consecutive.")
+                img = self._image_embeds(pixel_values)
+            elif pixel_values is None and self._img_cache is not None and n_patch_tokens:
+                self._slot_tokens = []
+            if T0 == 0:
+                raise ValueError("empty prompt")
+            if streamer is not None:
+                streamer.put(ids2d.cpu())
+            if T0 >= max_length:
+                if streamer is not None:
+                    streamer.end()
+                return ids2d.to(self.device)
+
+            # -- longest common prefix with the KV already in the working slot
+            hist = self._slot_tokens
+            L = 0
+            lim = min(len(hist), T0 - 1)
+            while L < lim and hist[L] == ids_host[L]:
+                L += 1
+            if img is not None and L < img_start + n_patch_tokens:
+                L = min(L, img_start)  # never split the image span
+            ids_dev = torch.tensor(ids_host[L:], dtype=torch.int64).pin_memory().to(self.device, non_blocking=True)
+            last_logits, _ = eng.prefill(self._slot, ids_dev, L, img, img_start)
+            self._slot_tokens = list(ids_host)
+
+            self._call_counter += 1
+            params = eng.sampling(
+                temperature=temperature, top_p=top_p, top_k=top_k or 0, do_sample=bool(do_sample),
+                bad_token=self._first(bad_words_ids), begin_suppress_token=self._first(begin_suppress_tokens),
+                seed=(seed if seed is not None else torch.initial_seed() + self._call_counter))
+            first, _ = eng.sample(last_logits, params, suppress=[1], steps=[0])
+            tok = int(first.item())
+
+            out_buf = torch.empty(1, max_length, dtype=torch.int64)
+            out_buf[0, :T0] = ids2d[0].cpu()
+            n_new = max_length - T0        # upper bound on new tokens
+            new_tokens: List[int] = []
+            launched = waited = 0
+            started = False
+            try:
+                while True:
+                    new_tokens.append(tok)
+                    out_buf[0, T0 + len(new_tokens) - 1] = tok
+                    if streamer is not None:
+                        streamer.put(out_buf[0, T0 + len(new_tokens) - 1: T0 + len(new_tokens)])
+                    cur = out_buf[:, : T0 + len(new_tokens)]
+                    if tok == eos or len(new_tokens) >= n_new or criteria(cur, None):
+                        break
+                    if not started:
+                        eng.gen_begin([self._slot], [T0], [tok], params)
+                        started = True
+                    while launched < waited + 2 and launched < n_new - 1:
+                        eng.gen_step()
+                        launched += 1
+                    tok = eng.gen_wait(waited)[0]
+                    waited += 1
+            finally:
+                if started:
+                    eng.gen_end()
+                # decode step s wrote KV at T0+s for new_tokens[s]; only tokens the host has seen count
+                self._slot_tokens = list(ids_host) + new_tokens[: min(launched, len(new_tokens))]
+            # exceptions escape before this point (the caller's error_callback feeds the streamer,
+            # detikzify/infer/generate.py:252); the normal path always terminates the stream
+            if streamer is not None:
+                streamer.end()
+            return out_buf[:, : T0 + len(new_tokens)].to(self.device)
+
+    # ---- SelfSim helper: pooled features straight from the engine --------------------------------
+    @torch.no_grad()
+    def pooled_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        with self._lock, torch.cuda.stream(self._stream):
+            _, pooled = self.engine.vit_encode(pixel_values, want_tokens=False)
+            self._stream.synchronize()
+        return pooled
+
+    def close(self):
+        self.engine.close()
