@@ -135,6 +135,15 @@ struct dtk_engine {
   cudaGraphExec_t gen_graph = nullptr;
   cudaStream_t gen_stream = nullptr;
   cudaStream_t cap_stream = nullptr;  // engine-owned: graph capture never touches the caller's stream
+  // persistent decode kernel (B = 1)
+  MegaArgs mega{};
+  int mega_grid = 0;
+  bool mega_ok = false;
+  int decode_impl = 1;       // 1 = persistent weight-streaming kernel (default), 0 = per-op kernels / CUDA graph
+  bool gen_mega = false;
+  SampleArgs gen_sample{};
+  float* d_part = nullptr;
+  unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
 };
 
 namespace {
@@ -190,6 +199,9 @@ __global__ void set_state_kernel(StateArgs a, int* slots, int* pos, int* tok) {
     pos[i] = a.pos[i];
     if (a.have_tok) tok[i] = (int)a.tok[i];
   }
+}
+__global__ void tok64_to_32_kernel(const int64_t* in, int* out, int n) {
+  if ((int)threadIdx.x < n) out[threadIdx.x] = (int)in[threadIdx.x];
 }
 __global__ void reset_gen_kernel(unsigned long long* gen, unsigned int* done) {
   gen[0] = 0ull;
@@ -343,6 +355,17 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
   const dtk_config& c = eng->cfg;
   const int H = c.hidden, I = c.inter, qd = c.heads * 128, kd = c.kv_heads * 128;
   uint64_t* lc = &eng->launches;
+  if (B == 1 && eng->decode_impl == 1 && eng->mega_ok) {
+    if (tok64) {
+      tok64_to_32_kernel<<<1, 32, 0, s>>>(tok64, eng->d_tok, 1);
+      ++*lc;
+      DTK_CK(cudaGetLastError());
+    }
+    MegaArgs m = eng->mega;
+    m.logits = logits;
+    DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
+    return DTK_OK;
+  }
   DTK_CK(launch_embed_tokens(tok64 ? nullptr : eng->d_tok, tok64, B, W(eng, "dec.embed"), H, c.vocab, eng->d_x, s, lc));
   const int nsplit = nsplit_for(c, B);
   for (int l = 0; l < c.layers; ++l) {
@@ -507,6 +530,32 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
   DTK_ALLOC(eng->d_gen, 2);
   DTK_CK(cudaMemset(eng->d_gen, 0, 2 * sizeof(unsigned long long)));
   DTK_ALLOC(eng->v_pq, c.v_hidden);
+  {
+    int smem_optin = 0, sms = 0, coop = 0;
+    DTK_CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    DTK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DTK_CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    MegaArgs& m = eng->mega;
+    int grid = 0;
+    if (coop && mega_configure(m, c.hidden, c.inter, c.heads, smem_optin, sms, &grid) == cudaSuccess) {
+      m.H = c.hidden; m.I = c.inter; m.L = c.layers; m.heads = c.heads; m.kv_heads = c.kv_heads; m.V = c.vocab;
+      m.max_len = c.max_len; m.eps = c.rms_eps;
+      m.embed = W(eng, "dec.embed"); m.lm_head = W(eng, "dec.lm_head"); m.final_norm = W(eng, "dec.norm");
+      m.norm1_0 = W(eng, "dec.L0.norm1"); m.wqkv0 = W(eng, "dec.L0.wqkv"); m.wo0 = W(eng, "dec.L0.wo");
+      m.norm2_0 = W(eng, "dec.L0.norm2"); m.wgu0 = W(eng, "dec.L0.wgu"); m.wd0 = W(eng, "dec.L0.wd");
+      m.layer_stride = c.layers > 1 ? (int64_t)(W(eng, "dec.L1.norm1") - W(eng, "dec.L0.norm1")) : 0;
+      m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
+      m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
+      m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
+      m.x = eng->d_x; m.q = eng->d_q; m.h = eng->d_h; m.logits = eng->d_logits;
+      DTK_ALLOC(eng->d_part, (int64_t)grid * 132);
+      DTK_ALLOC(eng->d_bar, 2);
+      DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
+      m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
+      eng->mega_grid = grid;
+      eng->mega_ok = true;
+    }
+  }
   DTK_CK(cudaHostAlloc((void**)&eng->host_ring, (size_t)eng->ring * 64 * sizeof(int), cudaHostAllocMapped));
   DTK_CK(cudaHostAlloc((void**)&eng->host_flag, sizeof(long long), cudaHostAllocMapped));
   *eng->host_flag = 0;
@@ -523,7 +572,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
@@ -740,6 +789,22 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
   DTK_CK(cudaStreamSynchronize(s));
   *eng->host_flag = 0;
 
+  eng->gen_B = B;
+  eng->gen_params = *params;
+  eng->gen_stream = s;
+  {  // sampler arguments of the loop (suppress = 0, RNG counter = 1 + step)
+    SampleArgs& a = eng->gen_sample;
+    fill_sample_args(eng, a, eng->d_logits, B, *params);
+    for (int i = 0; i < B; ++i) { a.seq[i].suppress = 0; a.seq[i].step = 1; a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i; }
+    a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
+    a.host_ring = eng->dev_ring; a.host_flag = eng->dev_flag; a.ring = eng->ring;
+    a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
+  }
+  eng->gen_mega = (B == 1 && eng->decode_impl == 1 && eng->mega_ok);
+  if (eng->gen_mega) {  // one cooperative launch + sampler per token: no graph needed
+    eng->gen_graph = nullptr;
+    return DTK_OK;
+  }
   // graph key: everything baked into kernel arguments
   char key[256];
   std::snprintf(key, sizeof(key), "B%d|t%.9g|p%.17g|k%d|s%d|b%d|e%d|seed%llu", B, (double)params->temperature,
@@ -756,13 +821,7 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     DTK_CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     int r = decode_launches(eng, B, nullptr, eng->d_logits, cs);
     if (r == DTK_OK) {
-      SampleArgs a;
-      fill_sample_args(eng, a, eng->d_logits, B, *params);
-      for (int i = 0; i < B; ++i) { a.seq[i].suppress = 0; a.seq[i].step = 1; a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i; }
-      a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
-      a.host_ring = eng->dev_ring; a.host_flag = eng->dev_flag; a.ring = eng->ring;
-      a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
-      cudaError_t e = launch_sample(a, cs, &eng->launches);
+      cudaError_t e = launch_sample(eng->gen_sample, cs, &eng->launches);
       if (e != cudaSuccess) { eng->err = std::string("launch_sample: ") + cudaGetErrorString(e); r = DTK_ERR_CUDA; }
     }
     cudaError_t ce = cudaStreamEndCapture(cs, &graph);
@@ -779,14 +838,18 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     it = eng->graphs.emplace(skey, exec).first;
   }
   eng->gen_graph = it->second;
-  eng->gen_B = B;
-  eng->gen_params = *params;
-  eng->gen_stream = s;
   return DTK_OK;
 }
 
 int dtk_gen_step(dtk_engine* eng, void* stream) {
   if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->gen_B > 0, "dtk_gen_begin not called");
+  if (eng->gen_mega) {
+    int r = decode_launches(eng, 1, nullptr, eng->d_logits, (cudaStream_t)stream);
+    if (r != DTK_OK) return r;
+    DTK_CK(launch_sample(eng->gen_sample, (cudaStream_t)stream, &eng->launches));
+    return DTK_OK;
+  }
   DTK_REQUIRE(eng->gen_graph != nullptr, "dtk_gen_begin not called");
   DTK_CK(cudaGraphLaunch(eng->gen_graph, (cudaStream_t)stream));
   eng->launches += (uint64_t)eng->cfg.layers * 5 + 3;
@@ -795,7 +858,7 @@ int dtk_gen_step(dtk_engine* eng, void* stream) {
 
 int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host) {
   if (!eng) return DTK_ERR_INVALID;
-  DTK_REQUIRE(eng->gen_graph != nullptr && step >= 0 && tokens_out_host, "gen state/step/out");
+  DTK_REQUIRE(eng->gen_B > 0 && step >= 0 && tokens_out_host, "gen state/step/out");
   volatile long long* flag = eng->host_flag;
   auto t0 = std::chrono::steady_clock::now();
   uint64_t spins = 0;
@@ -823,13 +886,26 @@ int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host) {
 
 int dtk_gen_end(dtk_engine* eng) {
   if (!eng) return DTK_ERR_INVALID;
-  if (eng->gen_stream || eng->gen_graph) {
+  if (eng->gen_B > 0) {
     DTK_CK(cudaSetDevice(eng->device));
     DTK_CK(cudaStreamSynchronize(eng->gen_stream));
   }
   eng->gen_graph = nullptr;
+  eng->gen_mega = false;
   eng->gen_B = 0;
   return DTK_OK;
+}
+
+int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
+  if (!eng || !key) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->gen_B == 0, "options cannot change inside a generation loop");
+  if (std::strcmp(key, "decode_impl") == 0) {
+    DTK_REQUIRE(value == 0 || value == 1, "decode_impl must be 0 (per-op) or 1 (persistent)");
+    eng->decode_impl = (int)value;
+    return DTK_OK;
+  }
+  eng->err = std::string("unknown option ") + key;
+  return DTK_ERR_INVALID;
 }
 
 // ---- kernel-level test hooks ---------------------------------------------------------------

@@ -144,6 +144,25 @@ struct SampleArgs {
 };
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s, uint64_t* counter);
 
+// ---------------------------------------------------------------- persistent decode kernel (B = 1)
+struct MegaArgs {
+  int H, I, L, heads, kv_heads, V, max_len;
+  float eps;
+  const bf16 *embed, *lm_head, *final_norm;
+  const bf16 *norm1_0, *wqkv0, *wo0, *norm2_0, *wgu0, *wd0;  // layer-0 tensors; layer l = ptr + l * layer_stride
+  int64_t layer_stride;                                       // elements between consecutive layers in the arena
+  const int *tok, *pos, *slots;                               // device state of the sequence being decoded
+  bf16* kv;
+  int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
+  const float* rope_cs;
+  float *x, *q, *h, *part, *logits;                           // part: [grid][132] attention partials
+  unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
+  int nslots, slot_bytes, act_floats;                         // shared-memory ring geometry (mega_configure)
+};
+int mega_smem_bytes(const MegaArgs& a);
+cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out);
+cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint64_t* counter);
+
 // single-query attention of the SigLIP attention-pool head: q fp32 [heads*72] (shared by all images),
 // kv bf16 [B*N, 2*D] -> out bf16 [B, D]
 cudaError_t launch_pool_attn(const float* q, const bf16* kv, int B, int N, int D, int heads, float scale,

@@ -199,6 +199,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.dtk_launch_count(self._h))
 
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.dtk_set_option(self._h, key.encode(), int(value)), "dtk_set_option")
+
     def decode_bytes(self, context_len: int) -> int:
         return int(self.lib.dtk_decode_bytes(C.byref(self.ccfg), context_len))
 

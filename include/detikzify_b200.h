@@ -152,6 +152,10 @@ DTK_API int dtk_gen_step(dtk_engine* eng, void* stream);
 DTK_API int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host /* [B] */);
 DTK_API int dtk_gen_end(dtk_engine* eng);
 
+/* ---- engine options. "decode_impl": 1 = persistent weight-streaming decode kernel (default for
+ *      B = 1), 0 = per-op kernels replayed from a CUDA graph (always used for B > 1). ----------- */
+DTK_API int dtk_set_option(dtk_engine* eng, const char* key, int64_t value);
+
 /* ---- introspection for benches: algorithmic HBM bytes of one decode step at context T ----- */
 DTK_API uint64_t dtk_decode_bytes(const dtk_config* cfg, int context_len);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */

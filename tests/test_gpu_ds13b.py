@@ -1,0 +1,68 @@
+"""
+BASELINE.json configs[1]: detikzify-ds-1.3b shape, 1 GPU, batch-1 — logits parity of the CUDA path against
+the fp32 CPU oracle at the real checkpoint shape (random-init weights), including the
+2k-context end of the KV cache. Tolerance: logits max-abs 3e-2 (|logits| ~ 1), greedy ids equal wherever
+the oracle's top-1 margin exceeds 2x that tolerance (teacher-forced).
+"""
+import pytest
+import torch
+
+from conftest import engine_for, model_bundle
+
+pytestmark = pytest.mark.gpu
+NAME = "nllg/detikzify-ds-1.3b"
+TOL = 3e-2
+
+
+def test_ds13b_prefill_decode_and_2k_context():
+    from oracle.hf_oracle import synthetic_pixels
+    cfg, sd, oracle = model_bundle(NAME)
+    eng = engine_for(NAME, max_seqs=2, max_batch=1)
+    P = cfg.num_patches
+    assert P == 243 and cfg.vision_config.num_positions == 729
+    pix = synthetic_pixels(1, 384)
+
+    # (a) ViT tokens + pooled vector + projector at the real shape
+    ref_tok, ref_pool = oracle.vision(pix)
+    tok, pool = eng.vit_encode(pix.cuda())
+    assert (tok.cpu() - ref_tok).abs().max() < TOL
+    assert (pool.cpu() - ref_pool).abs().max() < TOL
+    ref_img = oracle.image_embeds(pix)
+    img = eng.image_embeds(pix.cuda())[0]
+    assert (img.cpu() - ref_img[0]).abs().max() < TOL
+
+    # (b) image-prefix prefill + 24 teacher-forced greedy decode steps
+    g = torch.Generator().manual_seed(2000)
+    ids = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, 32000, (5,), generator=g)]).long()
+    T0, steps = ids.numel(), 24
+    ref_ids = oracle.generate(ids[None], pix, max_length=T0 + steps, stop_on_eos=False)[0]
+    ref_all, _ = oracle.forward_logits(ref_ids[None], pix)
+    slot = eng.seq_alloc()
+    try:
+        last, _ = eng.prefill(slot, ids.cuda(), 0, img, 0)
+        worst = (last.cpu() - ref_all[0, T0 - 1]).abs().max().item()
+        agree = checked = 0
+        for t in range(T0, T0 + steps - 1):
+            lg = eng.decode([slot], [t], ref_ids[t:t + 1].cuda())[0].cpu()
+            worst = max(worst, (lg - ref_all[0, t]).abs().max().item())
+            top2 = ref_all[0, t].topk(2).values
+            if (top2[0] - top2[1]) > 2 * TOL:
+                checked += 1
+                agree += int(lg.argmax() == ref_all[0, t].argmax())
+        assert worst < TOL, worst
+        assert agree == checked
+
+        # (c) the 2k-context end: 2047 cached positions, decode the token at position 2047
+        long_ids = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, 32000, (2048 - P,), generator=g)]).long()
+        ref_long, _ = oracle.forward_logits(long_ids[None], pix)
+        lastp, _ = eng.prefill(slot, long_ids[:2047].cuda(), 0, img, 0)
+        assert (lastp.cpu() - ref_long[0, 2046]).abs().max() < TOL
+        lg = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()
+        assert (lg - ref_long[0, 2047]).abs().max() < TOL
+        # per-op implementation at the same point
+        eng.set_option("decode_impl", 0)
+        lg0 = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()
+        eng.set_option("decode_impl", 1)
+        assert (lg0 - ref_long[0, 2047]).abs().max() < TOL
+    finally:
+        eng.seq_free(slot)

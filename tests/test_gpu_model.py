@@ -79,11 +79,14 @@ def test_prefill_logits_all_positions(name):
     assert (last.cpu() - ref[0, -1]).abs().max() < TOL_LOGITS
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["persistent", "per-op"])
 @pytest.mark.parametrize("name", ["tiny", "tiny2"])
-def test_decode_teacher_forced_matches_oracle(name):
-    """KV-cached single-token steps == oracle cached decode (v1/modeling_detikzify.py:285-305)."""
+def test_decode_teacher_forced_matches_oracle(name, impl):
+    """KV-cached single-token steps == oracle cached decode (v1/modeling_detikzify.py:285-305),
+    for both decode implementations (persistent weight-streaming kernel / per-op kernels)."""
     cfg, sd, oracle = model_bundle(name)
     eng = engine_for(name)
+    eng.set_option("decode_impl", impl)
     pix = _pixels(cfg, 1)
     ids = _prompt(cfg)
     T0 = ids.numel()
@@ -106,6 +109,7 @@ def test_decode_teacher_forced_matches_oracle(name):
                 agree += int(lg.argmax() == ref_all[0, t].argmax())
     finally:
         eng.seq_free(slot)
+        eng.set_option("decode_impl", 1)
     assert worst < TOL_LOGITS, worst
     assert agree == checked
 
@@ -248,10 +252,12 @@ def test_sampler_distribution_statistics():
 
 
 # ---------------------------------------------------------------- fused generation loop (CUDA graph)
+@pytest.mark.parametrize("impl", [1, 0], ids=["persistent", "graph"])
 @pytest.mark.parametrize("name", ["tiny", "tiny2"])
-def test_graph_generation_loop_equals_stepwise_greedy(name):
+def test_generation_loop_equals_stepwise_greedy(name, impl):
     cfg, sd, oracle = model_bundle(name)
     eng = engine_for(name)
+    eng.set_option("decode_impl", impl)
     pix = _pixels(cfg, 1)
     ids = _prompt(cfg)
     T0 = ids.numel()
@@ -280,4 +286,29 @@ def test_graph_generation_loop_equals_stepwise_greedy(name):
         eng.gen_end()
     finally:
         eng.seq_free(slot)
+        eng.set_option("decode_impl", 1)
     assert got == toks
+
+
+def test_persistent_and_per_op_decode_agree():
+    """The two decode implementations compute the same function (different summation order only)."""
+    cfg, sd, oracle = model_bundle("tiny2")
+    eng = engine_for("tiny2")
+    pix = _pixels(cfg, 1)
+    ids = _prompt(cfg, n_text=30).cuda()
+    img = eng.image_embeds(pix.cuda())[0]
+    slot = eng.seq_alloc()
+    try:
+        out = {}
+        for impl in (0, 1):
+            eng.set_option("decode_impl", impl)
+            eng.prefill(slot, ids, 0, img, 0)
+            lg = []
+            for i in range(8):
+                lg.append(eng.decode([slot], [ids.numel() + i], torch.tensor([17 + i], device="cuda")).clone())
+            out[impl] = torch.stack(lg)
+        torch.cuda.synchronize()
+    finally:
+        eng.seq_free(slot)
+        eng.set_option("decode_impl", 1)
+    assert (out[0] - out[1]).abs().max() < 2e-3
