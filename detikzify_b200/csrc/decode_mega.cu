@@ -73,12 +73,13 @@ DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_T
 
 DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 
-// grid barrier over the consumer threads of all CTAs (producer warps never take part)
+// grid barrier over the consumer threads of all CTAs (producer warps never take part).
+// bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
+// cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
 DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target) {
   consumer_sync();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1ull);
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
     uint32_t spins = 0;
     long long t0 = 0;
     unsigned long long v;
@@ -90,7 +91,6 @@ DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target
         else if (now - t0 > SPIN_CYCLES) __trap();
       }
     } while (v < target);
-    __threadfence();
   }
   consumer_sync();
 }
@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const int act_floats = p.act_floats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(actf + act_floats);
   float* red = reinterpret_cast<float*>(bars + 2 * nslots);  // 16 floats
+  float* rope_s = red + 16;                                   // [64][2] cos/sin of this position
+  float* wts = rope_s + 128;                                  // [heads][16] attention-merge weights
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -248,29 +250,29 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   int tok = p.tok[0];
   if (tok < 0 || tok >= p.V) tok = 0;
   const int qd = p.heads * 128, kd = p.kv_heads * 128;
+  if (tid < 128) rope_s[tid] = p.rope_cs[(int64_t)pos * 128 + tid];
+  __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
 
   if (warp == NCW) {
     // =============================================================== PRODUCER
     if (lane == 0) {
-      uint32_t n = 0;             // CTA-local item counter -> ring slot
-      unsigned long long gbase = 0;  // global item counter -> round-robin offset
-      auto acquire = [&](uint32_t& s_out, uint32_t& dst, uint32_t& fb) {
-        const uint32_t s = n % nslots;
-        const uint32_t use = n / nslots;
-        if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
-        s_out = s; dst = ring_u32 + s * slot_bytes; fb = full0 + 8 * s;
-        ++n;
+      uint32_t ps = 0, pu = 0;     // ring slot of the next item / how many times the ring wrapped
+      uint32_t gmod = 0;           // (global item counter) mod G -> round-robin offset of the next phase
+      auto acquire = [&](uint32_t& dst, uint32_t& fb) {
+        if (pu > 0) mbar_wait(empty0 + 8 * ps, (pu - 1) & 1);
+        dst = ring_u32 + ps * slot_bytes; fb = full0 + 8 * ps;
+        if (++ps == (uint32_t)nslots) { ps = 0; ++pu; }
       };
       auto stream_phase = [&](const Phase& d) {
         const uint32_t rb = (uint32_t)d.K * 2;
-        int it = (int)(((unsigned long long)c + G - (gbase % G)) % G);
+        int it = (int)(((uint32_t)c + (uint32_t)G - gmod) % (uint32_t)G);
         for (; it < d.n_items; it += G) {
           int r0, r1;
           item_rows(d, it, r0, r1);
-          uint32_t s, dst, fb;
-          acquire(s, dst, fb);
+          uint32_t dst, fb;
+          acquire(dst, fb);
           if (d.mode == 0) {           // rows 2i, 2i+1 are contiguous in memory: one copy
             mbar_expect_tx(fb, 2 * rb);
             bulk_g2s(dst, d.W + (int64_t)r0 * d.K, 2 * rb, fb);
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             bulk_g2s(dst, d.W + (int64_t)r0 * d.K, rb, fb);
           }
         }
-        gbase += d.n_items;
+        gmod = (gmod + (uint32_t)d.n_items) % (uint32_t)G;
       };
       for (int l = 0; l < p.L; ++l) {
         stream_phase(make_phase(p, l, PH_QKV));
@@ -293,8 +295,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           const bf16* vb = kb + p.kv_v_offset;
           for (int i = 0; i < as.n_items; ++i) {
             const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
-            uint32_t s, dst, fb;
-            acquire(s, dst, fb);
+            uint32_t dst, fb;
+            acquire(dst, fb);
             mbar_expect_tx(fb, (uint32_t)nk * 512);
             bulk_g2s(dst, kb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
             bulk_g2s(dst + 16 * 256, vb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
@@ -313,42 +315,65 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   ActView X;
   X.lo = reinterpret_cast<float4*>(actf);
   unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
-  uint32_t n_local = 0;                          // CTA-local items consumed so far (all warps)
-  unsigned long long gbase = 0;
+  uint32_t cs = 0, cu = 0;                       // ring slot / wrap count of the CTA's next local item
+  uint32_t cw = 0;                               // (local item counter) mod NCW -> owning consumer warp
+  uint32_t gmod = 0;
 
-  // wait for local item n (if it is this warp's), returns the smem pointer
-  auto slot_ptr = [&](uint32_t n) -> uint8_t* {
-    const uint32_t s = n % nslots, use = n / nslots;
-    mbar_wait(full0 + 8 * s, use & 1);
-    return ring + (size_t)s * slot_bytes;
+  // advance the local item cursor by one item; returns true when the item belongs to this warp and
+  // yields its slot pointer (after waiting for the producer's bytes)
+  auto next_item = [&](const uint8_t*& base, uint32_t& my_slot) -> bool {
+    const bool mine = ((int)cw == warp);
+    if (mine) {
+      mbar_wait(full0 + 8 * cs, cu & 1);
+      base = ring + (size_t)cs * slot_bytes;
+      my_slot = cs;
+    }
+    if (++cs == (uint32_t)nslots) { cs = 0; ++cu; }
+    if (++cw == NCW) cw = 0;
+    return mine;
   };
-  auto release = [&](uint32_t n) {
+  auto release = [&](uint32_t sl) {
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty0 + 8 * (n % nslots));
+    if (lane == 0) mbar_arrive(empty0 + 8 * sl);
   };
 
-  const float* rope = p.rope_cs + (int64_t)pos * 128;  // [64][2]
+  // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, barrier done}
+  long long* dbg = (p.dbg && (c == 0 || c == G / 2 || c == G - 1)) ? p.dbg + (int64_t)(c == 0 ? 0 : (c == G - 1 ? 2 : 1)) * (p.L * 5 + 1) * 4 : nullptr;
+  int dbg_i = 0;
+  auto stamp = [&](int k) { if (dbg && tid == 0) dbg[dbg_i * 4 + k] = clock64(); };
 
   auto run_phase = [&](const Phase& d, int ph, int layer) {
     const int KC = d.K >> 3;
     X.hi = X.lo + KC;
-    int it = (int)(((unsigned long long)c + G - (gbase % G)) % G);
-    uint32_t k = 0;
-    for (; it < d.n_items; it += G, ++k) {
-      const uint32_t n = n_local + k;
-      if ((int)(n % NCW) != warp) continue;
+    int it = (int)(((uint32_t)c + (uint32_t)G - gmod) % (uint32_t)G);
+    for (; it < d.n_items; it += G) {
+      const uint8_t* base = nullptr;
+      uint32_t sl = 0;
       int r0, r1;
       item_rows(d, it, r0, r1);
-      const uint8_t* base = slot_ptr(n);
+      // residuals are fetched before waiting on the weights so their L2 latency hides behind the wait
+      float b0 = 0.f, b1 = 0.f;
+      const bool mine_pre = ((int)cw == warp);
+      if (mine_pre && lane == 0) {
+        if (ph == PH_O) {
+          if (layer == 0) {  // residual stream starts as the token embedding
+            b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
+            b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
+          } else { b0 = ldcg_f(p.x + r0); b1 = ldcg_f(p.x + r1); }
+        } else if (ph == PH_DOWN) {
+          b0 = ldcg_f(p.x + r0);
+        }
+      }
+      if (!next_item(base, sl)) continue;
       float a0, a1;
       dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
-      release(n);
+      release(sl);
       if (lane == 0) {
         if (ph == PH_QKV) {
           const int i = r0 & 127;
           if (r0 < qd + kd) {
-            const float2 cs = *reinterpret_cast<const float2*>(rope + i * 2);
-            const float y0 = a0 * cs.x - a1 * cs.y, y1 = a1 * cs.x + a0 * cs.y;
+            const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+            const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
             if (r0 < qd) { p.q[r0] = y0; p.q[r1] = y1; }
             else {
               const int kh = (r0 - qd) >> 7;
@@ -363,37 +388,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             dd[i + 64] = __float2bfloat16_rn(a1);
           }
         } else if (ph == PH_O) {
-          float b0, b1;
-          if (layer == 0) {  // residual stream starts as the token embedding
-            b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
-            b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
-          } else { b0 = ldcg_f(p.x + r0); b1 = ldcg_f(p.x + r1); }
           p.x[r0] = b0 + a0;
           p.x[r1] = b1 + a1;
         } else if (ph == PH_GU) {
           p.h[it] = silu(a0) * a1;
         } else if (ph == PH_DOWN) {
-          p.x[r0] = ldcg_f(p.x + r0) + a0;
+          p.x[r0] = b0 + a0;
         } else {
           p.logits[r0] = a0;
           p.logits[r1] = a1;
         }
       }
     }
-    n_local += k;
-    gbase += d.n_items;
+    gmod = (gmod + (uint32_t)d.n_items) % (uint32_t)G;
   };
 
   for (int l = 0; l < p.L; ++l) {
     const int64_t lo = (int64_t)l * p.layer_stride;
     // ---------------- P1: RMSNorm + qkv + RoPE + KV write
+    stamp(0);
     X.hi = X.lo + (p.H >> 3);
     stage_vector(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, p.norm1_0 + lo, p.eps, X, red);
+    stamp(1);
     run_phase(make_phase(p, l, PH_QKV), PH_QKV, l);
+    stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
+    stamp(3); ++dbg_i;
 
     // ---------------- P2: attention over this CTA's key range of its head
+    stamp(0); stamp(1);
     if (as.active) {
       const int hw = lane >> 4, l16 = lane & 15;
       const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
@@ -404,21 +428,28 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         q[0] = a.x * sl2; q[1] = a.y * sl2; q[2] = a.z * sl2; q[3] = a.w * sl2;
         q[4] = b.x * sl2; q[5] = b.y * sl2; q[6] = b.z * sl2; q[7] = b.w * sl2;
       }
+      // the key/value of the token being decoded (written in P1 of this launch): fetch early
+      uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
+      if (as.last && warp == 0) {
+        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + pos) * 128;
+        knew = __ldcg(reinterpret_cast<const uint4*>(kb + l16 * 8));
+        vnew = __ldcg(reinterpret_cast<const uint4*>(kb + p.kv_v_offset + l16 * 8));
+      }
       float m = -INFINITY, lsum = 0.f, o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
       auto key_update = [&](const uint4& kraw, const uint4& vraw, bool valid) {
         float kf[8];
         unpack8(kraw, kf);
-        float s = 0.f;
+        float s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += q[i] * kf[i];
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         if (valid) {
-          const float mn = fmaxf(m, s), alpha = exp2f(m - mn), pj = exp2f(s - mn);
+          const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
           float vf[8];
           unpack8(vraw, vf);
           lsum = lsum * alpha + pj;
@@ -428,10 +459,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       };
       for (int i = 0; i < as.n_items; ++i) {
-        const uint32_t n = n_local + i;
-        if ((int)(n % NCW) != warp) continue;
+        const uint8_t* base = nullptr;
+        uint32_t sl = 0;
+        if (!next_item(base, sl)) continue;
         const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
-        const uint8_t* base = slot_ptr(n);
 #pragma unroll 4
         for (int kk = 0; kk < 8; ++kk) {
           const int key = kk * 2 + hw;
@@ -443,14 +474,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           }
           key_update(kraw, vraw, valid);
         }
-        release(n);
+        release(sl);
       }
-      if (as.last && warp == 0) {  // the key/value of the token being decoded (written in P1 of this launch)
-        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + pos) * 128;
-        const uint4 kraw = __ldcg(reinterpret_cast<const uint4*>(kb + l16 * 8));
-        const uint4 vraw = __ldcg(reinterpret_cast<const uint4*>(kb + p.kv_v_offset + l16 * 8));
-        key_update(kraw, vraw, hw == 0);
-      }
+      if (as.last && warp == 0) key_update(knew, vnew, hw == 0);
       // merge the 16 half-warp states -> one partial per CTA
       float* sm_m = actf;            // [16]
       float* sm_l = actf + 16;       // [16]
@@ -476,69 +502,112 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         if (tid == 0) { pp[128] = M; pp[129] = Lt; }
       }
     }
-    n_local += as.n_items;
+    stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
+    stamp(3); ++dbg_i;
 
     // ---------------- P3: merge attention partials (all CTAs, redundantly) -> o-proj + residual
+    stamp(0);
     {
       int cph = G / p.heads;
       if (cph > 16) cph = 16;
-      X.hi = X.lo + (qd >> 3);
-      for (int e = tid; e < qd; e += CONSUMER_THREADS) {
-        const int head = e >> 7, d = e & 127;
-        float ms[16], M = -INFINITY;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          ms[r] = (r < cph) ? ldcg_f(p.part + (int64_t)(r * p.heads + head) * 132 + 128) : -INFINITY;
-          M = fmaxf(M, ms[r]);
+      // (a) normalised merge weights w[head][r] = exp2(m_r - M) / sum_r l_r exp2(m_r - M): 16 lanes per head
+      const int nW = p.heads * 16;
+      for (int t = tid; t < ((nW + 31) & ~31); t += CONSUMER_THREADS) {  // warp-uniform trip count (shuffles below)
+        const int head = t >> 4, r = t & 15;
+        float mr = -INFINITY, lr = 0.f;
+        if (t < nW && r < cph) {
+          const float* pp = p.part + (int64_t)(r * p.heads + head) * 132;
+          mr = ldcg_f(pp + 128);
+          lr = ldcg_f(pp + 129);
         }
-        float Lt = 0.f, O = 0.f;
+        float M = mr;
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 1));
+        const float w = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
+        float Ls = lr * w;
+        Ls += __shfl_xor_sync(0xffffffffu, Ls, 8);
+        Ls += __shfl_xor_sync(0xffffffffu, Ls, 4);
+        Ls += __shfl_xor_sync(0xffffffffu, Ls, 2);
+        Ls += __shfl_xor_sync(0xffffffffu, Ls, 1);
+        if (t < nW) wts[t] = Ls > 0.f ? w / Ls : 0.f;
+      }
+      consumer_sync();
+      // (b) attention vector: all partial loads of a thread are independent -> one L2 round trip
+      X.hi = X.lo + (qd >> 3);
+      for (int e0 = tid; e0 < qd; e0 += 4 * CONSUMER_THREADS) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float v[4][16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          if (r < cph) {
-            const float* pp = p.part + (int64_t)(r * p.heads + head) * 132;
-            const float w = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
-            Lt += ldcg_f(pp + 129) * w;
-            O += ldcg_f(pp + d) * w;
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * CONSUMER_THREADS;
+          const int head = e >> 7, d = e & 127;
+#pragma unroll
+          for (int r = 0; r < 16; ++r)
+            v[u][r] = (e < qd && r < cph) ? ldcg_f(p.part + (int64_t)(r * p.heads + head) * 132 + d) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * CONSUMER_THREADS;
+          if (e < qd) {
+            const int head = e >> 7;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc[u] += v[u][r] * wts[head * 16 + r];
+            // plane layout: element e lives in chunk e/8, position e%8 (lo: 0..3, hi: 4..7)
+            const int ch = e >> 3, w8 = e & 7;
+            float* dst = (w8 < 4) ? reinterpret_cast<float*>(X.lo + ch) + w8 : reinterpret_cast<float*>(X.hi + ch) + (w8 - 4);
+            *dst = acc[u];
           }
         }
-        // plane layout: element e lives in chunk e/8, lane-in-chunk e%8 (lo: 0..3, hi: 4..7)
-        const int ch = e >> 3, w8 = e & 7;
-        float* dst = (w8 < 4) ? reinterpret_cast<float*>(X.lo + ch) + w8 : reinterpret_cast<float*>(X.hi + ch) + (w8 - 4);
-        *dst = O / Lt;
       }
       consumer_sync();
     }
+    stamp(1);
     run_phase(make_phase(p, l, PH_O), PH_O, l);
+    stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
+    stamp(3); ++dbg_i;
 
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
+    stamp(0);
     X.hi = X.lo + (p.H >> 3);
     stage_vector(p.x, nullptr, p.H, p.norm2_0 + lo, p.eps, X, red);
+    stamp(1);
     run_phase(make_phase(p, l, PH_GU), PH_GU, l);
+    stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
+    stamp(3); ++dbg_i;
 
     // ---------------- P5: down + residual
+    stamp(0);
     X.hi = X.lo + (p.I >> 3);
     stage_vector(p.h, nullptr, p.I, nullptr, 0.f, X, red);
+    stamp(1);
     run_phase(make_phase(p, l, PH_DOWN), PH_DOWN, l);
+    stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
+    stamp(3); ++dbg_i;
   }
   // ---------------- final RMSNorm + lm_head
+  stamp(0);
   X.hi = X.lo + (p.H >> 3);
   stage_vector(p.x, nullptr, p.H, p.final_norm, p.eps, X, red);
+  stamp(1);
   run_phase(make_phase(p, 0, PH_LM), PH_LM, 0);
+  stamp(2); stamp(3);
   // publish the barrier epoch for the next launch (stream-ordered): every CTA executed 5L barriers
   if (c == 0 && tid == 0) *p.bar_base = bar_target;
 }
 
 }  // namespace
 
-int mega_smem_bytes(const MegaArgs& a) { return a.nslots * a.slot_bytes + a.act_floats * 4 + 2 * a.nslots * 8 + 64; }
+int mega_smem_bytes(const MegaArgs& a) { return a.nslots * a.slot_bytes + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + a.heads * 16) * 4; }
 
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out) {
   // slot = the largest work item: a pair of K=H rows or one K=I row; 16-key attention item = 8 KB
@@ -553,7 +622,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   actf = (actf + 31) & ~31;
   a.slot_bytes = slot;
   a.act_floats = actf;
-  const int fixed = actf * 4 + 64;
+  const int fixed = actf * 4 + (16 + 128 + heads * 16) * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (slot + 16);
   if (nslots > 32) nslots = 32;
   if (nslots < 2) return cudaErrorInvalidValue;

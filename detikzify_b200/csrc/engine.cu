@@ -144,6 +144,8 @@ struct dtk_engine {
   SampleArgs gen_sample{};
   float* d_part = nullptr;
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
+  long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
+  int mega_debug = 0;
 };
 
 namespace {
@@ -363,6 +365,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     }
     MegaArgs m = eng->mega;
     m.logits = logits;
+    m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -552,6 +555,9 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
       m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
+      DTK_ALLOC(eng->d_dbg, (int64_t)3 * (c.layers * 5 + 1) * 4);
+      DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)3 * (c.layers * 5 + 1) * 4 * sizeof(long long)));
+      m.dbg = nullptr;
       eng->mega_grid = grid;
       eng->mega_ok = true;
     }
@@ -572,7 +578,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
@@ -904,11 +910,25 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->decode_impl = (int)value;
     return DTK_OK;
   }
+  if (std::strcmp(key, "mega_debug") == 0) {
+    eng->mega_debug = value ? 1 : 0;
+    return DTK_OK;
+  }
   eng->err = std::string("unknown option ") + key;
   return DTK_ERR_INVALID;
 }
 
 // ---- kernel-level test hooks ---------------------------------------------------------------
+int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values) {
+  if (!eng || !out_host) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->d_dbg != nullptr, "persistent kernel unavailable");
+  const int n = 3 * (eng->cfg.layers * 5 + 1) * 4;
+  DTK_CK(cudaSetDevice(eng->device));
+  DTK_CK(cudaDeviceSynchronize());
+  DTK_CK(cudaMemcpy(out_host, eng->d_dbg, (size_t)(n < max_values ? n : max_values) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return n;
+}
+
 int dtk_dbg_gemm(const void* A, const void* Wm, const void* bias, const float* resid, int M, int N, int K, int act,
                  int glu, float* out_f32, void* out_bf16, void* stream) {
   GemmArgs g{};

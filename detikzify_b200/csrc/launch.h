@@ -158,6 +158,7 @@ struct MegaArgs {
   float *x, *q, *h, *part, *logits;                           // part: [grid][132] attention partials
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, slot_bytes, act_floats;                         // shared-memory ring geometry (mega_configure)
+  long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
 };
 int mega_smem_bytes(const MegaArgs& a);
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out);

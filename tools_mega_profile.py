@@ -1,0 +1,43 @@
+"""Phase-level timing breakdown of the persistent decode kernel (dev tool; run on the GPU box)."""
+import ctypes as C, sys, json
+import torch
+sys.path.insert(0, ".")
+from detikzify_b200.model import load
+name = sys.argv[1] if len(sys.argv) > 1 else "nllg/detikzify-ds-1.3b"
+ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+model, _ = load(name, device_map=0)
+eng, cfg = model.engine, model.config
+slot = eng.seq_alloc()
+g = torch.Generator().manual_seed(1)
+ids = torch.randint(0, 30000, (ctx,), generator=g).cuda()
+eng.prefill(slot, ids, 0, None, 0)
+tok = torch.tensor([5], device="cuda")
+for _ in range(5):
+    eng.decode([slot], [ctx], tok)
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+for _ in range(20):
+    eng.decode([slot], [ctx], tok)
+ev1.record(); torch.cuda.synchronize()
+print("ms/token (incl tok copy kernel):", ev0.elapsed_time(ev1) / 20)
+eng.set_option("mega_debug", 1)
+eng.decode([slot], [ctx], tok)
+L = cfg.num_hidden_layers
+n = 3 * (L * 5 + 1) * 4
+buf = (C.c_longlong * n)()
+got = eng.lib.dtk_dbg_mega_times(eng._h, buf, n)
+t = torch.tensor(list(buf), dtype=torch.float64).view(3, L * 5 + 1, 4)
+names = ["qkv", "attn", "o", "gu", "down"]
+for cta in range(3):
+    d = t[cta]
+    tot = (d[-1, 2] - d[0, 0]).item()
+    print(f"CTA#{cta}: total cycles {tot:.0f}")
+    for ph in range(5):
+        rows = d[ph:L * 5:5]
+        stage = (rows[:, 1] - rows[:, 0]).mean().item()
+        items = (rows[:, 2] - rows[:, 1]).mean().item()
+        bar = (rows[:, 3] - rows[:, 2]).mean().item()
+        print(f"  {names[ph]:5s} stage {stage:8.0f}  items {items:8.0f}  barrier {bar:8.0f}  (cycles, mean over layers)")
+    lm = d[-1]
+    print(f"  lm    stage {(lm[1]-lm[0]).item():8.0f}  items {(lm[2]-lm[1]).item():8.0f}")
