@@ -32,7 +32,8 @@ namespace dtk {
 namespace {
 
 constexpr int NCW = 8;                       // consumer warps
-constexpr int MEGA_THREADS = (NCW + 1) * 32; // + 1 producer warp
+constexpr int NPW = 4;                       // producer warps (one issuing lane each): per-item issue cost ~0.3 us
+constexpr int MEGA_THREADS = (NCW + NPW) * 32;
 constexpr int CONSUMER_THREADS = NCW * 32;
 constexpr long long SPIN_CYCLES = 4000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
 
@@ -129,6 +130,7 @@ DTK_DEV void item_rows(const Phase& d, int it, int& r0, int& r1) {
 // attention split: CTA c handles head c % heads, key range index c / heads (cph ranges per head)
 struct AttnSplit {
   int active, head, j0, j1, last;  // keys [j0, j1) among the OLD keys [0, pos); `last` also takes key `pos`
+  int cph;                         // CTAs per head
   int n_items;                     // 16-key items
 };
 DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
@@ -136,6 +138,7 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   int cph = G / p.heads;
   if (cph < 1) cph = 1;            // (heads > G is rejected on the host)
   if (cph > 16) cph = 16;
+  a.cph = cph;
   a.active = c < cph * p.heads;
   a.head = c % p.heads;
   const int r = c / p.heads;
@@ -188,34 +191,55 @@ DTK_DEV float consumer_sum(float v, float* red) {
   return t;
 }
 
-// stage a K-vector (optionally RMS-normalised) into the planes. src_f32 (ld.cg) or src_bf16 (embedding row)
+// stage a K-vector (optionally RMS-normalised) into the planes. src_f32 (ld.cg) or src_bf16 (embedding row).
+// With a norm the vector (K <= 8192) is held in registers: the x and norm-weight loads are issued together
+// (one L2/HBM round trip) and the scaled values are written to shared memory once.
 DTK_DEV void stage_vector(const float* src_f32, const bf16* src_bf16, int K, const bf16* norm_w, float eps,
                           const ActView& x, float* red) {
   const int KC = K >> 3, tid = threadIdx.x;
-  float ss = 0.f;
-  for (int c = tid; c < KC; c += CONSUMER_THREADS) {
-    float4 a, b;
-    if (src_bf16) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(src_bf16 + c * 8), f);
-      a = make_float4(f[0], f[1], f[2], f[3]);
-      b = make_float4(f[4], f[5], f[6], f[7]);
-    } else {
-      a = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8));
-      b = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8 + 4));
-    }
-    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-    x.lo[c] = a;
-    x.hi[c] = b;
-  }
-  if (norm_w) {
-    const float r = rsqrtf(consumer_sum(ss, red) / K + eps);
+  if (!norm_w) {
     for (int c = tid; c < KC; c += CONSUMER_THREADS) {
+      x.lo[c] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8));
+      x.hi[c] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8 + 4));
+    }
+    consumer_sync();
+    return;
+  }
+  float4 a[4], b[4];
+  uint4 nw[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = tid + u * CONSUMER_THREADS;
+    if (c < KC) {
+      nw[u] = *reinterpret_cast<const uint4*>(norm_w + c * 8);
+      if (src_bf16) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(src_bf16 + c * 8), f);
+        a[u] = make_float4(f[0], f[1], f[2], f[3]);
+        b[u] = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        a[u] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8));
+        b[u] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8 + 4));
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = tid + u * CONSUMER_THREADS;
+    if (c < KC)
+      ss += a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w + b[u].x * b[u].x + b[u].y * b[u].y +
+            b[u].z * b[u].z + b[u].w * b[u].w;
+  }
+  const float r = rsqrtf(consumer_sum(ss, red) / K + eps);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = tid + u * CONSUMER_THREADS;
+    if (c < KC) {
       float w[8];
-      unpack8(*reinterpret_cast<const uint4*>(norm_w + c * 8), w);
-      float4 a = x.lo[c], b = x.hi[c];
-      x.lo[c] = make_float4(a.x * r * w[0], a.y * r * w[1], a.z * r * w[2], a.w * r * w[3]);
-      x.hi[c] = make_float4(b.x * r * w[4], b.y * r * w[5], b.z * r * w[6], b.w * r * w[7]);
+      unpack8(nw[u], w);
+      x.lo[c] = make_float4(a[u].x * r * w[0], a[u].y * r * w[1], a[u].z * r * w[2], a[u].w * r * w[3]);
+      x.hi[c] = make_float4(b[u].x * r * w[4], b[u].y * r * w[5], b[u].z * r * w[6], b[u].w * r * w[7]);
     }
   }
   consumer_sync();
@@ -232,7 +256,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   uint64_t* bars = reinterpret_cast<uint64_t*>(actf + act_floats);
   float* red = reinterpret_cast<float*>(bars + 2 * nslots);  // 16 floats
   float* rope_s = red + 16;                                   // [64][2] cos/sin of this position
-  float* wts = rope_s + 128;                                  // [heads][16] attention-merge weights
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -255,15 +278,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
 
-  if (warp == NCW) {
-    // =============================================================== PRODUCER
+  if (warp >= NCW) {
+    // =============================================================== PRODUCERS
+    // producer warp pw issues the CTA-local items n with n % NPW == pw (ring slot n % nslots)
+    const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       uint32_t ps = 0, pu = 0;     // ring slot of the next item / how many times the ring wrapped
+      uint32_t pwi = 0;            // (local item counter) mod NPW
       uint32_t gmod = 0;           // (global item counter) mod G -> round-robin offset of the next phase
-      auto acquire = [&](uint32_t& dst, uint32_t& fb) {
-        if (pu > 0) mbar_wait(empty0 + 8 * ps, (pu - 1) & 1);
-        dst = ring_u32 + ps * slot_bytes; fb = full0 + 8 * ps;
+      // advance the cursor by one item; true when this producer warp owns it (then dst/fb are valid)
+      auto acquire = [&](uint32_t& dst, uint32_t& fb) -> bool {
+        const bool mine = (pwi == pw);
+        if (mine) {
+          if (pu > 0) mbar_wait(empty0 + 8 * ps, (pu - 1) & 1);
+          dst = ring_u32 + ps * slot_bytes; fb = full0 + 8 * ps;
+        }
         if (++ps == (uint32_t)nslots) { ps = 0; ++pu; }
+        if (++pwi == NPW) pwi = 0;
+        return mine;
       };
       auto stream_phase = [&](const Phase& d) {
         const uint32_t rb = (uint32_t)d.K * 2;
@@ -272,7 +304,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           int r0, r1;
           item_rows(d, it, r0, r1);
           uint32_t dst, fb;
-          acquire(dst, fb);
+          if (!acquire(dst, fb)) continue;
           if (d.mode == 0) {           // rows 2i, 2i+1 are contiguous in memory: one copy
             mbar_expect_tx(fb, 2 * rb);
             bulk_g2s(dst, d.W + (int64_t)r0 * d.K, 2 * rb, fb);
@@ -296,7 +328,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           for (int i = 0; i < as.n_items; ++i) {
             const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
             uint32_t dst, fb;
-            acquire(dst, fb);
+            if (!acquire(dst, fb)) continue;
             mbar_expect_tx(fb, (uint32_t)nk * 512);
             bulk_g2s(dst, kb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
             bulk_g2s(dst + 16 * 256, vb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
@@ -501,70 +533,50 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         pp[tid] = O;
         if (tid == 0) { pp[128] = M; pp[129] = Lt; }
       }
+      // the LAST CTA of this head to get here merges the head's partials into the normalised output
+      consumer_sync();
+      if (tid == 0) {
+        unsigned prev;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
+        red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
+      }
+      consumer_sync();
+      if (red[8] != 0.f) {
+        if (tid < 128) {
+          float ms[16], M = -INFINITY;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            ms[r] = (r < as.cph) ? ldcg_f(p.part + (int64_t)(r * p.heads + as.head) * 132 + 128) : -INFINITY;
+            M = fmaxf(M, ms[r]);
+          }
+          float ov[16], lv[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
+            ov[r] = (r < as.cph) ? ldcg_f(pp + tid) : 0.f;
+            lv[r] = (r < as.cph) ? ldcg_f(pp + 129) : 0.f;
+          }
+          float Lt = 0.f, O = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float w = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
+            Lt += lv[r] * w;
+            O += ov[r] * w;
+          }
+          p.attn[as.head * 128 + tid] = O / Lt;
+        }
+        if (tid == 0) p.head_cnt[as.head] = 0u;  // self-resetting (next use is a grid barrier away)
+      }
     }
     stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target);
     stamp(3); ++dbg_i;
 
-    // ---------------- P3: merge attention partials (all CTAs, redundantly) -> o-proj + residual
+    // ---------------- P3: o-proj + residual on the merged attention output
     stamp(0);
-    {
-      int cph = G / p.heads;
-      if (cph > 16) cph = 16;
-      // (a) normalised merge weights w[head][r] = exp2(m_r - M) / sum_r l_r exp2(m_r - M): 16 lanes per head
-      const int nW = p.heads * 16;
-      for (int t = tid; t < ((nW + 31) & ~31); t += CONSUMER_THREADS) {  // warp-uniform trip count (shuffles below)
-        const int head = t >> 4, r = t & 15;
-        float mr = -INFINITY, lr = 0.f;
-        if (t < nW && r < cph) {
-          const float* pp = p.part + (int64_t)(r * p.heads + head) * 132;
-          mr = ldcg_f(pp + 128);
-          lr = ldcg_f(pp + 129);
-        }
-        float M = mr;
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 1));
-        const float w = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
-        float Ls = lr * w;
-        Ls += __shfl_xor_sync(0xffffffffu, Ls, 8);
-        Ls += __shfl_xor_sync(0xffffffffu, Ls, 4);
-        Ls += __shfl_xor_sync(0xffffffffu, Ls, 2);
-        Ls += __shfl_xor_sync(0xffffffffu, Ls, 1);
-        if (t < nW) wts[t] = Ls > 0.f ? w / Ls : 0.f;
-      }
-      consumer_sync();
-      // (b) attention vector: all partial loads of a thread are independent -> one L2 round trip
-      X.hi = X.lo + (qd >> 3);
-      for (int e0 = tid; e0 < qd; e0 += 4 * CONSUMER_THREADS) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        float v[4][16];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * CONSUMER_THREADS;
-          const int head = e >> 7, d = e & 127;
-#pragma unroll
-          for (int r = 0; r < 16; ++r)
-            v[u][r] = (e < qd && r < cph) ? ldcg_f(p.part + (int64_t)(r * p.heads + head) * 132 + d) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * CONSUMER_THREADS;
-          if (e < qd) {
-            const int head = e >> 7;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) acc[u] += v[u][r] * wts[head * 16 + r];
-            // plane layout: element e lives in chunk e/8, position e%8 (lo: 0..3, hi: 4..7)
-            const int ch = e >> 3, w8 = e & 7;
-            float* dst = (w8 < 4) ? reinterpret_cast<float*>(X.lo + ch) + w8 : reinterpret_cast<float*>(X.hi + ch) + (w8 - 4);
-            *dst = acc[u];
-          }
-        }
-      }
-      consumer_sync();
-    }
+    X.hi = X.lo + (qd >> 3);
+    stage_vector(p.attn, nullptr, qd, nullptr, 0.f, X, red);
     stamp(1);
     run_phase(make_phase(p, l, PH_O), PH_O, l);
     stamp(2);
@@ -627,7 +639,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   if (nslots > 32) nslots = 32;
   if (nslots < 2) return cudaErrorInvalidValue;
   a.nslots = nslots;
-  if (heads > num_sms) return cudaErrorInvalidValue;
+  if (heads > num_sms || H > 8192) return cudaErrorInvalidValue;  // normed vector is register-staged (K <= 8192)
   *grid_out = num_sms;
   return cudaSuccess;
 }

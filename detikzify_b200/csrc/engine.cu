@@ -144,6 +144,7 @@ struct dtk_engine {
   SampleArgs gen_sample{};
   float* d_part = nullptr;
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
+  unsigned int* d_head_cnt = nullptr;
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
 };
@@ -555,6 +556,10 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
       m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
+      m.attn = eng->d_att;
+      DTK_ALLOC(eng->d_head_cnt, c.heads);
+      DTK_CK(cudaMemset(eng->d_head_cnt, 0, c.heads * sizeof(unsigned int)));
+      m.head_cnt = eng->d_head_cnt;
       DTK_ALLOC(eng->d_dbg, (int64_t)3 * (c.layers * 5 + 1) * 4);
       DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)3 * (c.layers * 5 + 1) * 4 * sizeof(long long)));
       m.dbg = nullptr;
@@ -578,7 +583,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);

@@ -156,6 +156,8 @@ struct MegaArgs {
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
   const float* rope_cs;
   float *x, *q, *h, *part, *logits;                           // part: [grid][132] attention partials
+  float* attn;                                                // [heads*128] merged attention output
+  unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, slot_bytes, act_floats;                         // shared-memory ring geometry (mega_configure)
   long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
