@@ -77,8 +77,9 @@ DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 // grid barrier over the consumer threads of all CTAs (producer warps never take part).
 // bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
 // cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
-DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target) {
+DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int skip = 0) {
   consumer_sync();
+  if (skip) return;
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
     uint32_t spins = 0;
@@ -397,8 +398,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       }
       if (!next_item(base, sl)) continue;
-      float a0, a1;
-      dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
+      float a0 = 0.f, a1 = 0.f;
+      if (!(p.dbg_flags & 1)) dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
       release(sl);
       if (lane == 0) {
         if (ph == PH_QKV) {
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(make_phase(p, l, PH_QKV), PH_QKV, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
     stamp(3); ++dbg_i;
 
     // ---------------- P2: attention over this CTA's key range of its head
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     }
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
     stamp(3); ++dbg_i;
 
     // ---------------- P3: o-proj + residual on the merged attention output
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(make_phase(p, l, PH_O), PH_O, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
     stamp(3); ++dbg_i;
 
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(make_phase(p, l, PH_GU), PH_GU, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
     stamp(3); ++dbg_i;
 
     // ---------------- P5: down + residual
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(make_phase(p, l, PH_DOWN), PH_DOWN, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
     stamp(3); ++dbg_i;
   }
   // ---------------- final RMSNorm + lm_head
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   run_phase(make_phase(p, 0, PH_LM), PH_LM, 0);
   stamp(2); stamp(3);
   // publish the barrier epoch for the next launch (stream-ordered): every CTA executed 5L barriers
-  if (c == 0 && tid == 0) *p.bar_base = bar_target;
+  if (c == 0 && tid == 0 && !(p.dbg_flags & 2)) *p.bar_base = bar_target;
 }
 
 }  // namespace

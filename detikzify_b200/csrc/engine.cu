@@ -147,6 +147,7 @@ struct dtk_engine {
   unsigned int* d_head_cnt = nullptr;
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
+  int mega_flags = 0;
 };
 
 namespace {
@@ -367,6 +368,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     MegaArgs m = eng->mega;
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
+    m.dbg_flags = eng->mega_flags;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -913,6 +915,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   if (std::strcmp(key, "decode_impl") == 0) {
     DTK_REQUIRE(value == 0 || value == 1, "decode_impl must be 0 (per-op) or 1 (persistent)");
     eng->decode_impl = (int)value;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "mega_flags") == 0) {  // dev only (timing experiments; results are garbage when set)
+    eng->mega_flags = (int)value;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_debug") == 0) {

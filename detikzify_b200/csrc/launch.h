@@ -160,6 +160,7 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, slot_bytes, act_floats;                         // shared-memory ring geometry (mega_configure)
+  int dbg_flags;                                              // dev only: 1 = skip dot products, 2 = skip grid barriers
   long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
 };
 int mega_smem_bytes(const MegaArgs& a);
