@@ -35,6 +35,7 @@ constexpr int NCW = 8;                       // consumer warps
 constexpr int NPW = 4;                       // producer warps (one issuing lane each): per-item issue cost ~0.3 us
 constexpr int MEGA_THREADS = (NCW + NPW) * 32;
 constexpr int CONSUMER_THREADS = NCW * 32;
+static_assert(NCW % NPW == 0, "slot ownership: NPW must divide NCW");
 constexpr long long SPIN_CYCLES = 4000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
@@ -638,7 +639,11 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   const int fixed = actf * 4 + (16 + 128 + heads * 16) * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (slot + 16);
   if (nslots > 32) nslots = 32;
-  if (nslots < 2) return cudaErrorInvalidValue;
+  // every ring slot must always be filled by the same producer warp and drained by the same consumer warp
+  // (slot s <-> producer s % NPW, consumer s % NCW): mbarrier parity waits are only alias-free when the
+  // successive uses of one barrier are ordered inside one thread.
+  nslots &= ~(NCW - 1);
+  if (nslots < NCW) return cudaErrorInvalidValue;
   a.nslots = nslots;
   if (heads > num_sms || H > 8192) return cudaErrorInvalidValue;  // normed vector is register-staged (K <= 8192)
   *grid_out = num_sms;
