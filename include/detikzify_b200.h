@@ -163,6 +163,10 @@ DTK_API uint64_t dtk_launch_count(const dtk_engine* eng);
 
 /* ---- kernel-level test hooks (used only by tests/: shape sweeps at the real model sizes
  *      without instantiating a model). All pointers are device pointers. --------------------- */
+/* dev microbenchmark: stream `bytes` of `buf` with one persistent CTA per SM. mode 0 = TMA bulk ring
+ * (chunk bytes per copy, nslots slots, ncw consumer / npw producer warps), mode 1 = 128-bit LDG. */
+DTK_API int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int chunk, int nslots, int ncw,
+                                 int npw, int read_smem, int hint, int grid, float* sink, void* stream);
 /* phase timestamps of the last persistent-kernel launch (option "mega_debug" = 1):
  * [3 CTAs][5*layers+1 phases][4] clock64 values; returns the value count */
 DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values);
