@@ -280,61 +280,72 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
 
+  // ---- item ownership. The CTA's local item sequence (all phases, in order) is dealt to agents by index:
+  // local item n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
+  // both, so a slot always has the same producer and the same consumer). An agent visits ONLY its own items.
+  struct Walk {
+    uint32_t nb = 0;     // local items before the current phase
+    uint32_t gmod = 0;   // (global item counter) mod G -> round-robin offset of the current phase
+  };
+  // items of this CTA in a weight phase: it = first + k * G, k in [0, cnt)
+  auto phase_span = [&](const Walk& w, int n_items, int& first, int& cnt) {
+    first = (int)(((uint32_t)c + (uint32_t)G - w.gmod) % (uint32_t)G);
+    cnt = first < n_items ? (n_items - 1 - first) / G + 1 : 0;
+  };
+
   if (warp >= NCW) {
     // =============================================================== PRODUCERS
-    // producer warp pw issues the CTA-local items n with n % NPW == pw (ring slot n % nslots)
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
-      uint32_t ps = 0, pu = 0;     // ring slot of the next item / how many times the ring wrapped
-      uint32_t pwi = 0;            // (local item counter) mod NPW
-      uint32_t gmod = 0;           // (global item counter) mod G -> round-robin offset of the next phase
-      // advance the cursor by one item; true when this producer warp owns it (then dst/fb are valid)
-      auto acquire = [&](uint32_t& dst, uint32_t& fb) -> bool {
-        const bool mine = (pwi == pw);
-        if (mine) {
-          if (pu > 0) mbar_wait(empty0 + 8 * ps, (pu - 1) & 1);
-          dst = ring_u32 + ps * slot_bytes; fb = full0 + 8 * ps;
+      Walk w;
+      // visit own items k = k0, k0 + NPW, ... of a phase with cnt local items
+      auto for_own = [&](int cnt, auto&& issue) {
+        uint32_t k = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
+        if ((int)k < cnt) {
+          const uint32_t n0 = w.nb + k;
+          uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
+          for (; (int)k < cnt; k += NPW) {
+            if (use > 0) mbar_wait(empty0 + 8 * sl, (use - 1) & 1);
+            issue((int)k, ring_u32 + sl * slot_bytes, full0 + 8 * sl);
+            sl += NPW;
+            if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+          }
         }
-        if (++ps == (uint32_t)nslots) { ps = 0; ++pu; }
-        if (++pwi == NPW) pwi = 0;
-        return mine;
+        w.nb += cnt;
       };
       auto stream_phase = [&](const Phase& d) {
         const uint32_t rb = (uint32_t)d.K * 2;
-        int it = (int)(((uint32_t)c + (uint32_t)G - gmod) % (uint32_t)G);
-        for (; it < d.n_items; it += G) {
+        int first, cnt;
+        phase_span(w, d.n_items, first, cnt);
+        for_own(cnt, [&](int k, uint32_t dst, uint32_t fb) {
           int r0, r1;
-          item_rows(d, it, r0, r1);
-          uint32_t dst, fb;
-          if (!acquire(dst, fb)) continue;
+          item_rows(d, first + k * G, r0, r1);
+          const bf16* src = d.W + (int64_t)r0 * d.K;
           if (d.mode == 0) {           // rows 2i, 2i+1 are contiguous in memory: one copy
             mbar_expect_tx(fb, 2 * rb);
-            bulk_g2s(dst, d.W + (int64_t)r0 * d.K, 2 * rb, fb);
+            bulk_g2s(dst, src, 2 * rb, fb);
           } else if (d.mode == 1) {
             mbar_expect_tx(fb, 2 * rb);
-            bulk_g2s(dst, d.W + (int64_t)r0 * d.K, rb, fb);
-            bulk_g2s(dst + rb, d.W + (int64_t)r1 * d.K, rb, fb);
+            bulk_g2s(dst, src, rb, fb);
+            bulk_g2s(dst + rb, src + (int64_t)64 * d.K, rb, fb);
           } else {
             mbar_expect_tx(fb, rb);
-            bulk_g2s(dst, d.W + (int64_t)r0 * d.K, rb, fb);
+            bulk_g2s(dst, src, rb, fb);
           }
-        }
-        gmod = (gmod + (uint32_t)d.n_items) % (uint32_t)G;
+        });
+        w.gmod = (w.gmod + (uint32_t)d.n_items) % (uint32_t)G;
       };
       for (int l = 0; l < p.L; ++l) {
         stream_phase(make_phase(p, l, PH_QKV));
-        // old keys/values of this CTA's (head, range): 16-key items, K rows then V rows
-        if (as.n_items > 0) {
+        {  // old keys/values of this CTA's (head, range): 16-key items, K rows then V rows
           const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
           const bf16* vb = kb + p.kv_v_offset;
-          for (int i = 0; i < as.n_items; ++i) {
+          for_own(as.n_items, [&](int i, uint32_t dst, uint32_t fb) {
             const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
-            uint32_t dst, fb;
-            if (!acquire(dst, fb)) continue;
             mbar_expect_tx(fb, (uint32_t)nk * 512);
             bulk_g2s(dst, kb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
             bulk_g2s(dst + 16 * 256, vb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
-          }
+          });
         }
         stream_phase(make_phase(p, l, PH_O));
         stream_phase(make_phase(p, l, PH_GU));
@@ -349,26 +360,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   ActView X;
   X.lo = reinterpret_cast<float4*>(actf);
   unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
-  uint32_t cs = 0, cu = 0;                       // ring slot / wrap count of the CTA's next local item
-  uint32_t cw = 0;                               // (local item counter) mod NCW -> owning consumer warp
-  uint32_t gmod = 0;
-
-  // advance the local item cursor by one item; returns true when the item belongs to this warp and
-  // yields its slot pointer (after waiting for the producer's bytes)
-  auto next_item = [&](const uint8_t*& base, uint32_t& my_slot) -> bool {
-    const bool mine = ((int)cw == warp);
-    if (mine) {
-      mbar_wait(full0 + 8 * cs, cu & 1);
-      base = ring + (size_t)cs * slot_bytes;
-      my_slot = cs;
+  Walk w;
+  // visit own items of a phase with cnt local items; body(k, smem pointer) runs after the bytes landed and
+  // must finish reading the slot before returning (the slot is released right after)
+  auto for_own = [&](int cnt, auto&& pre, auto&& body) {
+    uint32_t k = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
+    if ((int)k < cnt) {
+      const uint32_t n0 = w.nb + k;
+      uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
+      for (; (int)k < cnt; k += NCW) {
+        pre((int)k);
+        mbar_wait(full0 + 8 * sl, use & 1);
+        body((int)k, ring + (size_t)sl * slot_bytes);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * sl);
+        sl += NCW;
+        if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+      }
     }
-    if (++cs == (uint32_t)nslots) { cs = 0; ++cu; }
-    if (++cw == NCW) cw = 0;
-    return mine;
-  };
-  auto release = [&](uint32_t sl) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty0 + 8 * sl);
+    w.nb += cnt;
   };
 
   // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, barrier done}
@@ -379,62 +389,60 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   auto run_phase = [&](const Phase& d, int ph, int layer) {
     const int KC = d.K >> 3;
     X.hi = X.lo + KC;
-    int it = (int)(((uint32_t)c + (uint32_t)G - gmod) % (uint32_t)G);
-    for (; it < d.n_items; it += G) {
-      const uint8_t* base = nullptr;
-      uint32_t sl = 0;
-      int r0, r1;
-      item_rows(d, it, r0, r1);
-      // residuals are fetched before waiting on the weights so their L2 latency hides behind the wait
-      float b0 = 0.f, b1 = 0.f;
-      const bool mine_pre = ((int)cw == warp);
-      if (mine_pre && lane == 0) {
-        if (ph == PH_O) {
-          if (layer == 0) {  // residual stream starts as the token embedding
-            b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
-            b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
-          } else { b0 = ldcg_f(p.x + r0); b1 = ldcg_f(p.x + r1); }
-        } else if (ph == PH_DOWN) {
-          b0 = ldcg_f(p.x + r0);
-        }
-      }
-      if (!next_item(base, sl)) continue;
-      float a0 = 0.f, a1 = 0.f;
-      if (!(p.dbg_flags & 1)) dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
-      release(sl);
-      if (lane == 0) {
-        if (ph == PH_QKV) {
-          const int i = r0 & 127;
-          if (r0 < qd + kd) {
-            const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-            const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
-            if (r0 < qd) { p.q[r0] = y0; p.q[r1] = y1; }
-            else {
-              const int kh = (r0 - qd) >> 7;
-              bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-              dd[i] = __float2bfloat16_rn(y0);
-              dd[i + 64] = __float2bfloat16_rn(y1);
-            }
-          } else {
-            const int kh = (r0 - qd - kd) >> 7;
-            bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-            dd[i] = __float2bfloat16_rn(a0);
-            dd[i + 64] = __float2bfloat16_rn(a1);
+    int first, cnt;
+    phase_span(w, d.n_items, first, cnt);
+    int r0 = 0, r1 = 0;
+    float b0 = 0.f, b1 = 0.f;
+    for_own(cnt,
+      [&](int k) {  // before waiting on the weights: rows + residuals (their L2 latency hides behind the wait)
+        item_rows(d, first + k * G, r0, r1);
+        if (lane == 0) {
+          if (ph == PH_O) {
+            if (layer == 0) {  // residual stream starts as the token embedding
+              b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
+              b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
+            } else { b0 = ldcg_f(p.x + r0); b1 = ldcg_f(p.x + r1); }
+          } else if (ph == PH_DOWN) {
+            b0 = ldcg_f(p.x + r0);
           }
-        } else if (ph == PH_O) {
-          p.x[r0] = b0 + a0;
-          p.x[r1] = b1 + a1;
-        } else if (ph == PH_GU) {
-          p.h[it] = silu(a0) * a1;
-        } else if (ph == PH_DOWN) {
-          p.x[r0] = b0 + a0;
-        } else {
-          p.logits[r0] = a0;
-          p.logits[r1] = a1;
         }
-      }
-    }
-    gmod = (gmod + (uint32_t)d.n_items) % (uint32_t)G;
+      },
+      [&](int k, const uint8_t* base) {
+        float a0 = 0.f, a1 = 0.f;
+        if (!(p.dbg_flags & 1)) dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
+        if (lane == 0) {
+          if (ph == PH_QKV) {
+            const int i = r0 & 127;
+            if (r0 < qd + kd) {
+              const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+              const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
+              if (r0 < qd) { p.q[r0] = y0; p.q[r1] = y1; }
+              else {
+                const int kh = (r0 - qd) >> 7;
+                bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
+                dd[i] = __float2bfloat16_rn(y0);
+                dd[i + 64] = __float2bfloat16_rn(y1);
+              }
+            } else {
+              const int kh = (r0 - qd - kd) >> 7;
+              bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
+              dd[i] = __float2bfloat16_rn(a0);
+              dd[i + 64] = __float2bfloat16_rn(a1);
+            }
+          } else if (ph == PH_O) {
+            p.x[r0] = b0 + a0;
+            p.x[r1] = b1 + a1;
+          } else if (ph == PH_GU) {
+            p.h[first + k * G] = silu(a0) * a1;
+          } else if (ph == PH_DOWN) {
+            p.x[r0] = b0 + a0;
+          } else {
+            p.logits[r0] = a0;
+            p.logits[r1] = a1;
+          }
+        }
+      });
+    w.gmod = (w.gmod + (uint32_t)d.n_items) % (uint32_t)G;
   };
 
   for (int l = 0; l < p.L; ++l) {
@@ -492,10 +500,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           m = mn;
         }
       };
-      for (int i = 0; i < as.n_items; ++i) {
-        const uint8_t* base = nullptr;
-        uint32_t sl = 0;
-        if (!next_item(base, sl)) continue;
+      for_own(as.n_items, [&](int) {}, [&](int i, const uint8_t* base) {
         const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
 #pragma unroll 4
         for (int kk = 0; kk < 8; ++kk) {
@@ -508,8 +513,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           }
           key_update(kraw, vraw, valid);
         }
-        release(sl);
-      }
+      });
       if (as.last && warp == 0) key_update(knew, vnew, hw == 0);
       // merge the 16 half-warp states -> one partial per CTA
       float* sm_m = actf;            // [16]
