@@ -6,25 +6,28 @@
 // (measured 0.37 of the HBM roofline). Here the weight stream is decoupled from the dependency chain:
 //
 //   * grid = one CTA per SM, resident for the whole token (cooperative launch);
-//   * warp 8 of every CTA is a PRODUCER: it walks the CTA's statically known list of weight rows for
-//     ALL layers and phases and streams them with 1-D TMA bulk copies (cp.async.bulk, mbarrier
-//     complete_tx) into a ~176 KB shared-memory ring, never waiting for activations — weights do not
-//     depend on them — so HBM stays busy across phase boundaries;
-//   * warps 0-7 are CONSUMERS: they take ring slots in order, do the fp32-accumulated dot products
-//     against the activation vector held in shared memory and run the fused epilogues
-//     (RMSNorm prologue, RoPE + KV-cache write, SiLU*mul, residual add);
-//   * phases are separated by a hand-rolled grid barrier (monotonic atomic counter); the ring depth
-//     (~4 us of streaming per SM) covers the barrier + activation re-staging bubble;
-//   * work items are dealt round-robin over CTAs with a running offset across phases, so the
-//     cumulative bytes per CTA never differ by more than one item.
+//   * 4 PRODUCER warps per CTA walk the CTA's statically known list of weight tiles for ALL layers and
+//     phases and stream them with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a
+//     ~190 KB shared-memory ring of 8 KB slots, never waiting for activations — weights do not depend on
+//     them — so HBM stays busy across phase boundaries (measured: the ring sustains 7.2 TB/s);
+//   * 8 CONSUMER warps take tiles in order. A tile is 16 output rows x 256 k, pre-arranged in HBM
+//     (launch_retile, once at load) so that it lands in shared memory exactly in ldmatrix.x4 order; the
+//     dot products run on the tensor pipe (mma.sync m16n8k16, fp32 accumulate) with the activation vector
+//     split into bf16 hi + lo parts (x = hi + lo to 2^-17), i.e. fp32-grade GEMV at ~1/6 of the issue slots
+//     of a CUDA-core unpack+FMA loop (which measured consumer-bound);
+//   * rows are grouped so that one thread's two accumulator rows (g, g+8) are a RoPE pair (i, i+64) or a
+//     SwiGLU pair (gate_i, up_i): RMSNorm prologue, RoPE + KV-cache write, SiLU*mul and residual add are
+//     all fused; partial sums of a group's k-tiles are combined in a fixed order (deterministic);
+//   * phases are separated by a hand-rolled grid barrier (release-reduction + acquire poll); the ring
+//     depth (~4 us of streaming per SM) covers the barrier + activation re-staging bubble;
+//   * 16-row groups are dealt round-robin over CTAs with a running offset across phases, so the cumulative
+//     bytes per CTA never differ by more than one group.
 //
 // Per layer: P1 qkv(+RMSNorm, RoPE, KV write) | P2 split-KV attention (old keys streamed through the
-// same ring; the new key read after the barrier) | P3 o-proj + residual (prologue merges the attention
-// partials) | P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final RMSNorm).
+// same ring; the new key read after the barrier; last CTA of a head merges) | P3 o-proj + residual |
+// P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final RMSNorm).
 //
 // Replaces the per-token HF eager path (modeling_llama.py:303-333, ~900 launches per token).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "launch.h"
 
@@ -32,10 +35,13 @@ namespace dtk {
 namespace {
 
 constexpr int NCW = 8;                       // consumer warps
-constexpr int NPW = 4;                       // producer warps (one issuing lane each): per-item issue cost ~0.3 us
+constexpr int NPW = 4;                       // producer warps (one issuing lane each): ~500 cycles per bulk copy
 constexpr int MEGA_THREADS = (NCW + NPW) * 32;
 constexpr int CONSUMER_THREADS = NCW * 32;
 static_assert(NCW % NPW == 0, "slot ownership: NPW must divide NCW");
+constexpr int TILE_BYTES = 8192;             // ring slot = one weight tile = one 16-key K+V attention item
+constexpr int NT = 128;                      // per-tile partial-sum entries (>= max tiles/group + tiles in flight)
+constexpr int NG = 64;                       // per-group arrival counters
 constexpr long long SPIN_CYCLES = 4000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
@@ -72,13 +78,12 @@ DTK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t ba
                : "memory");
 }
 DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_THREADS) : "memory"); }
-
 DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 
 // grid barrier over the consumer threads of all CTAs (producer warps never take part).
 // bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
 // cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
-DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int skip = 0) {
+DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int skip) {
   consumer_sync();
   if (skip) return;
   if (threadIdx.x == 0) {
@@ -99,35 +104,7 @@ DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target
 }
 
 // ------------------------------------------------------------------ work description
-enum { PH_QKV = 0, PH_ATTN = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_LM = 5 };
-
-struct Phase {
-  const bf16* W;   // weight matrix [N, K]
-  int N, K;
-  int mode;        // 0: contiguous row pairs (2i, 2i+1); 1: rope pairs (i, i+64) inside 128-row groups; 2: single rows
-  int n_items;
-};
-
-DTK_DEV Phase make_phase(const MegaArgs& p, int layer, int ph) {
-  Phase d;
-  const int64_t lo = (int64_t)layer * p.layer_stride;
-  const int qd = p.heads * 128, kd = p.kv_heads * 128;
-  switch (ph) {
-    case PH_QKV: d.W = p.wqkv0 + lo; d.N = qd + 2 * kd; d.K = p.H; d.mode = 1; d.n_items = d.N / 2; break;
-    case PH_O: d.W = p.wo0 + lo; d.N = p.H; d.K = qd; d.mode = 0; d.n_items = d.N / 2; break;
-    case PH_GU: d.W = p.wgu0 + lo; d.N = 2 * p.I; d.K = p.H; d.mode = 0; d.n_items = d.N / 2; break;
-    case PH_DOWN: d.W = p.wd0 + lo; d.N = p.H; d.K = p.I; d.mode = 2; d.n_items = d.N; break;
-    default: d.W = p.lm_head; d.N = p.V; d.K = p.H; d.mode = 0; d.n_items = d.N / 2; break;
-  }
-  return d;
-}
-
-// rows of item `it`: (r0, r1); r1 < 0 for single-row items
-DTK_DEV void item_rows(const Phase& d, int it, int& r0, int& r1) {
-  if (d.mode == 0) { r0 = 2 * it; r1 = r0 + 1; }
-  else if (d.mode == 1) { r0 = (it >> 6) * 128 + (it & 63); r1 = r0 + 64; }
-  else { r0 = it; r1 = -1; }
-}
+enum { PH_QKV = 0, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_LM = 5 };
 
 // attention split: CTA c handles head c % heads, key range index c / heads (cph ranges per head)
 struct AttnSplit {
@@ -153,34 +130,6 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   return a;
 }
 
-// ------------------------------------------------------------------ consumer helpers
-// activation vector in shared memory as two float4 planes (conflict-free LDS.128): lo[c] = x[8c..8c+3], hi[c] = x[8c+4..8c+7]
-struct ActView {
-  float4* lo;
-  float4* hi;
-};
-
-DTK_DEV void dot_rows(const uint8_t* row0, const uint8_t* row1, int KC, const ActView& x, int lane, float& a0, float& a1) {
-  a0 = 0.f; a1 = 0.f;
-  const uint4* w0 = reinterpret_cast<const uint4*>(row0);
-  const uint4* w1 = reinterpret_cast<const uint4*>(row1);
-#pragma unroll 4
-  for (int c = lane; c < KC; c += 32) {
-    const uint4 v0 = w0[c];
-    const float4 xl = x.lo[c], xh = x.hi[c];
-    float f[8];
-    unpack8(v0, f);
-    a0 += f[0] * xl.x + f[1] * xl.y + f[2] * xl.z + f[3] * xl.w + f[4] * xh.x + f[5] * xh.y + f[6] * xh.z + f[7] * xh.w;
-    if (row1) {
-      const uint4 v1 = w1[c];
-      unpack8(v1, f);
-      a1 += f[0] * xl.x + f[1] * xl.y + f[2] * xl.z + f[3] * xl.w + f[4] * xh.x + f[5] * xh.y + f[6] * xh.z + f[7] * xh.w;
-    }
-  }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-}
-
 // sum over the 256 consumer threads
 DTK_DEV float consumer_sum(float v, float* red) {
   v = warp_sum(v);
@@ -193,55 +142,80 @@ DTK_DEV float consumer_sum(float v, float* red) {
   return t;
 }
 
-// stage a K-vector (optionally RMS-normalised) into the planes. src_f32 (ld.cg) or src_bf16 (embedding row).
-// With a norm the vector (K <= 8192) is held in registers: the x and norm-weight loads are issued together
-// (one L2/HBM round trip) and the scaled values are written to shared memory once.
-DTK_DEV void stage_vector(const float* src_f32, const bf16* src_bf16, int K, const bf16* norm_w, float eps,
-                          const ActView& x, float* red) {
-  const int KC = K >> 3, tid = threadIdx.x;
-  if (!norm_w) {
-    for (int c = tid; c < KC; c += CONSUMER_THREADS) {
-      x.lo[c] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8));
-      x.hi[c] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8 + 4));
-    }
-    consumer_sync();
-    return;
-  }
-  float4 a[4], b[4];
-  uint4 nw[4];
+// Stage a K-vector (optionally RMS-normalised) into shared memory as the B operand of mma.m16n8k16:
+// entry [kstep S][t] (uint4) = { hi(x[16S+2t], x[16S+2t+1]), hi(x[16S+2t+8], +9), lo(..2t..), lo(..2t+8..) }
+// where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad
+// column reads entry t = lane & 3. Entries for k >= K (padding up to Kp) are zero.
+DTK_DEV void stage_xb(const float* src_f32, const bf16* src_bf16, int K, int Kp, const bf16* norm_w, float eps,
+                      uint4* xb, float* red) {
+  const int tid = threadIdx.x, nsteps = Kp >> 4;
+  constexpr int MAXS = 2;  // k-steps held in registers per thread when normalising (K <= 8192)
+  float v[MAXS][16];
   float ss = 0.f;
+  if (norm_w) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = tid + u * CONSUMER_THREADS;
-    if (c < KC) {
-      nw[u] = *reinterpret_cast<const uint4*>(norm_w + c * 8);
-      if (src_bf16) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(src_bf16 + c * 8), f);
-        a[u] = make_float4(f[0], f[1], f[2], f[3]);
-        b[u] = make_float4(f[4], f[5], f[6], f[7]);
-      } else {
-        a[u] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8));
-        b[u] = __ldcg(reinterpret_cast<const float4*>(src_f32 + c * 8 + 4));
+    for (int u = 0; u < MAXS; ++u) {
+      const int S = tid + u * CONSUMER_THREADS;
+      if (S < nsteps) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int k = S * 16 + q4 * 4;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < K) {
+            if (src_bf16) {
+              const uint2 raw = *reinterpret_cast<const uint2*>(src_bf16 + k);
+              const float2 lo2 = unpack_bf16x2(raw.x), hi2 = unpack_bf16x2(raw.y);
+              a = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+            } else {
+              a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
+            }
+            const uint2 wr = *reinterpret_cast<const uint2*>(norm_w + k);
+            const float2 w0 = unpack_bf16x2(wr.x), w1 = unpack_bf16x2(wr.y);
+            ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            a.x *= w0.x; a.y *= w0.y; a.z *= w1.x; a.w *= w1.y;   // weight now, 1/rms after the reduction
+          }
+          v[u][q4 * 4 + 0] = a.x; v[u][q4 * 4 + 1] = a.y; v[u][q4 * 4 + 2] = a.z; v[u][q4 * 4 + 3] = a.w;
+        }
       }
     }
-  }
+    const float r = rsqrtf(consumer_sum(ss, red) / K + eps);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = tid + u * CONSUMER_THREADS;
-    if (c < KC)
-      ss += a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w + b[u].x * b[u].x + b[u].y * b[u].y +
-            b[u].z * b[u].z + b[u].w * b[u].w;
-  }
-  const float r = rsqrtf(consumer_sum(ss, red) / K + eps);
+    for (int u = 0; u < MAXS; ++u) {
+      const int S = tid + u * CONSUMER_THREADS;
+      if (S < nsteps) {
+        // HF order is (x * rsqrt) * w; here (x * w) * rsqrt — same value up to one fp32 rounding
+        uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = tid + u * CONSUMER_THREADS;
-    if (c < KC) {
-      float w[8];
-      unpack8(nw[u], w);
-      x.lo[c] = make_float4(a[u].x * r * w[0], a[u].y * r * w[1], a[u].z * r * w[2], a[u].w * r * w[3]);
-      x.hi[c] = make_float4(b[u].x * r * w[4], b[u].y * r * w[5], b[u].z * r * w[6], b[u].w * r * w[7]);
+        for (int j = 0; j < 8; ++j) {
+          const float a = v[u][2 * j] * r, b = v[u][2 * j + 1] * r;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+          hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+          lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
+      }
+    }
+  } else {
+    for (int S = tid; S < nsteps; S += CONSUMER_THREADS) {
+      float w16[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int k = S * 16 + q4 * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
+        w16[q4 * 4 + 0] = a.x; w16[q4 * 4 + 1] = a.y; w16[q4 * 4 + 2] = a.z; w16[q4 * 4 + 3] = a.w;
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = w16[2 * j], b = w16[2 * j + 1];
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
     }
   }
   consumer_sync();
@@ -251,13 +225,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x, G = gridDim.x;
-  const int nslots = p.nslots, slot_bytes = p.slot_bytes;
+  const int nslots = p.nslots;
   uint8_t* ring = smem;
-  float* actf = reinterpret_cast<float*>(smem + (size_t)nslots * slot_bytes);
-  const int act_floats = p.act_floats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(actf + act_floats);
+  float* actf = reinterpret_cast<float*>(smem + (size_t)nslots * TILE_BYTES);
+  uint4* xb = reinterpret_cast<uint4*>(actf);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(actf + p.act_floats);
   float* red = reinterpret_cast<float*>(bars + 2 * nslots);  // 16 floats
   float* rope_s = red + 16;                                   // [64][2] cos/sin of this position
+  float* tpart = rope_s + 128;                                // [NT][16] per-tile partial sums
+  int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] tiles finished per group
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -269,28 +245,28 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
-  __syncthreads();
-
   const int pos = p.pos[0], slot = p.slots[0];
   int tok = p.tok[0];
   if (tok < 0 || tok >= p.V) tok = 0;
   const int qd = p.heads * 128, kd = p.kv_heads * 128;
   if (tid < 128) rope_s[tid] = p.rope_cs[(int64_t)pos * 128 + tid];
+  if (tid < NG) gcnt[tid] = 0;
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
 
-  // ---- item ownership. The CTA's local item sequence (all phases, in order) is dealt to agents by index:
-  // local item n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
-  // both, so a slot always has the same producer and the same consumer). An agent visits ONLY its own items.
+  // ---- item ownership. The CTA's local TILE sequence (all phases, in order) is dealt to agents by index:
+  // local tile n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
+  // both, so a slot always has the same producer and the same consumer -> mbarrier parity waits never alias).
   struct Walk {
-    uint32_t nb = 0;     // local items before the current phase
-    uint32_t gmod = 0;   // (global item counter) mod G -> round-robin offset of the current phase
+    uint32_t nb = 0;     // local tiles before the current phase
+    uint32_t gb = 0;     // local groups before the current phase
+    uint32_t gmod = 0;   // (global group counter) mod G -> round-robin offset of the current phase
   };
-  // items of this CTA in a weight phase: it = first + k * G, k in [0, cnt)
-  auto phase_span = [&](const Walk& w, int n_items, int& first, int& cnt) {
+  // groups of this CTA in a weight phase: gi = first + k * G, k in [0, cnt)
+  auto phase_span = [&](const Walk& w, int n_groups, int& first, int& cnt) {
     first = (int)(((uint32_t)c + (uint32_t)G - w.gmod) % (uint32_t)G);
-    cnt = first < n_items ? (n_items - 1 - first) / G + 1 : 0;
+    cnt = first < n_groups ? (n_groups - 1 - first) / G + 1 : 0;
   };
 
   if (warp >= NCW) {
@@ -298,87 +274,84 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       Walk w;
-      // visit own items k = k0, k0 + NPW, ... of a phase with cnt local items
-      auto for_own = [&](int cnt, auto&& issue) {
-        uint32_t k = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
-        if ((int)k < cnt) {
-          const uint32_t n0 = w.nb + k;
+      // visit own tiles j = j0, j0 + NPW, ... of a phase with `ntiles` local tiles (tpg tiles per group)
+      auto for_own = [&](int ntiles, int tpg, auto&& issue) {
+        uint32_t j = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
+        if ((int)j < ntiles) {
+          const uint32_t n0 = w.nb + j;
           uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
-          for (; (int)k < cnt; k += NPW) {
+          uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
+          for (; (int)j < ntiles; j += NPW) {
             if (use > 0) mbar_wait(empty0 + 8 * sl, (use - 1) & 1);
-            issue((int)k, ring_u32 + sl * slot_bytes, full0 + 8 * sl);
+            issue((int)k, (int)ks, ring_u32 + sl * TILE_BYTES, full0 + 8 * sl);
             sl += NPW;
             if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+            ks += NPW;
+            while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
           }
         }
-        w.nb += cnt;
+        w.nb += ntiles;
       };
-      auto stream_phase = [&](const Phase& d) {
-        const uint32_t rb = (uint32_t)d.K * 2;
+      auto stream_phase = [&](const MegaMat& m, int layer) {
         int first, cnt;
-        phase_span(w, d.n_items, first, cnt);
-        for_own(cnt, [&](int k, uint32_t dst, uint32_t fb) {
-          int r0, r1;
-          item_rows(d, first + k * G, r0, r1);
-          const bf16* src = d.W + (int64_t)r0 * d.K;
-          if (d.mode == 0) {           // rows 2i, 2i+1 are contiguous in memory: one copy
-            mbar_expect_tx(fb, 2 * rb);
-            bulk_g2s(dst, src, 2 * rb, fb);
-          } else if (d.mode == 1) {
-            mbar_expect_tx(fb, 2 * rb);
-            bulk_g2s(dst, src, rb, fb);
-            bulk_g2s(dst + rb, src + (int64_t)64 * d.K, rb, fb);
-          } else {
-            mbar_expect_tx(fb, rb);
-            bulk_g2s(dst, src, rb, fb);
-          }
+        phase_span(w, m.groups, first, cnt);
+        const bf16* base = m.base + (int64_t)layer * m.layer_stride;
+        for_own(cnt * m.tpg, m.tpg, [&](int k, int ks, uint32_t dst, uint32_t fb) {
+          const int gi = first + k * G;
+          mbar_expect_tx(fb, TILE_BYTES);
+          bulk_g2s(dst, base + ((int64_t)gi * m.tpg + ks) * MEGA_TILE_ELEMS, TILE_BYTES, fb);
         });
-        w.gmod = (w.gmod + (uint32_t)d.n_items) % (uint32_t)G;
+        w.gb += cnt;
+        w.gmod = (w.gmod + (uint32_t)m.groups) % (uint32_t)G;
       };
       for (int l = 0; l < p.L; ++l) {
-        stream_phase(make_phase(p, l, PH_QKV));
+        stream_phase(p.qkv, l);
         {  // old keys/values of this CTA's (head, range): 16-key items, K rows then V rows
           const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
           const bf16* vb = kb + p.kv_v_offset;
-          for_own(as.n_items, [&](int i, uint32_t dst, uint32_t fb) {
+          for_own(as.n_items, 1, [&](int i, int, uint32_t dst, uint32_t fb) {
             const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
             mbar_expect_tx(fb, (uint32_t)nk * 512);
             bulk_g2s(dst, kb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
             bulk_g2s(dst + 16 * 256, vb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
           });
         }
-        stream_phase(make_phase(p, l, PH_O));
-        stream_phase(make_phase(p, l, PH_GU));
-        stream_phase(make_phase(p, l, PH_DOWN));
+        stream_phase(p.o, l);
+        stream_phase(p.gu, l);
+        stream_phase(p.down, l);
       }
-      stream_phase(make_phase(p, 0, PH_LM));
+      stream_phase(p.lm, 0);
     }
     return;
   }
 
   // ================================================================= CONSUMERS
-  ActView X;
-  X.lo = reinterpret_cast<float4*>(actf);
   unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
   Walk w;
-  // visit own items of a phase with cnt local items; body(k, smem pointer) runs after the bytes landed and
-  // must finish reading the slot before returning (the slot is released right after)
-  auto for_own = [&](int cnt, auto&& pre, auto&& body) {
-    uint32_t k = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
-    if ((int)k < cnt) {
-      const uint32_t n0 = w.nb + k;
+  // visit own tiles of a phase; body(j, k, ks, smem address of the slot) runs after the bytes landed and must
+  // finish READING the slot before calling release()
+  uint32_t cur_slot = 0;
+  auto release = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * cur_slot);
+  };
+  auto for_own = [&](int ntiles, int tpg, auto&& body) {
+    uint32_t j = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
+    if ((int)j < ntiles) {
+      const uint32_t n0 = w.nb + j;
       uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
-      for (; (int)k < cnt; k += NCW) {
-        pre((int)k);
+      uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
+      for (; (int)j < ntiles; j += NCW) {
         mbar_wait(full0 + 8 * sl, use & 1);
-        body((int)k, ring + (size_t)sl * slot_bytes);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * sl);
+        cur_slot = sl;
+        body((int)j, (int)k, (int)ks, sl);
         sl += NCW;
         if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+        ks += NCW;
+        while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
       }
     }
-    w.nb += cnt;
+    w.nb += ntiles;
   };
 
   // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, barrier done}
@@ -386,73 +359,109 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   int dbg_i = 0;
   auto stamp = [&](int k) { if (dbg && tid == 0) dbg[dbg_i * 4 + k] = clock64(); };
 
-  auto run_phase = [&](const Phase& d, int ph, int layer) {
-    const int KC = d.K >> 3;
-    X.hi = X.lo + KC;
+  // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a
+  // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows
+  auto run_phase = [&](const MegaMat& m, int ph, int layer) {
     int first, cnt;
-    phase_span(w, d.n_items, first, cnt);
-    int r0 = 0, r1 = 0;
-    float b0 = 0.f, b1 = 0.f;
-    for_own(cnt,
-      [&](int k) {  // before waiting on the weights: rows + residuals (their L2 latency hides behind the wait)
-        item_rows(d, first + k * G, r0, r1);
-        if (lane == 0) {
-          if (ph == PH_O) {
-            if (layer == 0) {  // residual stream starts as the token embedding
-              b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
-              b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
-            } else { b0 = ldcg_f(p.x + r0); b1 = ldcg_f(p.x + r1); }
-          } else if (ph == PH_DOWN) {
-            b0 = ldcg_f(p.x + r0);
-          }
+    phase_span(w, m.groups, first, cnt);
+    const uint32_t nb0 = w.nb, gb0 = w.gb;
+    const int tpg = m.tpg;
+    for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!(p.dbg_flags & 1)) {
+        const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
+        const uint4* xp = xb + (size_t)ks * 64 + (lane & 3);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          uint32_t a[4];
+          ldmatrix_x4(a[0], a[1], a[2], a[3], ta + s * 512);
+          const uint4 b = xp[s * 4];
+          mma_bf16_16816(acc, a, b.x, b.y);
+          mma_bf16_16816(acc, a, b.z, b.w);
         }
-      },
-      [&](int k, const uint8_t* base) {
-        float a0 = 0.f, a1 = 0.f;
-        if (!(p.dbg_flags & 1)) dot_rows(base, r1 >= 0 ? base + (size_t)d.K * 2 : nullptr, KC, X, lane, a0, a1);
-        if (lane == 0) {
-          if (ph == PH_QKV) {
-            const int i = r0 & 127;
-            if (r0 < qd + kd) {
-              const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-              const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
-              if (r0 < qd) { p.q[r0] = y0; p.q[r1] = y1; }
-              else {
-                const int kh = (r0 - qd) >> 7;
-                bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-                dd[i] = __float2bfloat16_rn(y0);
-                dd[i + 64] = __float2bfloat16_rn(y1);
-              }
-            } else {
-              const int kh = (r0 - qd - kd) >> 7;
-              bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-              dd[i] = __float2bfloat16_rn(a0);
-              dd[i + 64] = __float2bfloat16_rn(a1);
-            }
-          } else if (ph == PH_O) {
-            p.x[r0] = b0 + a0;
-            p.x[r1] = b1 + a1;
-          } else if (ph == PH_GU) {
-            p.h[first + k * G] = silu(a0) * a1;
-          } else if (ph == PH_DOWN) {
-            p.x[r0] = b0 + a0;
-          } else {
-            p.logits[r0] = a0;
-            p.logits[r1] = a1;
+      }
+      release();
+      const uint32_t n = nb0 + (uint32_t)j;
+      if ((lane & 3) == 0) {
+        float* tp = tpart + (n & (NT - 1)) * 16;
+        tp[lane >> 2] = acc[0];
+        tp[(lane >> 2) + 8] = acc[2];
+      }
+      __syncwarp();
+      int last = 0;
+      const uint32_t gslot = (gb0 + (uint32_t)k) & (NG - 1);
+      if (lane == 0) {
+        __threadfence_block();
+        last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) return;
+      __threadfence_block();
+      // ---- group epilogue (this warp saw the last tile of group k)
+      const uint32_t n0 = nb0 + (uint32_t)k * tpg;
+      float v = 0.f;
+      if (lane < 16)
+        for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) & (NT - 1)) * 16 + lane);
+      const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
+      if (lane == 0) gcnt[gslot] = 0;
+      if (lane >= 8) return;
+      const int gi = first + k * G, r = lane;
+      if (ph == PH_QKV) {
+        const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
+        const int row0 = hb * 128 + i;
+        if (row0 < qd + kd) {
+          const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+          const float y0 = v * csn.x - v1 * csn.y, y1 = v1 * csn.x + v * csn.y;
+          if (row0 < qd) { p.q[row0] = y0; p.q[row0 + 64] = y1; }
+          else {
+            const int kh = (row0 - qd) >> 7;
+            bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
+            dd[i] = __float2bfloat16_rn(y0);
+            dd[i + 64] = __float2bfloat16_rn(y1);
           }
+        } else {
+          const int kh = (row0 - qd - kd) >> 7;
+          bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
+          dd[i] = __float2bfloat16_rn(v);
+          dd[i + 64] = __float2bfloat16_rn(v1);
         }
-      });
-    w.gmod = (w.gmod + (uint32_t)d.n_items) % (uint32_t)G;
+      } else if (ph == PH_O) {
+        const int r0 = gi * 16 + r, r1 = r0 + 8;
+        float b0 = 0.f, b1 = 0.f;
+        if (layer == 0) {  // residual stream starts as the token embedding
+          if (r0 < p.H) b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
+          if (r1 < p.H) b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
+        } else {
+          if (r0 < p.H) b0 = ldcg_f(p.x + r0);
+          if (r1 < p.H) b1 = ldcg_f(p.x + r1);
+        }
+        if (r0 < p.H) p.x[r0] = b0 + v;
+        if (r1 < p.H) p.x[r1] = b1 + v1;
+      } else if (ph == PH_GU) {
+        const int i = gi * 8 + r;
+        if (i < p.I) p.h[i] = silu(v) * v1;
+      } else if (ph == PH_DOWN) {
+        const int r0 = gi * 16 + r, r1 = r0 + 8;
+        if (r0 < p.H) p.x[r0] = ldcg_f(p.x + r0) + v;
+        if (r1 < p.H) p.x[r1] = ldcg_f(p.x + r1) + v1;
+      } else {
+        const int r0 = gi * 16 + r, r1 = r0 + 8;
+        if (r0 < p.V) p.logits[r0] = v;
+        if (r1 < p.V) p.logits[r1] = v1;
+      }
+    });
+    w.gb += cnt;
+    w.gmod = (w.gmod + (uint32_t)m.groups) % (uint32_t)G;
   };
 
+  const int Hp = p.qkv.tpg * 256, Qp = p.o.tpg * 256, Ip = p.down.tpg * 256;
   for (int l = 0; l < p.L; ++l) {
-    const int64_t lo = (int64_t)l * p.layer_stride;
+    const int64_t no = (int64_t)l * p.norm_stride;
     // ---------------- P1: RMSNorm + qkv + RoPE + KV write
     stamp(0);
-    X.hi = X.lo + (p.H >> 3);
-    stage_vector(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, p.norm1_0 + lo, p.eps, X, red);
+    stage_xb(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
     stamp(1);
-    run_phase(make_phase(p, l, PH_QKV), PH_QKV, l);
+    run_phase(p.qkv, PH_QKV, l);
     stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
@@ -500,7 +509,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           m = mn;
         }
       };
-      for_own(as.n_items, [&](int) {}, [&](int i, const uint8_t* base) {
+      for_own(as.n_items, 1, [&](int i, int, int, uint32_t sl) {
+        const uint8_t* base = ring + (size_t)sl * TILE_BYTES;
         const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
 #pragma unroll 4
         for (int kk = 0; kk < 8; ++kk) {
@@ -513,6 +523,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           }
           key_update(kraw, vraw, valid);
         }
+        release();
       });
       if (as.last && warp == 0) key_update(knew, vnew, hw == 0);
       // merge the 16 half-warp states -> one partial per CTA
@@ -531,9 +542,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         float Lt = 0.f, O = 0.f;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float w = (sm_m[h] == -INFINITY) ? 0.f : exp2f(sm_m[h] - M);
-          Lt += sm_l[h] * w;
-          O += sm_o[h * 128 + tid] * w;
+          const float wgt = (sm_m[h] == -INFINITY) ? 0.f : exp2f(sm_m[h] - M);
+          Lt += sm_l[h] * wgt;
+          O += sm_o[h * 128 + tid] * wgt;
         }
         float* pp = p.part + (int64_t)c * 132;
         pp[tid] = O;
@@ -549,25 +560,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       consumer_sync();
       if (red[8] != 0.f) {
         if (tid < 128) {
-          float ms[16], M = -INFINITY;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            ms[r] = (r < as.cph) ? ldcg_f(p.part + (int64_t)(r * p.heads + as.head) * 132 + 128) : -INFINITY;
-            M = fmaxf(M, ms[r]);
-          }
-          float ov[16], lv[16];
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
-            ov[r] = (r < as.cph) ? ldcg_f(pp + tid) : 0.f;
-            lv[r] = (r < as.cph) ? ldcg_f(pp + 129) : 0.f;
-          }
+          float M = -INFINITY;
+          for (int r = 0; r < as.cph; ++r) M = fmaxf(M, ldcg_f(p.part + (int64_t)(r * p.heads + as.head) * 132 + 128));
           float Lt = 0.f, O = 0.f;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const float w = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
-            Lt += lv[r] * w;
-            O += ov[r] * w;
+          for (int r = 0; r < as.cph; ++r) {
+            const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
+            const float mr = ldcg_f(pp + 128);
+            const float wgt = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
+            Lt += ldcg_f(pp + 129) * wgt;
+            O += ldcg_f(pp + tid) * wgt;
           }
           p.attn[as.head * 128 + tid] = O / Lt;
         }
@@ -581,10 +582,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
     // ---------------- P3: o-proj + residual on the merged attention output
     stamp(0);
-    X.hi = X.lo + (qd >> 3);
-    stage_vector(p.attn, nullptr, qd, nullptr, 0.f, X, red);
+    stage_xb(p.attn, nullptr, qd, Qp, nullptr, 0.f, xb, red);
     stamp(1);
-    run_phase(make_phase(p, l, PH_O), PH_O, l);
+    run_phase(p.o, PH_O, l);
     stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
@@ -592,10 +592,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
     stamp(0);
-    X.hi = X.lo + (p.H >> 3);
-    stage_vector(p.x, nullptr, p.H, p.norm2_0 + lo, p.eps, X, red);
+    stage_xb(p.x, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red);
     stamp(1);
-    run_phase(make_phase(p, l, PH_GU), PH_GU, l);
+    run_phase(p.gu, PH_GU, l);
     stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
@@ -603,10 +602,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
     // ---------------- P5: down + residual
     stamp(0);
-    X.hi = X.lo + (p.I >> 3);
-    stage_vector(p.h, nullptr, p.I, nullptr, 0.f, X, red);
+    stage_xb(p.h, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
     stamp(1);
-    run_phase(make_phase(p, l, PH_DOWN), PH_DOWN, l);
+    run_phase(p.down, PH_DOWN, l);
     stamp(2);
     bar_target += G;
     grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
@@ -614,34 +612,68 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   }
   // ---------------- final RMSNorm + lm_head
   stamp(0);
-  X.hi = X.lo + (p.H >> 3);
-  stage_vector(p.x, nullptr, p.H, p.final_norm, p.eps, X, red);
+  stage_xb(p.x, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red);
   stamp(1);
-  run_phase(make_phase(p, 0, PH_LM), PH_LM, 0);
+  run_phase(p.lm, PH_LM, 0);
   stamp(2); stamp(3);
   // publish the barrier epoch for the next launch (stream-ordered): every CTA executed 5L barriers
   if (c == 0 && tid == 0 && !(p.dbg_flags & 2)) *p.bar_base = bar_target;
 }
 
+// ------------------------------------------------------------------ one-time weight re-tiling
+// dst chunk q (16 B) = tile (group, ks) -> [kstep s][matrix m][row r]: rows-half = m & 1, k-half = m >> 1
+__global__ void __launch_bounds__(256) retile_kernel(const bf16* __restrict__ src, int N, int K, int mode, int groups,
+                                                     int tpg, bf16* __restrict__ dst) {
+  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t total = (int64_t)groups * tpg * 512;
+  if (q >= total) return;
+  const int r = (int)(q & 7), m = (int)((q >> 3) & 3), s = (int)((q >> 5) & 15);
+  const int64_t tile = q >> 9;
+  const int ks = (int)(tile % tpg), gi = (int)(tile / tpg);
+  const int ar = (m & 1) * 8 + r;                      // A-operand row 0..15
+  const int col = ks * 256 + s * 16 + (m >> 1) * 8;
+  int row;
+  if (mode == TILE_SEQ) row = gi * 16 + ar;
+  else if (mode == TILE_ROPE) row = (gi >> 3) * 128 + ((gi & 7) << 3) + (ar & 7) + (ar >> 3) * 64;
+  else row = (ar < 8) ? 2 * (gi * 8 + ar) : 2 * (gi * 8 + ar - 8) + 1;  // source rows are interleaved (gate, up)
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < N && col < K) v = *reinterpret_cast<const uint4*>(src + (int64_t)row * K + col);
+  *reinterpret_cast<uint4*>(dst + q * 8) = v;
+}
+
 }  // namespace
 
-int mega_smem_bytes(const MegaArgs& a) { return a.nslots * a.slot_bytes + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + a.heads * 16) * 4; }
+int64_t mega_tiled_elems(int N, int K, int mode, int* groups, int* tpg) {
+  int g = (mode == TILE_GLU) ? (N / 2 + 7) / 8 : (N + 15) / 16;
+  int t = (K + 255) / 256;
+  if (groups) *groups = g;
+  if (tpg) *tpg = t;
+  return (int64_t)g * t * MEGA_TILE_ELEMS;
+}
+
+cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cudaStream_t s) {
+  if ((K & 7) || (mode == TILE_ROPE && (N & 127))) return cudaErrorInvalidValue;
+  int groups, tpg;
+  mega_tiled_elems(N, K, mode, &groups, &tpg);
+  const int64_t chunks = (int64_t)groups * tpg * 512;
+  retile_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(src, N, K, mode, groups, tpg, dst);
+  return cudaGetLastError();
+}
+
+int mega_smem_bytes(const MegaArgs& a) {
+  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4;
+}
 
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out) {
-  // slot = the largest work item: a pair of K=H rows or one K=I row; 16-key attention item = 8 KB
-  int slot = 2 * H * 2;
-  if (I * 2 > slot) slot = I * 2;
-  if (heads * 128 * 2 * 2 > slot) slot = heads * 128 * 2 * 2;  // o-proj pair (K = heads*128)
-  if (slot < 16 * 512) slot = 16 * 512;
-  slot = (slot + 127) & ~127;
-  int actf = H > I ? H : I;
-  if (heads * 128 > actf) actf = heads * 128;
+  auto pad = [](int k) { return (k + 255) / 256 * 256; };
+  int actf = pad(H) > pad(I) ? pad(H) : pad(I);
+  if (pad(heads * 128) > actf) actf = pad(heads * 128);
   if (actf < 32 + 16 * 128) actf = 32 + 16 * 128;  // attention merge scratch
   actf = (actf + 31) & ~31;
-  a.slot_bytes = slot;
   a.act_floats = actf;
-  const int fixed = actf * 4 + (16 + 128 + heads * 16) * 4 + 64;
-  int nslots = (max_smem_optin - fixed) / (slot + 16);
+  if ((I + 255) / 256 > NT - 40) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
+  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + 64;
+  int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
   if (nslots > 32) nslots = 32;
   // every ring slot must always be filled by the same producer warp and drained by the same consumer warp
   // (slot s <-> producer s % NPW, consumer s % NCW): mbarrier parity waits are only alias-free when the

@@ -145,6 +145,7 @@ struct dtk_engine {
   float* d_part = nullptr;
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
   unsigned int* d_head_cnt = nullptr;
+  bf16* d_tiled = nullptr;             // decode-side re-tiled copy of the decoder matrices
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
@@ -546,10 +547,30 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
     if (coop && mega_configure(m, c.hidden, c.inter, c.heads, smem_optin, sms, &grid) == cudaSuccess) {
       m.H = c.hidden; m.I = c.inter; m.L = c.layers; m.heads = c.heads; m.kv_heads = c.kv_heads; m.V = c.vocab;
       m.max_len = c.max_len; m.eps = c.rms_eps;
-      m.embed = W(eng, "dec.embed"); m.lm_head = W(eng, "dec.lm_head"); m.final_norm = W(eng, "dec.norm");
-      m.norm1_0 = W(eng, "dec.L0.norm1"); m.wqkv0 = W(eng, "dec.L0.wqkv"); m.wo0 = W(eng, "dec.L0.wo");
-      m.norm2_0 = W(eng, "dec.L0.norm2"); m.wgu0 = W(eng, "dec.L0.wgu"); m.wd0 = W(eng, "dec.L0.wd");
-      m.layer_stride = c.layers > 1 ? (int64_t)(W(eng, "dec.L1.norm1") - W(eng, "dec.L0.norm1")) : 0;
+      m.embed = W(eng, "dec.embed"); m.final_norm = W(eng, "dec.norm");
+      m.norm1_0 = W(eng, "dec.L0.norm1"); m.norm2_0 = W(eng, "dec.L0.norm2");
+      m.norm_stride = c.layers > 1 ? (int64_t)(W(eng, "dec.L1.norm1") - W(eng, "dec.L0.norm1")) : 0;
+      // decode-side tiled weight copy (one-time, on device): [layer][qkv | o | gu | down] ... [lm_head]
+      const int qkvN = (c.heads + 2 * c.kv_heads) * 128, qd = c.heads * 128;
+      struct Spec { MegaMat* mm; const char* name; int N, K, mode; } specs[4] = {
+          {&m.qkv, "wqkv", qkvN, c.hidden, TILE_ROPE}, {&m.o, "wo", c.hidden, qd, TILE_SEQ},
+          {&m.gu, "wgu", 2 * c.inter, c.hidden, TILE_GLU}, {&m.down, "wd", c.hidden, c.inter, TILE_SEQ}};
+      int64_t per_layer = 0, off[4];
+      for (int i = 0; i < 4; ++i) {
+        off[i] = per_layer;
+        per_layer += mega_tiled_elems(specs[i].N, specs[i].K, specs[i].mode, &specs[i].mm->groups, &specs[i].mm->tpg);
+      }
+      const int64_t lm_elems = mega_tiled_elems(c.vocab, c.hidden, TILE_SEQ, &m.lm.groups, &m.lm.tpg);
+      DTK_ALLOC(eng->d_tiled, per_layer * c.layers + lm_elems);
+      for (int i = 0; i < 4; ++i) {
+        MegaMat& mm = *specs[i].mm;
+        mm.base = eng->d_tiled + off[i]; mm.layer_stride = per_layer; mm.N = specs[i].N; mm.K = specs[i].K; mm.mode = specs[i].mode;
+        for (int l = 0; l < c.layers; ++l)
+          DTK_CK(launch_retile(W(eng, LN("dec.L", l, specs[i].name)), specs[i].N, specs[i].K, specs[i].mode,
+                               eng->d_tiled + (int64_t)l * per_layer + off[i], 0));
+      }
+      m.lm.base = eng->d_tiled + per_layer * c.layers; m.lm.layer_stride = 0; m.lm.N = c.vocab; m.lm.K = c.hidden; m.lm.mode = TILE_SEQ;
+      DTK_CK(launch_retile(W(eng, "dec.lm_head"), c.vocab, c.hidden, TILE_SEQ, eng->d_tiled + per_layer * c.layers, 0));
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
       m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
@@ -585,7 +606,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->d_tiled, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);

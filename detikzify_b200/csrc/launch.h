@@ -145,12 +145,26 @@ struct SampleArgs {
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s, uint64_t* counter);
 
 // ---------------------------------------------------------------- persistent decode kernel (B = 1)
+// Decode-side weight copy: every matrix is re-tiled once at load into 8 KB tiles of 16 rows x 256 k that a
+// single 1-D bulk copy lands in shared memory exactly as ldmatrix.x4 wants them ([kstep 16][matrix 4][row 8][8 bf16]).
+// Row groups are permuted so that the two accumulator rows (g, g+8) of one thread are a RoPE pair (i, i+64)
+// or a SwiGLU pair (gate_i, up_i).
+enum { TILE_SEQ = 0, TILE_ROPE = 1, TILE_GLU = 2 };
+constexpr int MEGA_TILE_ELEMS = 4096;  // 16 x 256 bf16 = 8 KB
+struct MegaMat {
+  const bf16* base;       // tiled copy, layer 0
+  int64_t layer_stride;   // elements between layers
+  int N, K;               // logical rows / cols of the matrix (GLU: N = 2I interleaved source rows)
+  int groups, tpg;        // 16-row groups, 256-column tiles per group
+  int mode;
+};
 struct MegaArgs {
   int H, I, L, heads, kv_heads, V, max_len;
   float eps;
-  const bf16 *embed, *lm_head, *final_norm;
-  const bf16 *norm1_0, *wqkv0, *wo0, *norm2_0, *wgu0, *wd0;  // layer-0 tensors; layer l = ptr + l * layer_stride
-  int64_t layer_stride;                                       // elements between consecutive layers in the arena
+  const bf16 *embed, *final_norm;
+  const bf16 *norm1_0, *norm2_0;                               // row-major arena; layer l = ptr + l * norm_stride
+  int64_t norm_stride;
+  MegaMat qkv, o, gu, down, lm;
   const int *tok, *pos, *slots;                               // device state of the sequence being decoded
   bf16* kv;
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
@@ -159,13 +173,16 @@ struct MegaArgs {
   float* attn;                                                // [heads*128] merged attention output
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
-  int nslots, slot_bytes, act_floats;                         // shared-memory ring geometry (mega_configure)
-  int dbg_flags;                                              // dev only: 1 = skip dot products, 2 = skip grid barriers
+  int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
+  int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers
   long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
 };
 int mega_smem_bytes(const MegaArgs& a);
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out);
 cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint64_t* counter);
+// one-time re-tiling of a row-major [N, K] (ld = K) matrix into the decode layout
+int64_t mega_tiled_elems(int N, int K, int mode, int* groups, int* tpg);
+cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cudaStream_t s);
 
 // single-query attention of the SigLIP attention-pool head: q fp32 [heads*72] (shared by all images),
 // kv bf16 [B*N, 2*D] -> out bf16 [B, D]
