@@ -83,16 +83,18 @@ DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 // grid barrier over the consumer threads of all CTAs (producer warps never take part).
 // bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
 // cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
-DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int skip) {
+DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int flags) {
   consumer_sync();
-  if (skip) return;
+  if (flags & 2) return;
   if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
+    if (flags & 4) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
+    else asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
     uint32_t spins = 0;
     long long t0 = 0;
     unsigned long long v;
     do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
+      if (flags & 8) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
+      else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
       if (v < target && (++spins & 1023u) == 0) {
         const long long now = clock64();
         if (t0 == 0) t0 = now;
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(p.qkv, PH_QKV, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
 
     // ---------------- P2: attention over this CTA's key range of its head
@@ -560,15 +562,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       consumer_sync();
       if (red[8] != 0.f) {
         if (tid < 128) {
-          float M = -INFINITY;
-          for (int r = 0; r < as.cph; ++r) M = fmaxf(M, ldcg_f(p.part + (int64_t)(r * p.heads + as.head) * 132 + 128));
-          float Lt = 0.f, O = 0.f;
-          for (int r = 0; r < as.cph; ++r) {
+          float ms[16], lv[16], ov[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {   // all loads are independent: one L2 round trip
             const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
-            const float mr = ldcg_f(pp + 128);
-            const float wgt = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
-            Lt += ldcg_f(pp + 129) * wgt;
-            O += ldcg_f(pp + tid) * wgt;
+            const bool ok = r < as.cph;
+            ms[r] = ok ? ldcg_f(pp + 128) : -INFINITY;
+            lv[r] = ok ? ldcg_f(pp + 129) : 0.f;
+            ov[r] = ok ? ldcg_f(pp + tid) : 0.f;
+          }
+          float M = -INFINITY;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) M = fmaxf(M, ms[r]);
+          float Lt = 0.f, O = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float wgt = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
+            Lt += lv[r] * wgt;
+            O += ov[r] * wgt;
           }
           p.attn[as.head * 128 + tid] = O / Lt;
         }
@@ -577,7 +588,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     }
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
 
     // ---------------- P3: o-proj + residual on the merged attention output
@@ -587,7 +598,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(p.o, PH_O, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
 
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(p.gu, PH_GU, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
 
     // ---------------- P5: down + residual
@@ -607,7 +618,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     run_phase(p.down, PH_DOWN, l);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags & 2);
+    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
   }
   // ---------------- final RMSNorm + lm_head

@@ -21,7 +21,7 @@ for _ in range(20):
     eng.decode([slot], [ctx], tok)
 ev1.record(); torch.cuda.synchronize()
 print("ms/token (incl tok copy kernel):", ev0.elapsed_time(ev1) / 20)
-for flags in (1, 2, 3, 0):
+for flags in (1, 2, 3, 4, 8, 12, 0):
     eng.set_option("mega_flags", flags)
     for _ in range(3):
         eng.decode([slot], [ctx], tok)
@@ -30,7 +30,7 @@ for flags in (1, 2, 3, 0):
     for _ in range(10):
         eng.decode([slot], [ctx], tok)
     ev1.record(); torch.cuda.synchronize()
-    print(f"flags={flags} (1=no dot, 2=no grid barrier): ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
+    print(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive, 8=relaxed poll): ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
