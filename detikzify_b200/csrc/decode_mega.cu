@@ -78,31 +78,50 @@ DTK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t ba
                : "memory");
 }
 DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_THREADS) : "memory"); }
-DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 
-// grid barrier over the consumer threads of all CTAs (producer warps never take part).
-// bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
-// cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
-DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int flags) {
-  consumer_sync();
-  if (flags & 2) return;
-  if (threadIdx.x == 0) {
-    if (flags & 4) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
-    else asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
-    uint32_t spins = 0;
-    long long t0 = 0;
-    unsigned long long v;
-    do {
-      if (flags & 8) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
-      else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
-      if (v < target && (++spins & 1023u) == 0) {
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > SPIN_CYCLES) __trap();
-      }
-    } while (v < target);
+// ---- data-carried synchronisation. A cross-CTA value is an 8-byte {fp32 bits, tag} pair: aligned 8-byte
+// accesses are single-copy atomic, so a reader sees the old or the new pair, never a mix. Writers use one
+// plain store; readers poll the L2 copy (ld.cg) until the tag of the expected phase shows up. Write-after-read
+// hazards are excluded by the data-flow itself (a buffer is only rewritten by work that transitively depends
+// on every reader of the previous version; see DESIGN.md "decode synchronisation").
+DTK_DEV void st_tag(uint2* p, float v, uint32_t tag) {
+  asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+struct Spin {
+  uint32_t n = 0;
+  long long t0 = 0;
+  DTK_DEV void tick() {
+    if ((++n & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPIN_CYCLES) __trap();
+    }
   }
-  consumer_sync();
+};
+DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
+  Spin sp;
+  uint2 u = __ldcg(p);
+  while (u.y != tag && !nowait) { sp.tick(); __nanosleep(32); u = __ldcg(p); }
+  return __uint_as_float(u.x);
+}
+// 8 consecutive tagged elements (64 B). To keep the polling traffic of 148 x 256 waiting threads off the L2
+// (the weight stream shares it), only the last element is polled (one 32-byte sector per attempt, with a short
+// back-off); once it carries the tag the whole line is fetched with four loads in flight and re-verified.
+DTK_DEV void ld_tag8(const uint2* p, uint32_t tag, int nowait, float (&out)[8]) {
+  Spin sp;
+  if (!nowait) {
+    uint2 probe = __ldcg(p + 7);
+    while (probe.y != tag) { sp.tick(); __nanosleep(32); probe = __ldcg(p + 7); }
+  }
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+  while (!nowait && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
+    sp.tick();
+    __nanosleep(32);
+    a = __ldcg(q); b = __ldcg(q + 1); c = __ldcg(q + 2); d = __ldcg(q + 3);
+  }
+  out[0] = __uint_as_float(a.x); out[1] = __uint_as_float(a.z); out[2] = __uint_as_float(b.x); out[3] = __uint_as_float(b.z);
+  out[4] = __uint_as_float(c.x); out[5] = __uint_as_float(c.z); out[6] = __uint_as_float(d.x); out[7] = __uint_as_float(d.z);
 }
 
 // ------------------------------------------------------------------ work description
@@ -148,35 +167,65 @@ DTK_DEV float consumer_sum(float v, float* red) {
 // entry [kstep S][t] (uint4) = { hi(x[16S+2t], x[16S+2t+1]), hi(x[16S+2t+8], +9), lo(..2t..), lo(..2t+8..) }
 // where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad
 // column reads entry t = lane & 3. Entries for k >= K (padding up to Kp) are zero.
-DTK_DEV void stage_xb(const float* src_f32, const bf16* src_bf16, int K, int Kp, const bf16* norm_w, float eps,
-                      uint4* xb, float* red) {
+DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* src_bf16, int K, int Kp, const bf16* norm_w,
+                      float eps, uint4* xb, float* red) {
   const int tid = threadIdx.x, nsteps = Kp >> 4;
+  consumer_sync();         // every warp of the CTA is done reading the previous phase's xb
   constexpr int MAXS = 2;  // k-steps held in registers per thread when normalising (K <= 8192)
   float v[MAXS][16];
   float ss = 0.f;
   if (norm_w) {
+    // norm weights do not depend on other CTAs: fetch them first so their latency overlaps the tag polling
+    uint4 nw[MAXS][2];
+#pragma unroll
+    for (int u = 0; u < MAXS; ++u) {
+      const int S = tid + u * CONSUMER_THREADS;
+      nw[u][0] = nw[u][1] = make_uint4(0, 0, 0, 0);
+      if (S < nsteps && S * 16 < K) {
+        nw[u][0] = *reinterpret_cast<const uint4*>(norm_w + S * 16);
+        nw[u][1] = *reinterpret_cast<const uint4*>(norm_w + S * 16 + 8);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < MAXS; ++u) {
       const int S = tid + u * CONSUMER_THREADS;
       if (S < nsteps) {
+        float x16[16];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int k = S * 16 + q4 * 4;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < K) {
-            if (src_bf16) {
-              const uint2 raw = *reinterpret_cast<const uint2*>(src_bf16 + k);
-              const float2 lo2 = unpack_bf16x2(raw.x), hi2 = unpack_bf16x2(raw.y);
-              a = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
-            } else {
-              a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
-            }
-            const uint2 wr = *reinterpret_cast<const uint2*>(norm_w + k);
-            const float2 w0 = unpack_bf16x2(wr.x), w1 = unpack_bf16x2(wr.y);
-            ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-            a.x *= w0.x; a.y *= w0.y; a.z *= w1.x; a.w *= w1.y;   // weight now, 1/rms after the reduction
+        for (int i = 0; i < 16; ++i) x16[i] = 0.f;
+        if (S * 16 < K) {   // K is a multiple of 16 for every normed vector (hidden size)
+          if (src_bf16) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(src_bf16 + S * 16), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x16[i] = f[i];
+            unpack8(*reinterpret_cast<const uint4*>(src_bf16 + S * 16 + 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x16[8 + i] = f[i];
+          } else {
+            float f[8];
+            ld_tag8(src_t + S * 16, tag, nowait, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x16[i] = f[i];
+            ld_tag8(src_t + S * 16 + 8, tag, nowait, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x16[8 + i] = f[i];
           }
-          v[u][q4 * 4 + 0] = a.x; v[u][q4 * 4 + 1] = a.y; v[u][q4 * 4 + 2] = a.z; v[u][q4 * 4 + 3] = a.w;
+        }
+        float wv[16];
+        {
+          float f[8];
+          unpack8(nw[u][0], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[i] = f[i];
+          unpack8(nw[u][1], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[8 + i] = f[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          ss += x16[i] * x16[i];
+          v[u][i] = x16[i] * wv[i];   // weight now, 1/rms after the reduction
         }
       }
     }
@@ -202,11 +251,16 @@ DTK_DEV void stage_xb(const float* src_f32, const bf16* src_bf16, int K, int Kp,
     for (int S = tid; S < nsteps; S += CONSUMER_THREADS) {
       float w16[16];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int k = S * 16 + q4 * 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < K) a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
-        w16[q4 * 4 + 0] = a.x; w16[q4 * 4 + 1] = a.y; w16[q4 * 4 + 2] = a.z; w16[q4 * 4 + 3] = a.w;
+      for (int i = 0; i < 16; ++i) w16[i] = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int k = S * 16 + half * 8;
+        if (k < K) {    // K is a multiple of 8
+          float f[8];
+          ld_tag8(src_t + k, tag, nowait, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w16[half * 8 + i] = f[i];
+        }
       }
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -222,6 +276,9 @@ DTK_DEV void stage_xb(const float* src_f32, const bf16* src_bf16, int K, int Kp,
   }
   consumer_sync();
 }
+
+// epoch tags of one launch: tag(l, k) = base + 8 l + k + 1
+enum { TG_QKV = 0, TG_PART = 1, TG_ATTN = 2, TG_XO = 3, TG_H = 4, TG_XD = 5 };
 
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -256,19 +313,26 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
+  const int nowait = p.dbg_flags & 2;
 
-  // ---- item ownership. The CTA's local TILE sequence (all phases, in order) is dealt to agents by index:
-  // local tile n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
-  // both, so a slot always has the same producer and the same consumer -> mbarrier parity waits never alias).
+  // ---- work assignment. A weight phase with `groups` 16-row groups is cut into equal blocks of
+  // per = ceil(groups / G) groups; only ceil(groups / per) CTAs take part (all with the same amount of work, so
+  // they finish together), the others idle for that phase while their producers prefetch ahead. The set of
+  // participating CTAs rotates from phase to phase. The CTA's local TILE sequence (all phases, in order) is
+  // dealt to agents by index: local tile n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW
+  // (nslots is a multiple of both: a slot always has the same producer and consumer, so mbarrier parity waits
+  // never alias).
   struct Walk {
     uint32_t nb = 0;     // local tiles before the current phase
     uint32_t gb = 0;     // local groups before the current phase
-    uint32_t gmod = 0;   // (global group counter) mod G -> round-robin offset of the current phase
+    uint32_t rot = 0;    // rotation of the participating CTA set
   };
-  // groups of this CTA in a weight phase: gi = first + k * G, k in [0, cnt)
-  auto phase_span = [&](const Walk& w, int n_groups, int& first, int& cnt) {
-    first = (int)(((uint32_t)c + (uint32_t)G - w.gmod) % (uint32_t)G);
-    cnt = first < n_groups ? (n_groups - 1 - first) / G + 1 : 0;
+  auto phase_span = [&](const Walk& w, int groups, int& g0, int& cnt, int& nact) {
+    const int per = (groups + G - 1) / G;
+    nact = (groups + per - 1) / per;
+    const int ci = (int)(((uint32_t)c + (uint32_t)G - w.rot) % (uint32_t)G);
+    g0 = ci * per;
+    cnt = (ci < nact) ? min(per, groups - g0) : 0;
   };
 
   if (warp >= NCW) {
@@ -295,16 +359,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         w.nb += ntiles;
       };
       auto stream_phase = [&](const MegaMat& m, int layer) {
-        int first, cnt;
-        phase_span(w, m.groups, first, cnt);
+        int g0, cnt, nact;
+        phase_span(w, m.groups, g0, cnt, nact);
         const bf16* base = m.base + (int64_t)layer * m.layer_stride;
         for_own(cnt * m.tpg, m.tpg, [&](int k, int ks, uint32_t dst, uint32_t fb) {
-          const int gi = first + k * G;
           mbar_expect_tx(fb, TILE_BYTES);
-          bulk_g2s(dst, base + ((int64_t)gi * m.tpg + ks) * MEGA_TILE_ELEMS, TILE_BYTES, fb);
+          bulk_g2s(dst, base + ((int64_t)(g0 + k) * m.tpg + ks) * MEGA_TILE_ELEMS, TILE_BYTES, fb);
         });
         w.gb += cnt;
-        w.gmod = (w.gmod + (uint32_t)m.groups) % (uint32_t)G;
+        w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
       };
       for (int l = 0; l < p.L; ++l) {
         stream_phase(p.qkv, l);
@@ -328,15 +391,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   }
 
   // ================================================================= CONSUMERS
-  unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
+  const uint32_t tag0 = (uint32_t)(*p.epoch);   // tags of this launch: tag0 + 8 l + k + 1
+  auto TAG = [&](int l, int k) -> uint32_t { return tag0 + (uint32_t)(8 * l + k + 1); };
   Walk w;
-  // visit own tiles of a phase; body(j, k, ks, smem address of the slot) runs after the bytes landed and must
-  // finish READING the slot before calling release()
   uint32_t cur_slot = 0;
   auto release = [&]() {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * cur_slot);
   };
+  // visit own tiles of a phase; body(j, k, ks, slot) runs after the bytes landed and must finish READING the slot
+  // before calling release()
   auto for_own = [&](int ntiles, int tpg, auto&& body) {
     uint32_t j = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
     if ((int)j < ntiles) {
@@ -356,18 +420,22 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     w.nb += ntiles;
   };
 
-  // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, barrier done}
+  // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, items done}
   long long* dbg = (p.dbg && (c == 0 || c == G / 2 || c == G - 1)) ? p.dbg + (int64_t)(c == 0 ? 0 : (c == G - 1 ? 2 : 1)) * (p.L * 5 + 1) * 4 : nullptr;
   int dbg_i = 0;
   auto stamp = [&](int k) { if (dbg && tid == 0) dbg[dbg_i * 4 + k] = clock64(); };
 
-  // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a
-  // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows
-  auto run_phase = [&](const MegaMat& m, int ph, int layer) {
-    int first, cnt;
-    phase_span(w, m.groups, first, cnt);
+  // one weight phase. stage(): fills xb (only called when this CTA has work in the phase). Every tile = 16
+  // k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a group's last tile sums the group's
+  // partials in k order and runs the epilogue for its 16 rows.
+  auto run_phase = [&](const MegaMat& m, int ph, int layer, auto&& stage) {
+    int g0, cnt, nact;
+    phase_span(w, m.groups, g0, cnt, nact);
     const uint32_t nb0 = w.nb, gb0 = w.gb;
     const int tpg = m.tpg;
+    stamp(0);
+    if (cnt > 0) stage();
+    stamp(1);
     for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (!(p.dbg_flags & 1)) {
@@ -407,25 +475,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
       if (lane == 0) gcnt[gslot] = 0;
       if (lane >= 8) return;
-      const int gi = first + k * G, r = lane;
+      const int gi = g0 + k, r = lane;
       if (ph == PH_QKV) {
         const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
         const int row0 = hb * 128 + i;
+        const uint32_t tg = TAG(layer, TG_QKV);
         if (row0 < qd + kd) {
           const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
           const float y0 = v * csn.x - v1 * csn.y, y1 = v1 * csn.x + v * csn.y;
-          if (row0 < qd) { p.q[row0] = y0; p.q[row0 + 64] = y1; }
+          if (row0 < qd) { st_tag(p.qt + row0, y0, tg); st_tag(p.qt + row0 + 64, y1, tg); }
           else {
             const int kh = (row0 - qd) >> 7;
             bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-            dd[i] = __float2bfloat16_rn(y0);
-            dd[i + 64] = __float2bfloat16_rn(y1);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+            dd[i] = h0;
+            dd[i + 64] = h1;
+            st_tag(p.kvt + kh * 128 + i, __bfloat162float(h0), tg);       // this token's key for the attention CTAs
+            st_tag(p.kvt + kh * 128 + i + 64, __bfloat162float(h1), tg);
           }
         } else {
           const int kh = (row0 - qd - kd) >> 7;
           bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-          dd[i] = __float2bfloat16_rn(v);
-          dd[i + 64] = __float2bfloat16_rn(v1);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v), h1 = __float2bfloat16_rn(v1);
+          dd[i] = h0;
+          dd[i + 64] = h1;
+          st_tag(p.kvt + kd + kh * 128 + i, __bfloat162float(h0), tg);
+          st_tag(p.kvt + kd + kh * 128 + i + 64, __bfloat162float(h1), tg);
         }
       } else if (ph == PH_O) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
@@ -434,40 +509,39 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           if (r0 < p.H) b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
           if (r1 < p.H) b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
         } else {
-          if (r0 < p.H) b0 = ldcg_f(p.x + r0);
-          if (r1 < p.H) b1 = ldcg_f(p.x + r1);
+          const uint32_t tprev = TAG(layer - 1, TG_XD);
+          if (r0 < p.H) b0 = ld_tag(p.xt + r0, tprev, nowait);
+          if (r1 < p.H) b1 = ld_tag(p.xt + r1, tprev, nowait);
         }
-        if (r0 < p.H) p.x[r0] = b0 + v;
-        if (r1 < p.H) p.x[r1] = b1 + v1;
+        if (r0 < p.H) st_tag(p.xt + r0, b0 + v, TAG(layer, TG_XO));
+        if (r1 < p.H) st_tag(p.xt + r1, b1 + v1, TAG(layer, TG_XO));
       } else if (ph == PH_GU) {
         const int i = gi * 8 + r;
-        if (i < p.I) p.h[i] = silu(v) * v1;
+        if (i < p.I) st_tag(p.ht + i, silu(v) * v1, TAG(layer, TG_H));
       } else if (ph == PH_DOWN) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        if (r0 < p.H) p.x[r0] = ldcg_f(p.x + r0) + v;
-        if (r1 < p.H) p.x[r1] = ldcg_f(p.x + r1) + v1;
+        const uint32_t tprev = TAG(layer, TG_XO);
+        if (r0 < p.H) st_tag(p.xt + r0, ld_tag(p.xt + r0, tprev, nowait) + v, TAG(layer, TG_XD));
+        if (r1 < p.H) st_tag(p.xt + r1, ld_tag(p.xt + r1, tprev, nowait) + v1, TAG(layer, TG_XD));
       } else {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
         if (r0 < p.V) p.logits[r0] = v;
         if (r1 < p.V) p.logits[r1] = v1;
       }
     });
+    stamp(2); stamp(3); ++dbg_i;
     w.gb += cnt;
-    w.gmod = (w.gmod + (uint32_t)m.groups) % (uint32_t)G;
+    w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
   };
 
   const int Hp = p.qkv.tpg * 256, Qp = p.o.tpg * 256, Ip = p.down.tpg * 256;
   for (int l = 0; l < p.L; ++l) {
     const int64_t no = (int64_t)l * p.norm_stride;
     // ---------------- P1: RMSNorm + qkv + RoPE + KV write
-    stamp(0);
-    stage_xb(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
-    stamp(1);
-    run_phase(p.qkv, PH_QKV, l);
-    stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
-    stamp(3); ++dbg_i;
+    run_phase(p.qkv, PH_QKV, l, [&]() {
+      stage_xb(p.xt, l == 0 ? 0u : TAG(l - 1, TG_XD), nowait, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp,
+               p.norm1_0 + no, p.eps, xb, red);
+    });
 
     // ---------------- P2: attention over this CTA's key range of its head
     stamp(0); stamp(1);
@@ -475,25 +549,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const int hw = lane >> 4, l16 = lane & 15;
       const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
       float q[8];
-      {
-        const float* qp = p.q + as.head * 128 + l16 * 8;
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(qp)), b = __ldcg(reinterpret_cast<const float4*>(qp + 4));
-        q[0] = a.x * sl2; q[1] = a.y * sl2; q[2] = a.z * sl2; q[3] = a.w * sl2;
-        q[4] = b.x * sl2; q[5] = b.y * sl2; q[6] = b.z * sl2; q[7] = b.w * sl2;
-      }
-      // the key/value of the token being decoded (written in P1 of this launch): fetch early
-      uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
-      if (as.last && warp == 0) {
-        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + pos) * 128;
-        knew = __ldcg(reinterpret_cast<const uint4*>(kb + l16 * 8));
-        vnew = __ldcg(reinterpret_cast<const uint4*>(kb + p.kv_v_offset + l16 * 8));
-      }
+      ld_tag8(p.qt + as.head * 128 + l16 * 8, TAG(l, TG_QKV), nowait, q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] *= sl2;
       float m = -INFINITY, lsum = 0.f, o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
-      auto key_update = [&](const uint4& kraw, const uint4& vraw, bool valid) {
-        float kf[8];
-        unpack8(kraw, kf);
+      auto key_update = [&](const float (&kf)[8], const float (&vf)[8], bool valid) {
         float s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
@@ -503,8 +565,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         if (valid) {
           const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
-          float vf[8];
-          unpack8(vraw, vf);
           lsum = lsum * alpha + pj;
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * vf[i];
@@ -518,21 +578,29 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         for (int kk = 0; kk < 8; ++kk) {
           const int key = kk * 2 + hw;
           const bool valid = key < nk;
-          uint4 kraw = make_uint4(0, 0, 0, 0), vraw = make_uint4(0, 0, 0, 0);
+          float kf[8], vf[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { kf[e] = 0.f; vf[e] = 0.f; }
           if (valid) {
-            kraw = *reinterpret_cast<const uint4*>(base + key * 256 + l16 * 16);
-            vraw = *reinterpret_cast<const uint4*>(base + 16 * 256 + key * 256 + l16 * 16);
+            unpack8(*reinterpret_cast<const uint4*>(base + key * 256 + l16 * 16), kf);
+            unpack8(*reinterpret_cast<const uint4*>(base + 16 * 256 + key * 256 + l16 * 16), vf);
           }
-          key_update(kraw, vraw, valid);
+          key_update(kf, vf, valid);
         }
         release();
       });
-      if (as.last && warp == 0) key_update(knew, vnew, hw == 0);
+      if (as.last && warp == 0) {   // the key/value of the token being decoded (produced in P1 of this launch)
+        float kf[8], vf[8];
+        ld_tag8(p.kvt + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, kf);
+        ld_tag8(p.kvt + kd + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, vf);
+        key_update(kf, vf, hw == 0);
+      }
       // merge the 16 half-warp states -> one partial per CTA
       float* sm_m = actf;            // [16]
       float* sm_l = actf + 16;       // [16]
       float* sm_o = actf + 32;       // [16][128]
       const int hidx = warp * 2 + hw;
+      consumer_sync();               // the scratch aliases xb: all warps are done with the previous phase's tiles
       if (l16 == 0) { sm_m[hidx] = m; sm_l[hidx] = lsum; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) sm_o[hidx * 128 + l16 * 8 + i] = o[i];
@@ -548,87 +616,65 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           Lt += sm_l[h] * wgt;
           O += sm_o[h * 128 + tid] * wgt;
         }
-        float* pp = p.part + (int64_t)c * 132;
-        pp[tid] = O;
-        if (tid == 0) { pp[128] = M; pp[129] = Lt; }
-      }
-      // the LAST CTA of this head to get here merges the head's partials into the normalised output
-      consumer_sync();
-      if (tid == 0) {
-        unsigned prev;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
-        red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
-      }
-      consumer_sync();
-      if (red[8] != 0.f) {
-        if (tid < 128) {
+        if (!as.last) {
+          // publish this CTA's partial (m, l, o[128]) for the head's merger
+          uint2* pp = p.partt + (int64_t)c * 132;
+          const uint32_t tg = TAG(l, TG_PART);
+          st_tag(pp + tid, O, tg);
+          if (tid == 0) { st_tag(pp + 128, M, tg); st_tag(pp + 129, Lt, tg); }
+        } else {
+          // the CTA that also owns the newest key merges the head: poll the other ranges' partials
+          const uint32_t tg = TAG(l, TG_PART);
           float ms[16], lv[16], ov[16];
 #pragma unroll
-          for (int r = 0; r < 16; ++r) {   // all loads are independent: one L2 round trip
-            const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
-            const bool ok = r < as.cph;
-            ms[r] = ok ? ldcg_f(pp + 128) : -INFINITY;
-            lv[r] = ok ? ldcg_f(pp + 129) : 0.f;
-            ov[r] = ok ? ldcg_f(pp + tid) : 0.f;
-          }
-          float M = -INFINITY;
+          for (int r = 0; r < 16; ++r) { ms[r] = -INFINITY; lv[r] = 0.f; ov[r] = 0.f; }
+          Spin sp;
+          bool ok = false;
+          while (!ok) {
+            ok = true;
 #pragma unroll
-          for (int r = 0; r < 16; ++r) M = fmaxf(M, ms[r]);
-          float Lt = 0.f, O = 0.f;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const float wgt = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
-            Lt += lv[r] * wgt;
-            O += ov[r] * wgt;
+            for (int r = 0; r < 15; ++r) {
+              if (r < as.cph - 1) {
+                const uint2* pp = p.partt + (int64_t)(r * p.heads + as.head) * 132;
+                const uint2 a = __ldcg(pp + 128), b = __ldcg(pp + 129), d = __ldcg(pp + tid);
+                ok = ok && a.y == tg && b.y == tg && d.y == tg;
+                ms[r] = __uint_as_float(a.x); lv[r] = __uint_as_float(b.x); ov[r] = __uint_as_float(d.x);
+              }
+            }
+            if (nowait) break;
+            if (!ok) { sp.tick(); __nanosleep(32); }
           }
-          p.attn[as.head * 128 + tid] = O / Lt;
+          float MM = M;
+#pragma unroll
+          for (int r = 0; r < 15; ++r) if (r < as.cph - 1) MM = fmaxf(MM, ms[r]);
+          const float wown = (M == -INFINITY) ? 0.f : exp2f(M - MM);
+          float LL = Lt * wown, OO = O * wown;
+#pragma unroll
+          for (int r = 0; r < 15; ++r) {
+            if (r < as.cph - 1) {
+              const float wgt = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - MM);
+              LL += lv[r] * wgt;
+              OO += ov[r] * wgt;
+            }
+          }
+          st_tag(p.attnt + as.head * 128 + tid, OO / LL, TAG(l, TG_ATTN));
         }
-        if (tid == 0) p.head_cnt[as.head] = 0u;  // self-resetting (next use is a grid barrier away)
       }
+      consumer_sync();   // sm_* scratch (aliases xb) is free again
     }
-    stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
-    stamp(3); ++dbg_i;
+    stamp(2); stamp(3); ++dbg_i;
 
     // ---------------- P3: o-proj + residual on the merged attention output
-    stamp(0);
-    stage_xb(p.attn, nullptr, qd, Qp, nullptr, 0.f, xb, red);
-    stamp(1);
-    run_phase(p.o, PH_O, l);
-    stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
-    stamp(3); ++dbg_i;
-
+    run_phase(p.o, PH_O, l, [&]() { stage_xb(p.attnt, TAG(l, TG_ATTN), nowait, nullptr, qd, Qp, nullptr, 0.f, xb, red); });
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
-    stamp(0);
-    stage_xb(p.x, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red);
-    stamp(1);
-    run_phase(p.gu, PH_GU, l);
-    stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
-    stamp(3); ++dbg_i;
-
+    run_phase(p.gu, PH_GU, l, [&]() { stage_xb(p.xt, TAG(l, TG_XO), nowait, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red); });
     // ---------------- P5: down + residual
-    stamp(0);
-    stage_xb(p.h, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
-    stamp(1);
-    run_phase(p.down, PH_DOWN, l);
-    stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
-    stamp(3); ++dbg_i;
+    run_phase(p.down, PH_DOWN, l, [&]() { stage_xb(p.ht, TAG(l, TG_H), nowait, nullptr, p.I, Ip, nullptr, 0.f, xb, red); });
   }
   // ---------------- final RMSNorm + lm_head
-  stamp(0);
-  stage_xb(p.x, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red);
-  stamp(1);
-  run_phase(p.lm, PH_LM, 0);
-  stamp(2); stamp(3);
-  // publish the barrier epoch for the next launch (stream-ordered): every CTA executed 5L barriers
-  if (c == 0 && tid == 0 && !(p.dbg_flags & 2)) *p.bar_base = bar_target;
+  run_phase(p.lm, PH_LM, 0, [&]() { stage_xb(p.xt, TAG(p.L - 1, TG_XD), nowait, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red); });
+  // next launch uses fresh tags (stream order makes this visible to it)
+  if (c == 0 && tid == 0) *p.epoch = (unsigned long long)(tag0 + 8u * (uint32_t)p.L + 8u);
 }
 
 // ------------------------------------------------------------------ one-time weight re-tiling
@@ -692,7 +738,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   nslots &= ~(NCW - 1);
   if (nslots < NCW) return cudaErrorInvalidValue;
   a.nslots = nslots;
-  if (heads > num_sms || H > 8192) return cudaErrorInvalidValue;  // normed vector is register-staged (K <= 8192)
+  if (heads > num_sms || H > 8192 || (H & 15) || (I & 7)) return cudaErrorInvalidValue;  // normed vector is register-staged
   *grid_out = num_sms;
   return cudaSuccess;
 }

@@ -146,6 +146,7 @@ struct dtk_engine {
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
   unsigned int* d_head_cnt = nullptr;
   bf16* d_tiled = nullptr;             // decode-side re-tiled copy of the decoder matrices
+  uint2* d_tagged = nullptr;           // {value, epoch} activation buffers of the persistent kernel
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
@@ -574,15 +575,23 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
       m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
-      m.x = eng->d_x; m.q = eng->d_q; m.h = eng->d_h; m.logits = eng->d_logits;
-      DTK_ALLOC(eng->d_part, (int64_t)grid * 132);
+      m.logits = eng->d_logits;
+      {  // tagged cross-CTA activation buffers: xt[H] qt[qd] kvt[2kd] ht[I] attnt[qd] partt[grid*132]
+        const int64_t kd2 = 2 * (int64_t)c.kv_heads * 128;
+        const int64_t n = (int64_t)c.hidden + qd + kd2 + c.inter + qd + (int64_t)grid * 132;
+        DTK_ALLOC(eng->d_tagged, n);
+        DTK_CK(cudaMemset(eng->d_tagged, 0, n * sizeof(uint2)));
+        uint2* t = eng->d_tagged;
+        m.xt = t; t += c.hidden;
+        m.qt = t; t += qd;
+        m.kvt = t; t += kd2;
+        m.ht = t; t += c.inter;
+        m.attnt = t; t += qd;
+        m.partt = t;
+      }
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
-      m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
-      m.attn = eng->d_att;
-      DTK_ALLOC(eng->d_head_cnt, c.heads);
-      DTK_CK(cudaMemset(eng->d_head_cnt, 0, c.heads * sizeof(unsigned int)));
-      m.head_cnt = eng->d_head_cnt;
+      m.epoch = eng->d_bar;
       DTK_ALLOC(eng->d_dbg, (int64_t)3 * (c.layers * 5 + 1) * 4);
       DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)3 * (c.layers * 5 + 1) * 4 * sizeof(long long)));
       m.dbg = nullptr;
@@ -606,7 +615,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->d_tiled, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);

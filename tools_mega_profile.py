@@ -21,7 +21,7 @@ for _ in range(20):
     eng.decode([slot], [ctx], tok)
 ev1.record(); torch.cuda.synchronize()
 print("ms/token (incl tok copy kernel):", ev0.elapsed_time(ev1) / 20)
-for flags in (1, 2, 3, 4, 8, 12, 0):
+for flags in (1, 2, 3, 0):
     eng.set_option("mega_flags", flags)
     for _ in range(3):
         eng.decode([slot], [ctx], tok)
@@ -30,7 +30,7 @@ for flags in (1, 2, 3, 4, 8, 12, 0):
     for _ in range(10):
         eng.decode([slot], [ctx], tok)
     ev1.record(); torch.cuda.synchronize()
-    print(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive, 8=relaxed poll): ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
+    print(f"flags={flags} (1=no mma, 2=no tag waits): ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
@@ -47,7 +47,6 @@ for cta in range(3):
         rows = d[ph:L * 5:5]
         stage = (rows[:, 1] - rows[:, 0]).mean().item()
         items = (rows[:, 2] - rows[:, 1]).mean().item()
-        bar = (rows[:, 3] - rows[:, 2]).mean().item()
-        print(f"  {names[ph]:5s} stage {stage:8.0f}  items {items:8.0f}  barrier {bar:8.0f}  (cycles, mean over layers)")
+        print(f"  {names[ph]:5s} stage(+wait) {stage:8.0f}  items {items:8.0f}  (cycles, mean over layers)")
     lm = d[-1]
     print(f"  lm    stage {(lm[1]-lm[0]).item():8.0f}  items {(lm[2]-lm[1]).item():8.0f}")
