@@ -104,20 +104,15 @@ DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
   while (u.y != tag && !nowait) { sp.tick(); __nanosleep(32); u = __ldcg(p); }
   return __uint_as_float(u.x);
 }
-// 8 consecutive tagged elements (64 B). To keep the polling traffic of 148 x 256 waiting threads off the L2
-// (the weight stream shares it), only the last element is polled (one 32-byte sector per attempt, with a short
-// back-off); once it carries the tag the whole line is fetched with four loads in flight and re-verified.
+// 8 consecutive tagged elements (64 B): four 16-byte loads in flight per attempt (one round trip once the data
+// is there), short back-off between failed attempts to keep polling traffic off the L2.
 DTK_DEV void ld_tag8(const uint2* p, uint32_t tag, int nowait, float (&out)[8]) {
   Spin sp;
-  if (!nowait) {
-    uint2 probe = __ldcg(p + 7);
-    while (probe.y != tag) { sp.tick(); __nanosleep(32); probe = __ldcg(p + 7); }
-  }
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
   while (!nowait && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
     sp.tick();
-    __nanosleep(32);
+    __nanosleep(64);
     a = __ldcg(q); b = __ldcg(q + 1); c = __ldcg(q + 2); d = __ldcg(q + 3);
   }
   out[0] = __uint_as_float(a.x); out[1] = __uint_as_float(a.z); out[2] = __uint_as_float(b.x); out[3] = __uint_as_float(b.z);
@@ -341,6 +336,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     if (lane == 0) {
       Walk w;
       // visit own tiles j = j0, j0 + NPW, ... of a phase with `ntiles` local tiles (tpg tiles per group)
+      // Outstanding-copy throttle: any L2 round trip of this SM (tag polls, residual loads) queues behind the
+      // SM's own outstanding bulk-copy responses, so the number of issued-but-not-landed copies is bounded
+      // (depth per producer warp) while the ring may still hold many landed tiles.
+      constexpr int MAXD = 8;
+      uint32_t of_bar[MAXD], of_par[MAXD];
+      int of_n = 0, of_head = 0;
+      const int depth = p.prod_depth < 1 ? 1 : (p.prod_depth > MAXD ? MAXD : p.prod_depth);
       auto for_own = [&](int ntiles, int tpg, auto&& issue) {
         uint32_t j = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
         if ((int)j < ntiles) {
@@ -348,8 +350,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
           uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
           for (; (int)j < ntiles; j += NPW) {
+            if (of_n == depth) {   // wait until the oldest outstanding copy has landed
+              mbar_wait(of_bar[of_head], of_par[of_head]);
+              of_head = (of_head + 1 == depth) ? 0 : of_head + 1;
+              --of_n;
+            }
             if (use > 0) mbar_wait(empty0 + 8 * sl, (use - 1) & 1);
             issue((int)k, (int)ks, ring_u32 + sl * TILE_BYTES, full0 + 8 * sl);
+            {
+              int tail = of_head + of_n;
+              if (tail >= depth) tail -= depth;
+              of_bar[tail] = full0 + 8 * sl;
+              of_par[tail] = use & 1;
+              ++of_n;
+            }
             sl += NPW;
             if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
             ks += NPW;

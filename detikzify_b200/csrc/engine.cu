@@ -150,6 +150,7 @@ struct dtk_engine {
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
+  int mega_depth = 2;
 };
 
 namespace {
@@ -371,6 +372,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
+    m.prod_depth = eng->mega_depth;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -949,6 +951,11 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "mega_flags") == 0) {  // dev only (timing experiments; results are garbage when set)
     eng->mega_flags = (int)value;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "mega_depth") == 0) {  // outstanding bulk copies per producer warp (1..8)
+    DTK_REQUIRE(value >= 1 && value <= 8, "mega_depth must be in 1..8");
+    eng->mega_depth = (int)value;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_debug") == 0) {

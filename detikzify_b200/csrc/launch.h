@@ -175,6 +175,7 @@ struct MegaArgs {
   float* logits;
   unsigned long long* epoch;                                  // tag base; advanced by 8L+8 per launch
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
+  int prod_depth;                                             // outstanding bulk copies per producer warp (x4 per SM)
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = do not wait for tags
   long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
 };

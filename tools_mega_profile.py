@@ -21,6 +21,17 @@ for _ in range(20):
     eng.decode([slot], [ctx], tok)
 ev1.record(); torch.cuda.synchronize()
 print("ms/token (incl tok copy kernel):", ev0.elapsed_time(ev1) / 20)
+for depth in (1, 2, 3, 4, 6):
+    eng.set_option('mega_depth', depth)
+    for _ in range(3):
+        eng.decode([slot], [ctx], tok)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(10):
+        eng.decode([slot], [ctx], tok)
+    ev1.record(); torch.cuda.synchronize()
+    print(f'depth={depth}: ms/token {ev0.elapsed_time(ev1) / 10:.4f}')
+eng.set_option('mega_depth', int(sys.argv[3]) if len(sys.argv) > 3 else 2)
 for flags in (1, 2, 3, 0):
     eng.set_option("mega_flags", flags)
     for _ in range(3):
