@@ -434,10 +434,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     w.nb += ntiles;
   };
 
-  // optional phase timestamps (CTA-local clock64): [phase][4] = {start, staged, items done, items done}
-  long long* dbg = (p.dbg && (c == 0 || c == G / 2 || c == G - 1)) ? p.dbg + (int64_t)(c == 0 ? 0 : (c == G - 1 ? 2 : 1)) * (p.L * 5 + 1) * 4 : nullptr;
+  // optional phase timestamps (globaltimer ns, comparable across SMs): [CTA][phase][4] = {start, staged, items done, -}
+  long long* dbg = p.dbg ? p.dbg + (int64_t)c * (p.L * 5 + 1) * 4 : nullptr;
   int dbg_i = 0;
-  auto stamp = [&](int k) { if (dbg && tid == 0) dbg[dbg_i * 4 + k] = clock64(); };
+  auto stamp = [&](int k) {
+    if (dbg && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+      dbg[dbg_i * 4 + k] = (long long)t;
+    }
+  };
 
   // one weight phase. stage(): fills xb (only called when this CTA has work in the phase). Every tile = 16
   // k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a group's last tile sums the group's

@@ -594,8 +594,8 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
       m.epoch = eng->d_bar;
-      DTK_ALLOC(eng->d_dbg, (int64_t)3 * (c.layers * 5 + 1) * 4);
-      DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)3 * (c.layers * 5 + 1) * 4 * sizeof(long long)));
+      DTK_ALLOC(eng->d_dbg, (int64_t)grid * (c.layers * 5 + 1) * 4);
+      DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)grid * (c.layers * 5 + 1) * 4 * sizeof(long long)));
       m.dbg = nullptr;
       eng->mega_grid = grid;
       eng->mega_ok = true;
@@ -970,7 +970,7 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
 int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values) {
   if (!eng || !out_host) return DTK_ERR_INVALID;
   DTK_REQUIRE(eng->d_dbg != nullptr, "persistent kernel unavailable");
-  const int n = 3 * (eng->cfg.layers * 5 + 1) * 4;
+  const int n = eng->mega_grid * (eng->cfg.layers * 5 + 1) * 4;
   DTK_CK(cudaSetDevice(eng->device));
   DTK_CK(cudaDeviceSynchronize());
   DTK_CK(cudaMemcpy(out_host, eng->d_dbg, (size_t)(n < max_values ? n : max_values) * sizeof(long long), cudaMemcpyDeviceToHost));

@@ -168,7 +168,7 @@ DTK_API uint64_t dtk_launch_count(const dtk_engine* eng);
 DTK_API int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int chunk, int nslots, int ncw,
                                  int npw, int read_smem, int hint, int grid, float* sink, void* stream);
 /* phase timestamps of the last persistent-kernel launch (option "mega_debug" = 1):
- * [3 CTAs][5*layers+1 phases][4] clock64 values; returns the value count */
+ * [grid CTAs][5*layers+1 phases][4] globaltimer (ns) stamps; returns the value count */
 DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values);
 /* C = act(A[M,K] * W[N,K]^T + bias) (+resid); glu: out[m, n/2] = silu(c[m,n]) * c[m,n+1] */
 DTK_API int dtk_dbg_gemm(const void* A_bf16, const void* W_bf16, const void* bias_bf16,

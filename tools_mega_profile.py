@@ -1,5 +1,5 @@
-"""Phase-level timing breakdown of the persistent decode kernel (dev tool; run on the GPU box)."""
-import ctypes as C, sys, json
+"""Phase-level timeline of the persistent decode kernel across all CTAs (dev tool; run on the GPU box)."""
+import ctypes as C, sys
 import torch
 sys.path.insert(0, ".")
 from detikzify_b200.model import load
@@ -12,17 +12,8 @@ g = torch.Generator().manual_seed(1)
 ids = torch.randint(0, 30000, (ctx,), generator=g).cuda()
 eng.prefill(slot, ids, 0, None, 0)
 tok = torch.tensor([5], device="cuda")
-for _ in range(5):
-    eng.decode([slot], [ctx], tok)
-torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-ev0.record()
-for _ in range(20):
-    eng.decode([slot], [ctx], tok)
-ev1.record(); torch.cuda.synchronize()
-print("ms/token (incl tok copy kernel):", ev0.elapsed_time(ev1) / 20)
-for depth in (1, 2, 3, 4, 6):
-    eng.set_option('mega_depth', depth)
+def timeit(label):
     for _ in range(3):
         eng.decode([slot], [ctx], tok)
     torch.cuda.synchronize()
@@ -30,34 +21,40 @@ for depth in (1, 2, 3, 4, 6):
     for _ in range(10):
         eng.decode([slot], [ctx], tok)
     ev1.record(); torch.cuda.synchronize()
-    print(f'depth={depth}: ms/token {ev0.elapsed_time(ev1) / 10:.4f}')
-eng.set_option('mega_depth', int(sys.argv[3]) if len(sys.argv) > 3 else 2)
+    print(f"{label}: ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
+for depth in (2, 6):
+    eng.set_option("mega_depth", depth)
+    timeit(f"depth={depth}")
+eng.set_option("mega_depth", int(sys.argv[3]) if len(sys.argv) > 3 else 2)
 for flags in (1, 2, 3, 0):
     eng.set_option("mega_flags", flags)
-    for _ in range(3):
-        eng.decode([slot], [ctx], tok)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(10):
-        eng.decode([slot], [ctx], tok)
-    ev1.record(); torch.cuda.synchronize()
-    print(f"flags={flags} (1=no mma, 2=no tag waits): ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
+    timeit(f"flags={flags} (1=no mma, 2=no tag waits)")
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
-n = 3 * (L * 5 + 1) * 4
+NP = L * 5 + 1
+G = 148
+n = G * NP * 4
 buf = (C.c_longlong * n)()
 got = eng.lib.dtk_dbg_mega_times(eng._h, buf, n)
-t = torch.tensor(list(buf), dtype=torch.float64).view(3, L * 5 + 1, 4)
+G = got // (NP * 4)
+t = torch.tensor(list(buf[:got]), dtype=torch.float64).view(G, NP, 4)
+t0 = t[:, 0, 0].min()
 names = ["qkv", "attn", "o", "gu", "down"]
-for cta in range(3):
-    d = t[cta]
-    tot = (d[-1, 2] - d[0, 0]).item()
-    print(f"CTA#{cta}: total cycles {tot:.0f}")
+print(f"kernel span: {(t[:, -1, 2].max() - t0).item() / 1e3:.1f} us  (G={G})")
+for layer in (1, L // 2):
+    print(f"layer {layer}: per phase over CTAs (us rel. to kernel start): start[min,max] staged[min,max] done[min,max] | mean(stage) mean(items) | n_active")
     for ph in range(5):
-        rows = d[ph:L * 5:5]
-        stage = (rows[:, 1] - rows[:, 0]).mean().item()
-        items = (rows[:, 2] - rows[:, 1]).mean().item()
-        print(f"  {names[ph]:5s} stage(+wait) {stage:8.0f}  items {items:8.0f}  (cycles, mean over layers)")
-    lm = d[-1]
-    print(f"  lm    stage {(lm[1]-lm[0]).item():8.0f}  items {(lm[2]-lm[1]).item():8.0f}")
+        d = t[:, layer * 5 + ph]
+        act = (d[:, 2] - d[:, 1]) > 300  # CTAs that did work (ns)
+        a = d[act] if act.any() else d
+        f = lambda x: f"[{(x.min() - t0).item() / 1e3:8.2f},{(x.max() - t0).item() / 1e3:8.2f}]"
+        print(f"  {names[ph]:5s} {f(a[:, 0])} {f(a[:, 1])} {f(a[:, 2])} | {(a[:, 1] - a[:, 0]).mean().item() / 1e3:6.2f} {(a[:, 2] - a[:, 1]).mean().item() / 1e3:6.2f} | {int(act.sum())}")
+# slowest CTAs per phase kind (who finishes last), aggregated over layers
+import collections
+cnt = collections.Counter()
+for layer in range(L):
+    for ph in range(5):
+        d = t[:, layer * 5 + ph, 2]
+        cnt[int(d.argmax())] += 1
+print("CTAs most often last to finish a phase:", cnt.most_common(12))
