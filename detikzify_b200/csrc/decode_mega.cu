@@ -101,7 +101,7 @@ struct Spin {
 DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
   Spin sp;
   uint2 u = __ldcg(p);
-  while (u.y != tag && !nowait) { sp.tick(); __nanosleep(32); u = __ldcg(p); }
+  while (u.y != tag && !(nowait & 2)) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); u = __ldcg(p); }
   return __uint_as_float(u.x);
 }
 // 8 consecutive tagged elements (64 B): four 16-byte loads in flight per attempt (one round trip once the data
@@ -110,13 +110,31 @@ DTK_DEV void ld_tag8(const uint2* p, uint32_t tag, int nowait, float (&out)[8]) 
   Spin sp;
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
-  while (!nowait && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
+  while (!(nowait & 2) && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
     sp.tick();
-    __nanosleep(64);
+    if (!(nowait & 4)) __nanosleep(64);
     a = __ldcg(q); b = __ldcg(q + 1); c = __ldcg(q + 2); d = __ldcg(q + 3);
   }
   out[0] = __uint_as_float(a.x); out[1] = __uint_as_float(a.z); out[2] = __uint_as_float(b.x); out[3] = __uint_as_float(b.z);
   out[4] = __uint_as_float(c.x); out[5] = __uint_as_float(c.z); out[6] = __uint_as_float(d.x); out[7] = __uint_as_float(d.z);
+}
+// 16 consecutive tagged elements (one k-step, 128 B): eight loads in flight per attempt
+DTK_DEV void ld_tag16(const uint2* p, uint32_t tag, int nowait, float (&out)[16]) {
+  Spin sp;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 u[8];
+  bool ok;
+  do {
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = __ldcg(q + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ok = ok && (u[i].y == tag) && (u[i].w == tag);
+    if (nowait & 2) break;
+    if (!ok) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); }
+  } while (!ok);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { out[2 * i] = __uint_as_float(u[i].x); out[2 * i + 1] = __uint_as_float(u[i].z); }
 }
 
 // ------------------------------------------------------------------ work description
@@ -198,13 +216,7 @@ DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) x16[8 + i] = f[i];
           } else {
-            float f[8];
-            ld_tag8(src_t + S * 16, tag, nowait, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x16[i] = f[i];
-            ld_tag8(src_t + S * 16 + 8, tag, nowait, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x16[8 + i] = f[i];
+            ld_tag16(src_t + S * 16, tag, nowait, x16);
           }
         }
         float wv[16];
@@ -247,15 +259,13 @@ DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* 
       float w16[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) w16[i] = 0.f;
+      if (S * 16 + 16 <= K) {
+        ld_tag16(src_t + S * 16, tag, nowait, w16);
+      } else if (S * 16 < K) {   // K is a multiple of 8: ragged last k-step
+        float f[8];
+        ld_tag8(src_t + S * 16, tag, nowait, f);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int k = S * 16 + half * 8;
-        if (k < K) {    // K is a multiple of 8
-          float f[8];
-          ld_tag8(src_t + k, tag, nowait, f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w16[half * 8 + i] = f[i];
-        }
+        for (int i = 0; i < 8; ++i) w16[i] = f[i];
       }
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
-  const int nowait = p.dbg_flags & 2;
+  const int nowait = p.dbg_flags & 6;   // dev flags: 2 = never wait for tags, 4 = poll without back-off
 
   // ---- work assignment. A weight phase with `groups` 16-row groups is cut into equal blocks of
   // per = ceil(groups / G) groups; only ceil(groups / per) CTAs take part (all with the same amount of work, so
@@ -661,8 +671,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                 ms[r] = __uint_as_float(a.x); lv[r] = __uint_as_float(b.x); ov[r] = __uint_as_float(d.x);
               }
             }
-            if (nowait) break;
-            if (!ok) { sp.tick(); __nanosleep(32); }
+            if (nowait & 2) break;
+            if (!ok) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); }
           }
           float MM = M;
 #pragma unroll
