@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
-  const int nowait = p.dbg_flags & 6;   // dev flags: 2 = never wait for tags, 4 = poll without back-off
+  const int nowait = (p.dbg_flags & 2) | ((p.dbg_flags & 4) ? 0 : 4);   // dev flags: 2 = never wait for tags, 4 = poll WITH back-off
 
   // ---- work assignment. A weight phase with `groups` 16-row groups is cut into equal blocks of
   // per = ceil(groups / G) groups; only ceil(groups / per) CTAs take part (all with the same amount of work, so
@@ -395,16 +395,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       };
       for (int l = 0; l < p.L; ++l) {
         stream_phase(p.qkv, l);
-        {  // old keys/values of this CTA's (head, range): 16-key items, K rows then V rows
-          const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
-          const bf16* vb = kb + p.kv_v_offset;
-          for_own(as.n_items, 1, [&](int i, int, uint32_t dst, uint32_t fb) {
-            const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
-            mbar_expect_tx(fb, (uint32_t)nk * 512);
-            bulk_g2s(dst, kb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
-            bulk_g2s(dst + 16 * 256, vb + (int64_t)k0 * 128, (uint32_t)nk * 256, fb);
-          });
-        }
         stream_phase(p.o, l);
         stream_phase(p.gu, l);
         stream_phase(p.down, l);
@@ -567,6 +557,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const int Hp = p.qkv.tpg * 256, Qp = p.o.tpg * 256, Ip = p.down.tpg * 256;
   for (int l = 0; l < p.L; ++l) {
     const int64_t no = (int64_t)l * p.norm_stride;
+    // KV rows of this CTA's (head, key range) are read with plain loads in P2: pull them into L2 now so that
+    // their DRAM latency hides behind P1 (126 MB L2 holds ~1.2 layers of weight stream, they stay resident)
+    if (as.active) {
+      const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + as.j0) * 128;
+      const int lines = (as.j1 - as.j0) * 2;   // 128-byte lines per K (and per V) range
+      for (int i = tid; i < lines; i += CONSUMER_THREADS) {
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(kb + (int64_t)i * 64));
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(kb + p.kv_v_offset + (int64_t)i * 64));
+      }
+    }
     // ---------------- P1: RMSNorm + qkv + RoPE + KV write
     run_phase(p.qkv, PH_QKV, l, [&]() {
       stage_xb(p.xt, l == 0 ? 0u : TAG(l - 1, TG_XD), nowait, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp,
@@ -601,24 +601,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           m = mn;
         }
       };
-      for_own(as.n_items, 1, [&](int i, int, int, uint32_t sl) {
-        const uint8_t* base = ring + (size_t)sl * TILE_BYTES;
-        const int k0 = as.j0 + i * 16, nk = min(16, as.j1 - k0);
-#pragma unroll 4
-        for (int kk = 0; kk < 8; ++kk) {
-          const int key = kk * 2 + hw;
-          const bool valid = key < nk;
-          float kf[8], vf[8];
+      {
+        // keys j0 + hidx, j0 + hidx + 16, ... for half-warp hidx (16 half-warps per CTA), 4 keys in flight
+        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
+        const bf16* vb = kb + p.kv_v_offset;
+        const int hid = warp * 2 + hw;
+        for (int jb = as.j0; jb < as.j1; jb += 64) {   // warp-uniform trip count
+          uint4 kr[4], vr[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { kf[e] = 0.f; vf[e] = 0.f; }
-          if (valid) {
-            unpack8(*reinterpret_cast<const uint4*>(base + key * 256 + l16 * 16), kf);
-            unpack8(*reinterpret_cast<const uint4*>(base + 16 * 256 + key * 256 + l16 * 16), vf);
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb + u * 16 + hid;
+            kr[u] = vr[u] = make_uint4(0, 0, 0, 0);
+            if (j < as.j1) {
+              kr[u] = __ldcg(reinterpret_cast<const uint4*>(kb + (int64_t)j * 128 + l16 * 8));
+              vr[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (int64_t)j * 128 + l16 * 8));
+            }
           }
-          key_update(kf, vf, valid);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb + u * 16 + hid;
+            float kf[8], vf[8];
+            unpack8(kr[u], kf);
+            unpack8(vr[u], vf);
+            key_update(kf, vf, j < as.j1);
+          }
         }
-        release();
-      });
+      }
       if (as.last && warp == 0) {   // the key/value of the token being decoded (produced in P1 of this launch)
         float kf[8], vf[8];
         ld_tag8(p.kvt + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, kf);

@@ -26,7 +26,7 @@ for depth in (2, 6):
     eng.set_option("mega_depth", depth)
     timeit(f"depth={depth}")
 eng.set_option("mega_depth", int(sys.argv[3]) if len(sys.argv) > 3 else 2)
-for flags in (2, 4, 0):
+for flags in (2, 0):
     eng.set_option("mega_flags", flags)
     timeit(f"flags={flags} (1=no mma, 2=no tag waits, 4=no backoff)")
 eng.set_option("mega_flags", int(sys.argv[4]) if len(sys.argv) > 4 else 0)
