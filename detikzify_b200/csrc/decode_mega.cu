@@ -574,12 +574,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     });
 
     // ---------------- P2: attention over this CTA's key range of its head
-    stamp(0); stamp(1);
+    stamp(0);
     if (as.active) {
       const int hw = lane >> 4, l16 = lane & 15;
       const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
       float q[8];
       ld_tag8(p.qt + as.head * 128 + l16 * 8, TAG(l, TG_QKV), nowait, q);
+      stamp(1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] *= sl2;
       float m = -INFINITY, lsum = 0.f, o[8];
@@ -638,6 +639,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       float* sm_l = actf + 16;       // [16]
       float* sm_o = actf + 32;       // [16][128]
       const int hidx = warp * 2 + hw;
+      stamp(3);
       consumer_sync();               // the scratch aliases xb: all warps are done with the previous phase's tiles
       if (l16 == 0) { sm_m[hidx] = m; sm_l[hidx] = lsum; }
 #pragma unroll
@@ -700,7 +702,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       consumer_sync();   // sm_* scratch (aliases xb) is free again
     }
-    stamp(2); stamp(3); ++dbg_i;
+    stamp(2); ++dbg_i;
 
     // ---------------- P3: o-proj + residual on the merged attention output
     run_phase(p.o, PH_O, l, [&]() { stage_xb(p.attnt, TAG(l, TG_ATTN), nowait, nullptr, qd, Qp, nullptr, 0.f, xb, red); });

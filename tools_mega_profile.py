@@ -59,3 +59,11 @@ for layer in range(L):
         d = t[:, layer * 5 + ph, 2]
         cnt[int(d.argmax())] += 1
 print("CTAs most often last to finish a phase:", cnt.most_common(12))
+
+layer = L // 2
+d = t[:, layer * 5 + 1]
+qd_done = t[:, layer * 5 + 0, 2].max()
+print("attention phase of layer", layer, "(us after the last CTA finished qkv): per CTA  q-arrived / keys-done / phase-done")
+order = d[:, 2].argsort()
+for c in list(order[:4].tolist()) + list(order[-24:].tolist()):
+    print(f"  cta {c:3d}: {(d[c,1]-qd_done).item()/1e3:7.2f} {(d[c,3]-qd_done).item()/1e3:7.2f} {(d[c,2]-qd_done).item()/1e3:7.2f}")
