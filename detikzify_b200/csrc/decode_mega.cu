@@ -87,6 +87,10 @@ DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_T
 DTK_DEV void st_tag(uint2* p, float v, uint32_t tag) {
   asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
+DTK_DEV void backoff(int cycles) {
+  const long long t = clock64();
+  while (clock64() - t < cycles) {}
+}
 struct Spin {
   uint32_t n = 0;
   long long t0 = 0;
@@ -101,7 +105,7 @@ struct Spin {
 DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
   Spin sp;
   uint2 u = __ldcg(p);
-  while (u.y != tag && !(nowait & 2)) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); u = __ldcg(p); }
+  while (u.y != tag && !(nowait & 2)) { sp.tick(); if (!(nowait & 4)) backoff(200); u = __ldcg(p); }
   return __uint_as_float(u.x);
 }
 // 8 consecutive tagged elements (64 B): four 16-byte loads in flight per attempt (one round trip once the data
@@ -112,7 +116,7 @@ DTK_DEV void ld_tag8(const uint2* p, uint32_t tag, int nowait, float (&out)[8]) 
   uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
   while (!(nowait & 2) && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
     sp.tick();
-    if (!(nowait & 4)) __nanosleep(64);
+    if (!(nowait & 4)) backoff(200);
     a = __ldcg(q); b = __ldcg(q + 1); c = __ldcg(q + 2); d = __ldcg(q + 3);
   }
   out[0] = __uint_as_float(a.x); out[1] = __uint_as_float(a.z); out[2] = __uint_as_float(b.x); out[3] = __uint_as_float(b.z);
@@ -131,7 +135,7 @@ DTK_DEV void ld_tag16(const uint2* p, uint32_t tag, int nowait, float (&out)[16]
 #pragma unroll
     for (int i = 0; i < 8; ++i) ok = ok && (u[i].y == tag) && (u[i].w == tag);
     if (nowait & 2) break;
-    if (!ok) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); }
+    if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
   } while (!ok);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { out[2 * i] = __uint_as_float(u[i].x); out[2 * i + 1] = __uint_as_float(u[i].z); }
@@ -255,28 +259,66 @@ DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* 
       }
     }
   } else {
-    for (int S = tid; S < nsteps; S += CONSUMER_THREADS) {
-      float w16[16];
+    for (int S0 = tid; S0 < nsteps; S0 += 2 * CONSUMER_THREADS) {
+      // two k-steps per thread with all 16 loads in flight (one round trip)
+      float w16[2][16];
+      const int S1 = S0 + CONSUMER_THREADS;
+      const bool full0 = S0 * 16 + 16 <= K, full1 = S1 < nsteps && S1 * 16 + 16 <= K;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w16[i] = 0.f;
-      if (S * 16 + 16 <= K) {
-        ld_tag16(src_t + S * 16, tag, nowait, w16);
-      } else if (S * 16 < K) {   // K is a multiple of 8: ragged last k-step
-        float f[8];
-        ld_tag8(src_t + S * 16, tag, nowait, f);
+      for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w16[i] = f[i];
+        for (int i = 0; i < 16; ++i) w16[h2][i] = 0.f;
+      if (full0 && full1) {
+        Spin sp;
+        const uint4* q0 = reinterpret_cast<const uint4*>(src_t + S0 * 16);
+        const uint4* q1 = reinterpret_cast<const uint4*>(src_t + S1 * 16);
+        uint4 u0[8], u1[8];
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { u0[i] = __ldcg(q0 + i); u1[i] = __ldcg(q1 + i); }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ok = ok && u0[i].y == tag && u0[i].w == tag && u1[i].y == tag && u1[i].w == tag;
+          if (nowait & 2) break;
+          if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
+        } while (!ok);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          w16[0][2 * i] = __uint_as_float(u0[i].x); w16[0][2 * i + 1] = __uint_as_float(u0[i].z);
+          w16[1][2 * i] = __uint_as_float(u1[i].x); w16[1][2 * i + 1] = __uint_as_float(u1[i].z);
+        }
+      } else {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int S = h2 ? S1 : S0;
+          if (S < nsteps) {
+            if (S * 16 + 16 <= K) ld_tag16(src_t + S * 16, tag, nowait, w16[h2]);
+            else if (S * 16 < K) {   // K is a multiple of 8: ragged last k-step
+              float f[8];
+              ld_tag8(src_t + S * 16, tag, nowait, f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w16[h2][i] = f[i];
+            }
+          }
+        }
       }
-      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a = w16[2 * j], b = w16[2 * j + 1];
-        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int S = h2 ? S1 : S0;
+        if (S < nsteps) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = w16[h2][2 * j], b = w16[h2][2 * j + 1];
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+            hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+            lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
+        }
       }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
     }
   }
   consumer_sync();
@@ -298,6 +340,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   float* rope_s = red + 16;                                   // [64][2] cos/sin of this position
   float* tpart = rope_s + 128;                                // [NT][16] per-tile partial sums
   int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] tiles finished per group
+  float* rbuf = reinterpret_cast<float*>(gcnt + NG);          // [NG][16] residuals prefetched at a group's first tile
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -471,6 +514,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       }
       release();
+      const uint32_t gslot = (gb0 + (uint32_t)k) & (NG - 1);
+      if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+        // residual of row (group, lane): its producer finished a whole phase ago, so this never waits long;
+        // fetched here (first tile of the group) its L2 latency is off the group's critical path
+        const int row = (g0 + k) * 16 + lane;
+        float b = 0.f;
+        if (row < p.H) {
+          if (ph == PH_O) b = (layer == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row]) : ld_tag(p.xt + row, TAG(layer - 1, TG_XD), nowait);
+          else b = ld_tag(p.xt + row, TAG(layer, TG_XO), nowait);
+        }
+        rbuf[gslot * 16 + lane] = b;
+      }
       const uint32_t n = nb0 + (uint32_t)j;
       if ((lane & 3) == 0) {
         float* tp = tpart + (n & (NT - 1)) * 16;
@@ -479,7 +534,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       __syncwarp();
       int last = 0;
-      const uint32_t gslot = (gb0 + (uint32_t)k) & (NG - 1);
       if (lane == 0) {
         __threadfence_block();
         last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
@@ -524,15 +578,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       } else if (ph == PH_O) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        float b0 = 0.f, b1 = 0.f;
-        if (layer == 0) {  // residual stream starts as the token embedding
-          if (r0 < p.H) b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
-          if (r1 < p.H) b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
-        } else {
-          const uint32_t tprev = TAG(layer - 1, TG_XD);
-          if (r0 < p.H) b0 = ld_tag(p.xt + r0, tprev, nowait);
-          if (r1 < p.H) b1 = ld_tag(p.xt + r1, tprev, nowait);
-        }
+        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
         if (r0 < p.H) st_tag(p.xt + r0, b0 + v, TAG(layer, TG_XO));
         if (r1 < p.H) st_tag(p.xt + r1, b1 + v1, TAG(layer, TG_XO));
       } else if (ph == PH_GU) {
@@ -540,9 +586,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         if (i < p.I) st_tag(p.ht + i, silu(v) * v1, TAG(layer, TG_H));
       } else if (ph == PH_DOWN) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        const uint32_t tprev = TAG(layer, TG_XO);
-        if (r0 < p.H) st_tag(p.xt + r0, ld_tag(p.xt + r0, tprev, nowait) + v, TAG(layer, TG_XD));
-        if (r1 < p.H) st_tag(p.xt + r1, ld_tag(p.xt + r1, tprev, nowait) + v1, TAG(layer, TG_XD));
+        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+        if (r0 < p.H) st_tag(p.xt + r0, b0 + v, TAG(layer, TG_XD));
+        if (r1 < p.H) st_tag(p.xt + r1, b1 + v1, TAG(layer, TG_XD));
       } else {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
         if (r0 < p.V) p.logits[r0] = v;
@@ -603,14 +649,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       };
       {
-        // keys j0 + hidx, j0 + hidx + 16, ... for half-warp hidx (16 half-warps per CTA), 4 keys in flight
+        // keys j0 + hid, j0 + hid + 16, ... for half-warp hid (16 half-warps per CTA); up to 8 keys (16 loads) in
+        // flight per lane so that a 128-key range costs ONE L2 round trip; the newest key (this token's, from P1)
+        // is handled last: its tag has long been set by then
         const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
         const bf16* vb = kb + p.kv_v_offset;
         const int hid = warp * 2 + hw;
-        for (int jb = as.j0; jb < as.j1; jb += 64) {   // warp-uniform trip count
-          uint4 kr[4], vr[4];
+        for (int jb = as.j0; jb < as.j1; jb += 128) {   // warp-uniform trip count
+          uint4 kr[8], vr[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int j = jb + u * 16 + hid;
             kr[u] = vr[u] = make_uint4(0, 0, 0, 0);
             if (j < as.j1) {
@@ -619,7 +667,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int j = jb + u * 16 + hid;
             float kf[8], vf[8];
             unpack8(kr[u], kf);
@@ -627,12 +675,30 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             key_update(kf, vf, j < as.j1);
           }
         }
-      }
-      if (as.last && warp == 0) {   // the key/value of the token being decoded (produced in P1 of this launch)
-        float kf[8], vf[8];
-        ld_tag8(p.kvt + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, kf);
-        ld_tag8(p.kvt + kd + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, vf);
-        key_update(kf, vf, hw == 0);
+        if (as.last && warp == 0) {
+          float nkf[8], nvf[8];
+          Spin sp;
+          const uint32_t tg = TAG(l, TG_QKV);
+          const uint4* qk = reinterpret_cast<const uint4*>(p.kvt + kvh * 128 + l16 * 8);
+          const uint4* qv = reinterpret_cast<const uint4*>(p.kvt + kd + kvh * 128 + l16 * 8);
+          uint4 a[4], b[4];
+          bool ok;
+          do {   // k and v rows together: one round trip
+            ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = __ldcg(qk + i); b[i] = __ldcg(qv + i); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ok = ok && a[i].y == tg && a[i].w == tg && b[i].y == tg && b[i].w == tg;
+            if (nowait & 2) break;
+            if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
+          } while (!ok);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            nkf[2 * i] = __uint_as_float(a[i].x); nkf[2 * i + 1] = __uint_as_float(a[i].z);
+            nvf[2 * i] = __uint_as_float(b[i].x); nvf[2 * i + 1] = __uint_as_float(b[i].z);
+          }
+          key_update(nkf, nvf, hw == 0);
+        }
       }
       // merge the 16 half-warp states -> one partial per CTA
       float* sm_m = actf;            // [16]
@@ -682,7 +748,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               }
             }
             if (nowait & 2) break;
-            if (!ok) { sp.tick(); if (!(nowait & 4)) __nanosleep(64); }
+            if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
           }
           float MM = M;
 #pragma unroll
@@ -758,7 +824,7 @@ cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cu
 }
 
 int mega_smem_bytes(const MegaArgs& a) {
-  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4;
+  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4;
 }
 
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out) {
@@ -769,7 +835,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   actf = (actf + 31) & ~31;
   a.act_floats = actf;
   if ((I + 255) / 256 > NT - 40) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
-  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + 64;
+  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
   if (nslots > 32) nslots = 32;
   // every ring slot must always be filled by the same producer warp and drained by the same consumer warp
