@@ -28,6 +28,8 @@
 // P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final RMSNorm).
 //
 // Replaces the per-token HF eager path (modeling_llama.py:303-333, ~900 launches per token).
+#include <cstdio>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -40,9 +42,9 @@ constexpr int MEGA_THREADS = (NCW + NPW) * 32;
 constexpr int CONSUMER_THREADS = NCW * 32;
 static_assert(NCW % NPW == 0, "slot ownership: NPW must divide NCW");
 constexpr int TILE_BYTES = 8192;             // ring slot = one weight tile = one 16-key K+V attention item
-constexpr int NT = 128;                      // per-tile partial-sum entries (>= max tiles/group + tiles in flight)
-constexpr int NG = 64;                       // per-group arrival counters
-constexpr long long SPIN_CYCLES = 4000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
+constexpr int NT = 112;                      // per-tile partial-sum entries (>= max tiles/group + tiles in flight)
+constexpr int NG = 48;                       // per-group arrival counters / residual rows (>= groups in flight)
+constexpr long long SPIN_CYCLES = 1000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
 DTK_DEV void mbar_init(uint32_t bar, uint32_t count) {
@@ -68,7 +70,10 @@ DTK_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && (++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > SPIN_CYCLES) __trap();
+      else if (now - t0 > SPIN_CYCLES) {
+        if ((threadIdx.x & 31) == 0) printf("[dtk] mbarrier wait timed out: cta %d tid %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
@@ -84,6 +89,16 @@ DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_T
 // plain store; readers poll the L2 copy (ld.cg) until the tag of the expected phase shows up. Write-after-read
 // hazards are excluded by the data-flow itself (a buffer is only rewritten by work that transitively depends
 // on every reader of the previous version; see DESIGN.md "decode synchronisation").
+DTK_DEV uint4 ld_poll4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+DTK_DEV uint2 ld_poll2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];\n" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
 DTK_DEV void st_tag(uint2* p, float v, uint32_t tag) {
   asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
@@ -94,18 +109,22 @@ DTK_DEV void backoff(int cycles) {
 struct Spin {
   uint32_t n = 0;
   long long t0 = 0;
-  DTK_DEV void tick() {
+  DTK_DEV void tick(const void* what = nullptr, uint32_t want = 0, uint32_t seen = 0) {
     if ((++n & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > SPIN_CYCLES) __trap();
+      else if (now - t0 > SPIN_CYCLES) {
+        if ((threadIdx.x & 31) == 0)
+          printf("[dtk] tag wait timed out: cta %d tid %d addr %p want %u seen %u\n", (int)blockIdx.x, (int)threadIdx.x, what, want, seen);
+        __trap();
+      }
     }
   }
 };
 DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
   Spin sp;
-  uint2 u = __ldcg(p);
-  while (u.y != tag && !(nowait & 2)) { sp.tick(); if (!(nowait & 4)) backoff(200); u = __ldcg(p); }
+  uint2 u = ld_poll2(p);
+  while (u.y != tag && !(nowait & 2)) { sp.tick(p, tag, u.y); if (!(nowait & 4)) backoff(200); u = ld_poll2(p); }
   return __uint_as_float(u.x);
 }
 // 8 consecutive tagged elements (64 B): four 16-byte loads in flight per attempt (one round trip once the data
@@ -113,11 +132,11 @@ DTK_DEV float ld_tag(const uint2* p, uint32_t tag, int nowait) {
 DTK_DEV void ld_tag8(const uint2* p, uint32_t tag, int nowait, float (&out)[8]) {
   Spin sp;
   const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+  uint4 a = ld_poll4(q), b = ld_poll4(q + 1), c = ld_poll4(q + 2), d = ld_poll4(q + 3);
   while (!(nowait & 2) && (a.y != tag || a.w != tag || b.y != tag || b.w != tag || c.y != tag || c.w != tag || d.y != tag || d.w != tag)) {
-    sp.tick();
+    sp.tick(p, tag, a.y);
     if (!(nowait & 4)) backoff(200);
-    a = __ldcg(q); b = __ldcg(q + 1); c = __ldcg(q + 2); d = __ldcg(q + 3);
+    a = ld_poll4(q); b = ld_poll4(q + 1); c = ld_poll4(q + 2); d = ld_poll4(q + 3);
   }
   out[0] = __uint_as_float(a.x); out[1] = __uint_as_float(a.z); out[2] = __uint_as_float(b.x); out[3] = __uint_as_float(b.z);
   out[4] = __uint_as_float(c.x); out[5] = __uint_as_float(c.z); out[6] = __uint_as_float(d.x); out[7] = __uint_as_float(d.z);
@@ -131,11 +150,11 @@ DTK_DEV void ld_tag16(const uint2* p, uint32_t tag, int nowait, float (&out)[16]
   do {
     ok = true;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = __ldcg(q + i);
+    for (int i = 0; i < 8; ++i) u[i] = ld_poll4(q + i);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ok = ok && (u[i].y == tag) && (u[i].w == tag);
     if (nowait & 2) break;
-    if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
+    if (!ok) { sp.tick(p, tag, u[0].y); if (!(nowait & 4)) backoff(200); }
   } while (!ok);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { out[2 * i] = __uint_as_float(u[i].x); out[2 * i + 1] = __uint_as_float(u[i].z); }
@@ -268,7 +287,7 @@ DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* 
       for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
         for (int i = 0; i < 16; ++i) w16[h2][i] = 0.f;
-      if (full0 && full1) {
+      if (full0 && full1 && !(nowait & 16)) {
         Spin sp;
         const uint4* q0 = reinterpret_cast<const uint4*>(src_t + S0 * 16);
         const uint4* q1 = reinterpret_cast<const uint4*>(src_t + S1 * 16);
@@ -277,7 +296,7 @@ DTK_DEV void stage_xb(const uint2* src_t, uint32_t tag, int nowait, const bf16* 
         do {
           ok = true;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { u0[i] = __ldcg(q0 + i); u1[i] = __ldcg(q1 + i); }
+          for (int i = 0; i < 8; ++i) { u0[i] = ld_poll4(q0 + i); u1[i] = ld_poll4(q1 + i); }
 #pragma unroll
           for (int i = 0; i < 8; ++i) ok = ok && u0[i].y == tag && u0[i].w == tag && u1[i].y == tag && u1[i].w == tag;
           if (nowait & 2) break;
@@ -360,8 +379,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   if (tid < NG) gcnt[tid] = 0;
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
+  if (tid == 0 && (p.dbg_flags & 64) && (c == 30 || c == 0 || c == 52)) printf("[dtk] cta %d G %d pos %d: active %d head %d j0 %d j1 %d last %d cph %d\n", c, G, pos, as.active, as.head, as.j0, as.j1, as.last, as.cph);
   const int kvh = as.head / (p.heads / p.kv_heads);
-  const int nowait = (p.dbg_flags & 2) | ((p.dbg_flags & 4) ? 0 : 4);   // dev flags: 2 = never wait for tags, 4 = poll WITH back-off
+  const int nowait = (p.dbg_flags & 2) | ((p.dbg_flags & 4) ? 0 : 4) | (p.dbg_flags & 16);   // dev flags: 2 = never wait for tags, 4 = poll WITH back-off
 
   // ---- work assignment. A weight phase with `groups` 16-row groups is cut into equal blocks of
   // per = ceil(groups / G) groups; only ceil(groups / per) CTAs take part (all with the same amount of work, so
@@ -514,8 +534,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       }
       release();
-      const uint32_t gslot = (gb0 + (uint32_t)k) & (NG - 1);
-      if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+      const uint32_t gslot = (gb0 + (uint32_t)k) % NG;
+      if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16 && !(p.dbg_flags & 8)) {
         // residual of row (group, lane): its producer finished a whole phase ago, so this never waits long;
         // fetched here (first tile of the group) its L2 latency is off the group's critical path
         const int row = (g0 + k) * 16 + lane;
@@ -528,7 +548,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       const uint32_t n = nb0 + (uint32_t)j;
       if ((lane & 3) == 0) {
-        float* tp = tpart + (n & (NT - 1)) * 16;
+        float* tp = tpart + (n % NT) * 16;
         tp[lane >> 2] = acc[0];
         tp[(lane >> 2) + 8] = acc[2];
       }
@@ -545,7 +565,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t n0 = nb0 + (uint32_t)k * tpg;
       float v = 0.f;
       if (lane < 16)
-        for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) & (NT - 1)) * 16 + lane);
+        for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
       const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
       if (lane == 0) gcnt[gslot] = 0;
       if (lane >= 8) return;
@@ -578,7 +598,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
       } else if (ph == PH_O) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+        float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+        if (p.dbg_flags & 8) {
+          b0 = b1 = 0.f;
+          if (layer == 0) {
+            if (r0 < p.H) b0 = __bfloat162float(p.embed[(int64_t)tok * p.H + r0]);
+            if (r1 < p.H) b1 = __bfloat162float(p.embed[(int64_t)tok * p.H + r1]);
+          } else {
+            if (r0 < p.H) b0 = ld_tag(p.xt + r0, TAG(layer - 1, TG_XD), nowait);
+            if (r1 < p.H) b1 = ld_tag(p.xt + r1, TAG(layer - 1, TG_XD), nowait);
+          }
+        }
         if (r0 < p.H) st_tag(p.xt + r0, b0 + v, TAG(layer, TG_XO));
         if (r1 < p.H) st_tag(p.xt + r1, b1 + v1, TAG(layer, TG_XO));
       } else if (ph == PH_GU) {
@@ -586,7 +616,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         if (i < p.I) st_tag(p.ht + i, silu(v) * v1, TAG(layer, TG_H));
       } else if (ph == PH_DOWN) {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+        float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+        if (p.dbg_flags & 8) {
+          b0 = b1 = 0.f;
+          if (r0 < p.H) b0 = ld_tag(p.xt + r0, TAG(layer, TG_XO), nowait);
+          if (r1 < p.H) b1 = ld_tag(p.xt + r1, TAG(layer, TG_XO), nowait);
+        }
         if (r0 < p.H) st_tag(p.xt + r0, b0 + v, TAG(layer, TG_XD));
         if (r1 < p.H) st_tag(p.xt + r1, b1 + v1, TAG(layer, TG_XD));
       } else {
@@ -655,13 +690,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
         const bf16* vb = kb + p.kv_v_offset;
         const int hid = warp * 2 + hw;
-        for (int jb = as.j0; jb < as.j1; jb += 128) {   // warp-uniform trip count
+        const int nb8 = (p.dbg_flags & 32) ? 4 : 8;   // keys per batch (dev flag 32: 4)
+        for (int jb = as.j0; jb < as.j1; jb += 16 * nb8) {   // warp-uniform trip count
           uint4 kr[8], vr[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int j = jb + u * 16 + hid;
             kr[u] = vr[u] = make_uint4(0, 0, 0, 0);
-            if (j < as.j1) {
+            if (u < nb8 && j < as.j1) {
               kr[u] = __ldcg(reinterpret_cast<const uint4*>(kb + (int64_t)j * 128 + l16 * 8));
               vr[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (int64_t)j * 128 + l16 * 8));
             }
@@ -672,31 +708,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             float kf[8], vf[8];
             unpack8(kr[u], kf);
             unpack8(vr[u], vf);
-            key_update(kf, vf, j < as.j1);
+            key_update(kf, vf, u < nb8 && j < as.j1);
           }
         }
-        if (as.last && warp == 0) {
+        if (as.last && warp == 0) {   // the key/value of the token being decoded (produced in P1 of this launch)
           float nkf[8], nvf[8];
-          Spin sp;
-          const uint32_t tg = TAG(l, TG_QKV);
-          const uint4* qk = reinterpret_cast<const uint4*>(p.kvt + kvh * 128 + l16 * 8);
-          const uint4* qv = reinterpret_cast<const uint4*>(p.kvt + kd + kvh * 128 + l16 * 8);
-          uint4 a[4], b[4];
-          bool ok;
-          do {   // k and v rows together: one round trip
-            ok = true;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = __ldcg(qk + i); b[i] = __ldcg(qv + i); }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ok = ok && a[i].y == tg && a[i].w == tg && b[i].y == tg && b[i].w == tg;
-            if (nowait & 2) break;
-            if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
-          } while (!ok);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            nkf[2 * i] = __uint_as_float(a[i].x); nkf[2 * i + 1] = __uint_as_float(a[i].z);
-            nvf[2 * i] = __uint_as_float(b[i].x); nvf[2 * i + 1] = __uint_as_float(b[i].z);
-          }
+          ld_tag8(p.kvt + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, nkf);
+          ld_tag8(p.kvt + kd + kvh * 128 + l16 * 8, TAG(l, TG_QKV), nowait, nvf);
           key_update(nkf, nvf, hw == 0);
         }
       }
@@ -742,13 +760,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             for (int r = 0; r < 15; ++r) {
               if (r < as.cph - 1) {
                 const uint2* pp = p.partt + (int64_t)(r * p.heads + as.head) * 132;
-                const uint2 a = __ldcg(pp + 128), b = __ldcg(pp + 129), d = __ldcg(pp + tid);
+                const uint2 a = ld_poll2(pp + 128), b = ld_poll2(pp + 129), d = ld_poll2(pp + tid);
                 ok = ok && a.y == tg && b.y == tg && d.y == tg;
                 ms[r] = __uint_as_float(a.x); lv[r] = __uint_as_float(b.x); ov[r] = __uint_as_float(d.x);
               }
             }
             if (nowait & 2) break;
-            if (!ok) { sp.tick(); if (!(nowait & 4)) backoff(200); }
+            if (!ok) { sp.tick(p.partt, tg, 12345u); if (!(nowait & 4)) backoff(200); }
           }
           float MM = M;
 #pragma unroll
@@ -764,6 +782,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             }
           }
           st_tag(p.attnt + as.head * 128 + tid, OO / LL, TAG(l, TG_ATTN));
+          if (tid == 0 && (p.dbg_flags & 64)) printf("[dtk] merger cta %d layer %d head %d wrote attn tag %u val %f (M %f L %f)\n", c, l, as.head, TAG(l, TG_ATTN), OO / LL, MM, LL);
         }
       }
       consumer_sync();   // sm_* scratch (aliases xb) is free again
@@ -834,7 +853,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   if (actf < 32 + 16 * 128) actf = 32 + 16 * 128;  // attention merge scratch
   actf = (actf + 31) & ~31;
   a.act_floats = actf;
-  if ((I + 255) / 256 > NT - 40) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
+  if ((I + 255) / 256 > NT - 44) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
   const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
   if (nslots > 32) nslots = 32;

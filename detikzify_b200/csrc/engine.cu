@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -590,6 +591,7 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
         m.ht = t; t += c.inter;
         m.attnt = t; t += qd;
         m.partt = t;
+        if (getenv("DTK_DEBUG")) fprintf(stderr, "[dtk] tagged buffers: xt %p qt %p kvt %p ht %p attnt %p partt %p\n", (void*)m.xt, (void*)m.qt, (void*)m.kvt, (void*)m.ht, (void*)m.attnt, (void*)m.partt);
       }
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
