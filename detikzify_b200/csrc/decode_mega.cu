@@ -89,18 +89,22 @@ DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_T
 // plain store; readers poll the L2 copy (ld.cg) until the tag of the expected phase shows up. Write-after-read
 // hazards are excluded by the data-flow itself (a buffer is only rewritten by work that transitively depends
 // on every reader of the previous version; see DESIGN.md "decode synchronisation").
-DTK_DEV uint4 ld_poll4(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-  return r;
-}
+// Tagged values are exchanged with morally-strong, gpu-scope 8-byte accesses: weak ld/st (even .cg) carry no
+// coherence guarantee between SMs — on the two-die B200 a weak polling load can keep hitting a stale
+// die-local L2 copy forever (observed). A u64 access is single-copy atomic, so {value, tag} never tears.
 DTK_DEV uint2 ld_poll2(const uint2* p) {
-  uint2 r;
-  asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];\n" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-  return r;
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+// two consecutive pairs
+DTK_DEV uint4 ld_poll4(const uint4* p) {
+  const uint2 a = ld_poll2(reinterpret_cast<const uint2*>(p)), b = ld_poll2(reinterpret_cast<const uint2*>(p) + 1);
+  return make_uint4(a.x, a.y, b.x, b.y);
 }
 DTK_DEV void st_tag(uint2* p, float v, uint32_t tag) {
-  asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+  const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(w) : "memory");
 }
 DTK_DEV void backoff(int cycles) {
   const long long t = clock64();

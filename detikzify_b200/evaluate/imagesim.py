@@ -1,0 +1,68 @@
+"""SelfSim image similarity (the MCTS reward): the model's own vision tower encodes the rendered candidate
+and the input figure; mode "cos" = cosine of the attention-pooled vectors in fp64, "cos_avg" = cosine of
+mean patch tokens (reference detikzify/evaluate/imagesim.py:91-125; v1 models use "cos",
+detikzify/model/v1/configuration_detikzify.py:11-13). The "emd" mode of the v2 models needs the POT
+network-simplex solver (CPU, third party) and is out of scope.
+
+torchmetrics is not a dependency here: the ``update / compute / reset`` protocol the MCTS driver uses
+(infer/generate.py:293-298) is implemented directly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Union
+
+import torch
+import torch.nn.functional as F
+from PIL import Image
+
+from ..util.image import expand, load
+
+
+class ImageSim:
+    higher_is_better = True
+
+    def __init__(self, model=None, processor=None, mode: str = "cos", preprocess: bool = True, **_):
+        if mode not in ("cos", "cos_avg"):
+            raise NotImplementedError(f"ImageSim mode {mode!r} is not supported (cos / cos_avg)")
+        self.model, self.processor = model, processor
+        self.mode, self.preprocess = mode, preprocess
+        self.reset()
+
+    def __str__(self):
+        return self.__class__.__name__ + f" ({self.mode.upper().replace('_', '-')})"
+
+    @classmethod
+    def from_detikzify(cls, model, processor, mode=None, *args, **kwargs):
+        from ..util.generation import unwrap_processor
+        kwargs.pop("sync_on_compute", None)
+        mode = getattr(model.config, "pooling_mode", "cos") if mode is None else mode
+        return cls(model=model.model.vision_model, processor=unwrap_processor(processor).image_processor, mode=mode, **kwargs)
+
+    def get_vision_features(self, image: Union[Image.Image, str]) -> torch.Tensor:
+        image = load(image)
+        if self.preprocess:
+            image = expand(image, max(image.size), do_trim=True)
+        with torch.inference_mode():
+            pixel_values = self.processor(images=image, return_tensors="pt")["pixel_values"]
+            out = self.model(pixel_values=pixel_values)
+            if self.mode == "cos":
+                return out.pooler_output.squeeze()
+            return out.last_hidden_state.squeeze().mean(dim=0)
+
+    def get_similarity(self, img1=None, img2=None, **_) -> float:
+        f1, f2 = self.get_vision_features(img1), self.get_vision_features(img2)
+        return F.cosine_similarity(f1.double(), f2.double(), dim=0).item()
+
+    def update(self, img1=None, img2=None, text1=None, text2=None):
+        imgs1 = img1 if isinstance(img1, list) else [img1]
+        imgs2 = img2 if isinstance(img2, list) else [img2]
+        assert len(imgs1) == len(imgs2) and all(i is not None for i in imgs1 + imgs2)
+        for a, b in zip(imgs1, imgs2):
+            self.score += self.get_similarity(a, b)
+            self.n_samples += 1
+
+    def compute(self) -> float:
+        return self.score / self.n_samples
+
+    def reset(self):
+        self.score, self.n_samples = 0.0, 0

@@ -20,6 +20,7 @@ expansion prefills only the tree-path suffix instead of re-encoding the image an
 from __future__ import annotations
 
 import threading
+from contextlib import nullcontext
 from types import SimpleNamespace
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -54,9 +55,9 @@ class DetikzifyVisionModel:
 
     def forward(self, pixel_values: torch.Tensor) -> VisionOutput:
         o = self._owner
-        with o._lock, torch.cuda.stream(o._stream):
+        with o._lock, o._on_stream():
             tokens, pooled = o.engine.vit_encode(pixel_values)
-            o._stream.synchronize()
+            o._sync()
         return VisionOutput(last_hidden_state=tokens.to(o.dtype), pooler_output=pooled.to(o.dtype))
 
     def get_intermediate_layers(self, pixel_values: torch.Tensor, n=None, norm: bool = True, **_):
@@ -73,24 +74,34 @@ class _Inner:
 
 
 class DetikzifyForCausalLM:
-    def __init__(self, config: DetikzifyConfig, arena: torch.Tensor, device=0, dtype=torch.bfloat16,
-                 max_seqs: int = 2, max_batch: int = 1, max_len: Optional[int] = None):
+    def __init__(self, config: DetikzifyConfig, arena: Optional[torch.Tensor] = None, device=0, dtype=torch.bfloat16,
+                 max_seqs: int = 2, max_batch: int = 1, max_len: Optional[int] = None, engine=None):
         self.config = config
         self.dtype = dtype
         self.name_or_path = config.name_or_path
-        self.engine = Engine(config, arena, device=device, max_seqs=max_seqs, max_batch=max_batch, max_len=max_len)
+        # ``engine`` injection exists for host-logic tests (a scripted engine on CPU); the product path always
+        # builds the CUDA engine and raises if no device / library is available.
+        self.engine = engine if engine is not None else Engine(config, arena, device=device, max_seqs=max_seqs,
+                                                                max_batch=max_batch, max_len=max_len)
         self.device = self.engine.device
         self.generation_config = GenerationConfig(
             max_length=config.model_max_length, do_sample=False, temperature=1.0, top_p=1.0, top_k=0,
             bos_token_id=config.bos_token_id, eos_token_id=config.eos_token_id, pad_token_id=config.pad_token_id)
         self.model = _Inner(self)
         self._lock = threading.Lock()
-        self._stream = torch.cuda.Stream(device=self.device)
+        self._stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._slot = self.engine.seq_alloc()
         self._slot_tokens: List[int] = []      # token history whose KV is valid in the working slot
         self._slot_image_key = None
         self._img_cache = None                  # (pixel tensor on device, image embeds [P,H])
         self._call_counter = 0
+
+    def _on_stream(self):
+        return torch.cuda.stream(self._stream) if self._stream is not None else nullcontext()
+
+    def _sync(self):
+        if self._stream is not None:
+            self._stream.synchronize()
 
     # ---- reference-compat trivia ---------------------------------------------------------------
     def eval(self):
@@ -156,7 +167,7 @@ class DetikzifyForCausalLM:
         max_length = min(int(max_length), eng.max_len)
         criteria = StoppingCriteriaList(stopping_criteria or [])
 
-        with self._lock, torch.cuda.stream(self._stream):
+        with self._lock, self._on_stream():
             # -- splice validation (v1/modeling_detikzify.py:176-184)
             img, img_start = None, 0
             patch = cfg.image_token_id
@@ -187,7 +198,9 @@ class DetikzifyForCausalLM:
                 L += 1
             if img is not None and L < img_start + n_patch_tokens:
                 L = min(L, img_start)  # never split the image span
-            ids_dev = torch.tensor(ids_host[L:], dtype=torch.int64).pin_memory().to(self.device, non_blocking=True)
+            ids_dev = torch.tensor(ids_host[L:], dtype=torch.int64)
+            if self.device.type == "cuda":
+                ids_dev = ids_dev.pin_memory().to(self.device, non_blocking=True)
             last_logits, _ = eng.prefill(self._slot, ids_dev, L, img, img_start)
             self._slot_tokens = list(ids_host)
 
@@ -236,9 +249,9 @@ class DetikzifyForCausalLM:
     # ---- SelfSim helper: pooled features straight from the engine --------------------------------
     @torch.no_grad()
     def pooled_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
-        with self._lock, torch.cuda.stream(self._stream):
+        with self._lock, self._on_stream():
             _, pooled = self.engine.vit_encode(pixel_values, want_tokens=False)
-            self._stream.synchronize()
+            self._sync()
         return pooled
 
     def close(self):

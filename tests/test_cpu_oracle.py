@@ -1,0 +1,98 @@
+"""The oracle (test infrastructure) against its committed golden fixtures and against the invariants the
+reference's semantics imply: KV-cached decode == full forward, concat-3 ordering, splice
+validation, logits-processor order, HF generate == the oracle's own loop."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import model_bundle
+
+GOLD = torch.load(Path(__file__).parent / "golden" / "tiny_oracle.pt", weights_only=False)
+
+
+def _pix(cfg, n=1, seed=1000):
+    from oracle.hf_oracle import synthetic_pixels
+    return synthetic_pixels(n, cfg.vision_config.image_size, seed)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_oracle_matches_golden_fixtures(name):
+    cfg, sd, o = model_bundle(name)
+    g = GOLD[name]
+    pix = _pix(cfg)
+    tok, pooled = o.vision(pix)
+    assert abs(tok.double().sum().item() - g["vit_tokens_sum"]) < 1e-2
+    torch.testing.assert_close(tok[0, 0, :16], g["vit_tokens_row0"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(pooled[0], g["pooled"], rtol=1e-4, atol=1e-5)
+    img = o.image_embeds(pix)
+    torch.testing.assert_close(img[0, 0, :32], g["img_embeds_row0"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(img[0, -1, :32], g["img_embeds_last"], rtol=1e-4, atol=1e-5)
+    logits, _ = o.forward_logits(g["ids"][None], pix)
+    torch.testing.assert_close(logits[0, -1], g["last_logits"], rtol=1e-4, atol=1e-5)
+    greedy = o.generate(g["ids"][None], pix, max_length=g["ids"].numel() + 16, stop_on_eos=False)[0]
+    assert torch.equal(greedy, g["greedy"])
+
+
+def test_cached_decode_equals_full_forward():
+    cfg, sd, o = model_bundle("tiny")
+    pix = _pix(cfg)
+    ids = GOLD["tiny"]["ids"][None]
+    logits, cache = o.forward_logits(ids, pix, use_cache=True)
+    nxt = torch.tensor([[9]])
+    step, _ = o.decode_logits(nxt, cache)
+    full, _ = o.forward_logits(torch.cat([ids, nxt], 1), pix)
+    assert (step[:, -1] - full[:, -1]).abs().max() < 1e-5
+
+
+def test_concat3_takes_last_tokens_row_major():
+    """[B, N, D] -> last 3P tokens -> [B, P, 3D] (v1/modeling_detikzify.py:132-137); tiny has N=16, P=5."""
+    cfg, sd, o = model_bundle("tiny")
+    pix = _pix(cfg)
+    tok, _ = o.vision(pix)
+    P, D = cfg.num_patches, cfg.vision_config.hidden_size
+    manual = torch.cat([tok[0, -3 * P + 3 * r: -3 * P + 3 * r + 3].reshape(-1) for r in range(P)]).view(P, 3 * D)
+    ref = torch.nn.functional.linear(manual, o.proj_w, o.proj_b)
+    assert (o.image_embeds(pix)[0] - ref).abs().max() < 1e-6
+
+
+def test_splice_validation_errors():
+    cfg, sd, o = model_bundle("tiny")
+    pix = _pix(cfg)
+    P, tok = cfg.num_patches, cfg.patch_token_id
+    bad_count = torch.tensor([[tok] * (P - 1) + [5, 6]])
+    with pytest.raises(ValueError, match="number of image patch tokens"):
+        o.forward_logits(bad_count, pix)
+    gap = torch.tensor([[tok] * (P - 1) + [5, tok]])
+    with pytest.raises(ValueError, match="consecutive"):
+        o.forward_logits(gap, pix)
+
+
+def test_processor_order_and_nucleus():
+    cfg, sd, o = model_bundle("tiny")
+    V = cfg.vocab_size
+    torch.manual_seed(0)
+    logits = torch.randn(1, V)
+    logits[0, cfg.image_token_id] = 100.0
+    logits[0, cfg.eos_token_id] = 50.0
+    ids = torch.zeros(1, 10, dtype=torch.long)
+    p_first = o.processed_probs(ids, logits, 10, temperature=0.8, top_p=0.9, top_k=0)[0]
+    assert p_first[cfg.image_token_id] == 0 and p_first[cfg.eos_token_id] == 0     # bad word + begin-suppress
+    p_later = o.processed_probs(torch.zeros(1, 12, dtype=torch.long), logits, 10, temperature=0.8, top_p=0.9, top_k=0)[0]
+    assert p_later[cfg.image_token_id] == 0 and p_later[cfg.eos_token_id] > 0.99   # EOS only masked at the first step
+    # minimal nucleus: dropping the least likely kept token leaves < top_p mass (of the pre-warp distribution)
+    base = torch.softmax(torch.where(torch.arange(V) == cfg.image_token_id, -float("inf"), logits[0].clone().index_fill(0, torch.tensor([cfg.eos_token_id]), -float("inf"))) / 0.8, -1)
+    kept = p_first > 0
+    assert base[kept].sum() >= 0.9 - 1e-6
+    assert base[kept].sum() - base[kept].min() < 0.9 + 1e-6
+    assert abs(p_first.sum() - 1) < 1e-5
+
+
+def test_hf_generate_equals_oracle_loop():
+    cfg, sd, o = model_bundle("tiny")
+    pix = _pix(cfg)
+    ids = GOLD["tiny"]["ids"][None]
+    a = o.generate(ids, pix, max_length=ids.shape[1] + 12)
+    b = o.hf_generate(ids, pix, max_length=ids.shape[1] + 12, do_sample=False)
+    assert torch.equal(a, b)
+    assert a.shape[1] <= ids.shape[1] + 12   # max_length counts the prompt (reference quirk B.4)
