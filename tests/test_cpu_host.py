@@ -1,0 +1,262 @@
+"""Host-side logic on CPU: tokenizer / processor / streamers, the generate() loop contract of the model
+object (driven by a scripted engine), the MCTS driver, SelfSim protocol, figure sharding helpers."""
+import threading
+
+import pytest
+import torch
+from PIL import Image, ImageDraw
+
+from scripted_engine import ScriptedEngine
+
+
+def _model(eos_at=None, max_len=None):
+    from detikzify_b200.model import build_processor, preset
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    cfg = preset("tiny")
+    eng = ScriptedEngine(cfg, max_len=max_len, eos_at=eos_at)
+    return DetikzifyForCausalLM(cfg, engine=eng), build_processor(cfg), eng
+
+
+def _figure(size=90):
+    im = Image.new("RGB", (size, size + 20), "white")
+    d = ImageDraw.Draw(im)
+    d.line((10, 10, size - 10, size - 5), fill="black", width=3)
+    d.ellipse((20, 30, 50, 60), outline="black")
+    return im
+
+
+# ------------------------------------------------------------------ tokenizer / processor
+def test_tokenizer_roundtrip_and_specials():
+    from detikzify_b200.model import build_processor, preset
+    cfg = preset("tiny")
+    proc = build_processor(cfg)
+    tok = proc.tokenizer
+    text = "\\begin{tikzpicture}\n\\draw (0,0) -- (1,1);\n\\end{tikzpicture}\n"
+    ids = tok(text=text)["input_ids"][0]
+    assert tok.decode(ids) == text
+    assert len(ids) < len(text)                      # multi-character tokens are used
+    assert tok.decode([cfg.bos_token_id, 65, cfg.eos_token_id], skip_special_tokens=True) == "A"
+    assert proc.image_token == tok.convert_ids_to_tokens(cfg.patch_token_id)
+    assert tok.model_max_length == cfg.model_max_length
+
+
+def test_processor_prompt_layout_and_pixels():
+    from detikzify_b200.model import build_processor, preset
+    cfg = preset("tiny")
+    proc = build_processor(cfg)
+    out = proc(images=_figure(), text="ab", return_tensors="pt", text_kwargs={"truncation": True})
+    ids = out.input_ids[0].tolist()
+    assert ids[: cfg.num_patches] == [cfg.patch_token_id] * cfg.num_patches and ids[cfg.num_patches:] == [97, 98]
+    pv = out["pixel_values"]
+    assert pv.shape == (1, 3, 56, 56) and pv.dtype == torch.float32
+    assert pv.max() <= 1.0 + 1e-6 and pv.min() >= -1.0 - 1e-6 and pv.max() > 0.99   # white background -> +1
+    assert set(out.to("cpu").keys()) == {"pixel_values", "input_ids", "attention_mask"}
+    with pytest.raises(ValueError):
+        proc(text="x", images=None)
+
+
+def test_streamers_contract():
+    from detikzify_b200.util import StreamerList, TextIteratorStreamer, TokenStreamer
+    from detikzify_b200.model import build_processor, preset
+    st = TokenStreamer()
+    st.put(torch.tensor([[1, 2, 3]]))          # prompt is skipped
+    st.put(torch.tensor([7]))
+    st.put(torch.tensor([8]))
+    st.end()
+    assert list(st) == [7, 8]
+    with pytest.raises(ValueError):
+        TokenStreamer().put(torch.zeros(2, 3))
+    st2 = TokenStreamer()
+    st2.propagate_error(RuntimeError("boom"))
+    with pytest.raises(RuntimeError, match="boom"):
+        next(st2)
+    tok = build_processor(preset("tiny")).tokenizer
+    ts = TextIteratorStreamer(tok, skip_prompt=True, skip_special_tokens=True)
+    sl = StreamerList([ts])
+    sl.put(torch.tensor([[500, 500]]))
+    for t in tok.encode("\\draw (0,0);\n"):
+        sl.put(torch.tensor([t]))
+    sl.end()
+    assert "".join(ts) == "\\draw (0,0);\n"
+
+
+# ------------------------------------------------------------------ generate() contract (scripted engine)
+def _prompt(cfg, extra=(65, 66)):
+    return torch.tensor([[cfg.patch_token_id] * cfg.num_patches + list(extra)])
+
+
+def test_generate_streams_prompt_then_tokens_then_end():
+    from detikzify_b200.util import TokenStreamer
+    model, proc, eng = _model(eos_at=30)
+    cfg = model.config
+    ids = _prompt(cfg)
+    st = TokenStreamer(skip_prompt=False)
+    out = model.generate(input_ids=ids, pixel_values=torch.zeros(1, 3, 56, 56), streamer=st,
+                         bad_words_ids=[[cfg.image_token_id]], begin_suppress_tokens=[cfg.eos_token_id], max_length=64)
+    streamed = list(st)
+    assert out.shape[0] == 1 and out[0, : ids.shape[1]].tolist() == ids[0].tolist()
+    assert streamed == out[0].tolist()                      # prompt first, then one put per token, then end()
+    assert out[0, -1] == cfg.eos_token_id and (out[0, :-1] != cfg.eos_token_id).all()
+    assert cfg.image_token_id not in out[0, ids.shape[1]:].tolist()
+    assert ("sample", True) in eng.calls                    # EOS suppressed on the first new token only
+    assert eng.calls[-1] == ("gen_end",)
+
+
+def test_generate_max_length_counts_prompt_and_early_returns():
+    from detikzify_b200.util import TokenStreamer
+    model, proc, eng = _model()
+    cfg = model.config
+    ids = _prompt(cfg)
+    out = model.generate(input_ids=ids, pixel_values=torch.zeros(1, 3, 56, 56), max_length=ids.shape[1] + 9)
+    assert out.shape[1] == ids.shape[1] + 9
+    steps = [c for c in eng.calls if c == ("gen_step",)]
+    assert len(steps) == 8                                   # first token from prefill, n-1 decode steps, no overrun
+    st = TokenStreamer()
+    out2 = model.generate(input_ids=ids, pixel_values=torch.zeros(1, 3, 56, 56), max_length=ids.shape[1], streamer=st)
+    assert out2.shape == ids.shape and list(st) == []        # nothing to do, but the stream is still terminated
+
+
+def test_generate_abort_within_one_token_and_errors_escape():
+    from detikzify_b200.util import ExplicitAbort, TokenStreamer
+    model, proc, eng = _model()
+    cfg = model.config
+    ids = _prompt(cfg)
+    ctl = ExplicitAbort()
+    seen = []
+
+    class Spy(TokenStreamer):
+        def put(self, value):
+            super().put(value)
+            if value.dim() == 1:
+                seen.append(int(value))
+                if len(seen) == 5:
+                    ctl.abort()
+    out = model.generate(input_ids=ids, pixel_values=torch.zeros(1, 3, 56, 56), streamer=Spy(), stopping_criteria=[ctl], max_length=90)
+    assert out.shape[1] == ids.shape[1] + 5                  # abort observed right after the 5th token
+    bad = torch.tensor([[cfg.patch_token_id] * (cfg.num_patches - 1) + [65, cfg.patch_token_id]])
+    with pytest.raises(ValueError, match="consecutive"):
+        model.generate(input_ids=bad, pixel_values=torch.zeros(1, 3, 56, 56), max_length=40)
+    with pytest.raises(ValueError, match="number of image patch tokens"):
+        model.generate(input_ids=bad[:, 1:-1], pixel_values=torch.zeros(1, 3, 56, 56), max_length=40)
+
+
+def test_generate_reuses_image_features_and_kv_prefix():
+    model, proc, eng = _model()
+    cfg = model.config
+    pix = torch.rand(1, 3, 56, 56)
+    ids = _prompt(cfg, extra=(65, 66, 67))
+    out = model.generate(input_ids=ids, pixel_values=pix, max_length=ids.shape[1] + 6)
+    n_img = sum(1 for c in eng.calls if c[0] == "image_embeds")
+    # second call: same figure, prompt = previous output prefix + 2 tokens -> only the suffix is prefilled
+    ids2 = torch.cat([out[:, : ids.shape[1] + 3], torch.tensor([[70, 71]])], dim=1)
+    eng.calls.clear()
+    model.generate(input_ids=ids2, pixel_values=pix.clone(), max_length=ids2.shape[1] + 4)
+    pre = [c for c in eng.calls if c[0] == "prefill"][0]
+    assert sum(1 for c in eng.calls if c[0] == "image_embeds") == 0 and n_img == 1
+    assert pre[2] == ids.shape[1] + 3 and pre[3] == 2        # start_pos = common prefix, 2 new tokens
+    # a different figure invalidates both caches
+    eng.calls.clear()
+    model.generate(input_ids=ids2, pixel_values=torch.rand(1, 3, 56, 56), max_length=ids2.shape[1] + 2)
+    pre = [c for c in eng.calls if c[0] == "prefill"][0]
+    assert ("image_embeds", (1, 3, 56, 56)) in eng.calls and pre[2] == 0 and pre[3] == ids2.shape[1]
+
+
+# ------------------------------------------------------------------ MCTS driver
+def _fake_renderer():
+    def render(code: str):
+        if "<t" in code[:0]:
+            return None
+        im = Image.new("RGB", (64, 64), "white")
+        d = ImageDraw.Draw(im)
+        for i, ch in enumerate(code[:40]):
+            d.point(((ord(ch) * 7 + i) % 64, (ord(ch) * 13 + 3 * i) % 64), fill="black")
+        return im
+    return render
+
+
+def test_pipeline_sample_and_mcts_simulate(monkeypatch):
+    from detikzify_b200.infer import DetikzifyPipeline, TikzDocument
+    model, proc, eng = _model(eos_at=40)
+    monkeypatch.setattr(TikzDocument, "backend", staticmethod(_fake_renderer()))
+    pipe = DetikzifyPipeline(model, proc, metric="model")
+    assert pipe.gen_kwargs["max_length"] == proc.tokenizer.model_max_length and pipe.gen_kwargs["do_sample"]
+    doc = pipe.sample(image=_figure())
+    assert isinstance(doc, TikzDocument) and ";\n" in doc.code
+    results = list(pipe.simulate(image=_figure(), expansions=4))
+    assert len(results) == 4
+    for score, tikz in results:
+        assert -1.0 <= score <= 1.0 + 1e-9 and tikz.is_rasterizable
+    with pytest.raises(AssertionError):
+        pipe.sample(image=_figure(), text="caption")          # no adapter loaded
+
+
+def test_mcts_tree_growth_and_failed_rollout_memo(monkeypatch):
+    from detikzify_b200.infer import DetikzifyGenerator, TikzDocument
+    model, proc, eng = _model(eos_at=36)
+    monkeypatch.setattr(TikzDocument, "backend", staticmethod(lambda code: None))   # nothing compiles
+    gen = DetikzifyGenerator(model, proc, image=_figure(), metric=None, max_length=proc.tokenizer.model_max_length,
+                             temperature=0.8, top_p=0.95, top_k=0, do_sample=True)
+    outs = [next(gen.simulate(expansions=1)) for _ in range(3)]
+    assert all(score <= 0 for score, _ in outs)
+    root = gen.montecarlo.root_node
+    assert root.visits >= 3 and root.children[0].is_widen_node
+    assert gen.newlineinfo[257].num_lines == 1 and gen.newlineinfo[257].trailing
+
+
+def test_reference_mcts_module_is_drop_in():
+    """The reference's vendored MCTS (importable offline) drives our generator unchanged."""
+    import importlib.util
+    import os
+    base = "/root/reference/detikzify/mcts"
+    if not os.path.isdir(base):
+        pytest.skip("reference checkout not available on this box")
+    mods = {}
+    for n in ("node", "montecarlo"):
+        spec = importlib.util.spec_from_file_location(f"refmcts_{n}", f"{base}/{n}.py")
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods[n] = m
+    ours_node = __import__("detikzify_b200.mcts.node", fromlist=["Node"]).Node
+    ref, mine = mods["node"].Node("s"), ours_node("s")
+    for obj in (ref, mine):
+        child = type(obj)("c")
+        obj.add_child(child)
+        child.update_policy_value(1.0)
+        child.update_win_value(0.5)
+    assert ref.visits == mine.visits == 1 and ref.win_value == mine.win_value == 0.5
+    assert ref.children[0].get_score(ref) == pytest.approx(mine.children[0].get_score(mine))
+    assert set(vars(ref)) <= set(vars(mine))
+
+
+def test_dyn_minmax_norm():
+    from detikzify_b200.infer import DynMinMaxNorm
+    norm = DynMinMaxNorm()
+    a = norm(0.2)
+    assert a.score == 0                                       # single value -> default
+    b = norm(0.8)
+    assert a.score == 0.0 and b.score == 1.0                  # lazily re-normalised
+    c = norm(0.5) + b + 3
+    assert c.score == pytest.approx(0.5 + 1.0 + 3)
+    assert (b * 2) == 2.0 and (1 / b) == 1.0
+
+
+def test_imagesim_protocol():
+    from detikzify_b200.evaluate import ImageSim
+    model, proc, eng = _model()
+    sim = ImageSim.from_detikzify(model, proc)
+    sim.update(img1=_figure(), img2=_figure())
+    assert sim.compute() == pytest.approx(1.0)
+    sim.reset()
+    other = Image.new("RGB", (80, 80), "white")
+    ImageDraw.Draw(other).rectangle((5, 5, 70, 70), fill="black")
+    sim.update(img1=_figure(), img2=other)
+    assert sim.compute() < 1.0
+    with pytest.raises(NotImplementedError):
+        ImageSim(mode="emd")
+
+
+def test_shard_and_interleave():
+    from detikzify_b200.parallel import interleave, shard
+    items = list(range(11))
+    chunks = [shard(items, r, 4) for r in range(4)]
+    assert chunks[1] == [1, 5, 9] and interleave(chunks) == items

@@ -51,7 +51,9 @@ def test_concat3_takes_last_tokens_row_major():
     pix = _pix(cfg)
     tok, _ = o.vision(pix)
     P, D = cfg.num_patches, cfg.vision_config.hidden_size
-    manual = torch.cat([tok[0, -3 * P + 3 * r: -3 * P + 3 * r + 3].reshape(-1) for r in range(P)]).view(P, 3 * D)
+    N = tok.shape[1]
+    assert N == 16 and N - 3 * P == 1   # the first patch token is dropped
+    manual = torch.cat([tok[0, N - 3 * P + 3 * r: N - 3 * P + 3 * r + 3].reshape(-1) for r in range(P)]).view(P, 3 * D)
     ref = torch.nn.functional.linear(manual, o.proj_w, o.proj_b)
     assert (o.image_embeds(pix)[0] - ref).abs().max() < 1e-6
 
