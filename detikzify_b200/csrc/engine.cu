@@ -151,7 +151,6 @@ struct dtk_engine {
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
-  int mega_depth = 2;
 };
 
 namespace {
@@ -373,7 +372,6 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
-    m.prod_depth = eng->mega_depth;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -578,24 +576,15 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
       m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
-      m.logits = eng->d_logits;
-      {  // tagged cross-CTA activation buffers: xt[H] qt[qd] kvt[2kd] ht[I] attnt[qd] partt[grid*132]
-        const int64_t kd2 = 2 * (int64_t)c.kv_heads * 128;
-        const int64_t n = (int64_t)c.hidden + qd + kd2 + c.inter + qd + (int64_t)grid * 132;
-        DTK_ALLOC(eng->d_tagged, n);
-        DTK_CK(cudaMemset(eng->d_tagged, 0, n * sizeof(uint2)));
-        uint2* t = eng->d_tagged;
-        m.xt = t; t += c.hidden;
-        m.qt = t; t += qd;
-        m.kvt = t; t += kd2;
-        m.ht = t; t += c.inter;
-        m.attnt = t; t += qd;
-        m.partt = t;
-        if (getenv("DTK_DEBUG")) fprintf(stderr, "[dtk] tagged buffers: xt %p qt %p kvt %p ht %p attnt %p partt %p\n", (void*)m.xt, (void*)m.qt, (void*)m.kvt, (void*)m.ht, (void*)m.attnt, (void*)m.partt);
-      }
+      m.x = eng->d_x; m.q = eng->d_q; m.h = eng->d_h; m.logits = eng->d_logits;
+      DTK_ALLOC(eng->d_part, (int64_t)grid * 132);
       DTK_ALLOC(eng->d_bar, 2);
       DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
-      m.epoch = eng->d_bar;
+      m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
+      m.attn = eng->d_att;
+      DTK_ALLOC(eng->d_head_cnt, c.heads);
+      DTK_CK(cudaMemset(eng->d_head_cnt, 0, c.heads * sizeof(unsigned int)));
+      m.head_cnt = eng->d_head_cnt;
       DTK_ALLOC(eng->d_dbg, (int64_t)grid * (c.layers * 5 + 1) * 4);
       DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)grid * (c.layers * 5 + 1) * 4 * sizeof(long long)));
       m.dbg = nullptr;
@@ -953,11 +942,6 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "mega_flags") == 0) {  // dev only (timing experiments; results are garbage when set)
     eng->mega_flags = (int)value;
-    return DTK_OK;
-  }
-  if (std::strcmp(key, "mega_depth") == 0) {  // outstanding bulk copies per producer warp (1..8)
-    DTK_REQUIRE(value >= 1 && value <= 8, "mega_depth must be in 1..8");
-    eng->mega_depth = (int)value;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_debug") == 0) {

@@ -169,15 +169,13 @@ struct MegaArgs {
   bf16* kv;
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
   const float* rope_cs;
-  // Cross-CTA activations carry their own synchronisation: every element is an 8-byte {fp32 bits, epoch tag}
-  // pair written with one store and polled by its consumer (no grid barrier, no fence, one L2 round trip).
-  uint2 *xt, *qt, *kvt, *ht, *attnt, *partt;                  // [H] [qd] [2*kd] [I] [qd] [grid][132]
-  float* logits;
-  unsigned long long* epoch;                                  // tag base; advanced by 8L+8 per launch
+  float *x, *q, *h, *part, *logits;                           // part: [grid][132] attention partials
+  float* attn;                                                // [heads*128] merged attention output
+  unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
+  unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
-  int prod_depth;                                             // outstanding bulk copies per producer warp (x4 per SM)
-  int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = do not wait for tags
-  long long* dbg;                                             // optional: [3 CTAs][5L+1][4] clock64 stamps (null = off)
+  int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
+  long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
 };
 int mega_smem_bytes(const MegaArgs& a);
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out);

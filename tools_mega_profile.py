@@ -22,14 +22,10 @@ def timeit(label):
         eng.decode([slot], [ctx], tok)
     ev1.record(); torch.cuda.synchronize()
     print(f"{label}: ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
-for depth in (2, 6):
-    eng.set_option("mega_depth", depth)
-    timeit(f"depth={depth}")
-eng.set_option("mega_depth", int(sys.argv[3]) if len(sys.argv) > 3 else 2)
-for flags in (2, 0):
+timeit("default")
+for flags in (1, 2, 4, 0):
     eng.set_option("mega_flags", flags)
-    timeit(f"flags={flags} (1=no mma, 2=no tag waits, 4=no backoff)")
-eng.set_option("mega_flags", int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+    timeit(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive)")
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
@@ -60,10 +56,3 @@ for layer in range(L):
         cnt[int(d.argmax())] += 1
 print("CTAs most often last to finish a phase:", cnt.most_common(12))
 
-layer = L // 2
-d = t[:, layer * 5 + 1]
-qd_done = t[:, layer * 5 + 0, 2].max()
-print("attention phase of layer", layer, "(us after the last CTA finished qkv): per CTA  q-arrived / keys-done / phase-done")
-order = d[:, 2].argsort()
-for c in list(order[:4].tolist()) + list(order[-24:].tolist()):
-    print(f"  cta {c:3d}: {(d[c,1]-qd_done).item()/1e3:7.2f} {(d[c,3]-qd_done).item()/1e3:7.2f} {(d[c,2]-qd_done).item()/1e3:7.2f}")
