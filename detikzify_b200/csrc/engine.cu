@@ -940,6 +940,11 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->decode_impl = (int)value;
     return DTK_OK;
   }
+  if (std::strcmp(key, "gemm_impl") == 0) {  // process-wide dev switch: 0 = mma.sync, 1 = tcgen05 where supported
+    DTK_REQUIRE(value == 0 || value == 1, "gemm_impl must be 0 or 1");
+    set_gemm_impl((int)value);
+    return DTK_OK;
+  }
   if (std::strcmp(key, "mega_flags") == 0) {  // dev only (timing experiments; results are garbage when set)
     eng->mega_flags = (int)value;
     return DTK_OK;
@@ -961,6 +966,11 @@ int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values) {
   DTK_CK(cudaDeviceSynchronize());
   DTK_CK(cudaMemcpy(out_host, eng->d_dbg, (size_t)(n < max_values ? n : max_values) * sizeof(long long), cudaMemcpyDeviceToHost));
   return n;
+}
+
+int dtk_dbg_gemm_impl(int impl) {
+  if (impl >= 0) set_gemm_impl(impl);
+  return get_gemm_impl();
 }
 
 int dtk_dbg_gemm(const void* A, const void* Wm, const void* bias, const float* resid, int M, int N, int K, int act,

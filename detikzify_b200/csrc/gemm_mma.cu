@@ -156,7 +156,17 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_tn_kernel(const GemmArgs p)
 
 }  // namespace
 
+static int g_gemm_impl = 0;  // flipped to 1 by the engine once validated on the device (see dtk_set_option "gemm_impl")
+void set_gemm_impl(int impl) { g_gemm_impl = impl; }
+int get_gemm_impl() { return g_gemm_impl; }
+
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  // large-M dense contractions go to the tcgen05/TMEM kernel; tiny M (pool head, M = B) stays on mma.sync
+  if (g_gemm_impl == 1 && a.M >= 64 && gemm_tc_supported(a)) return launch_gemm_tc(a, s, counter);
+  return launch_gemm_mma(a, s, counter);
+}
+
+cudaError_t launch_gemm_mma(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
   if ((a.K & 7) || (a.N & 1) || (a.lda & 7) || (a.ldw & 7)) return cudaErrorInvalidValue;
   static bool attr_done = false;

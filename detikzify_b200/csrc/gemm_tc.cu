@@ -1,0 +1,239 @@
+// tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (bf16 operands, fp32 accumulate in TMEM) — the Blackwell tensor path for
+// the dense contractions of the ViT (qkv / out / fc1+GELU / fc2, patch embed) and the LLaMA prefill (qkv, o, gate/up
+// with SiLU*mul, down), with the same fused epilogues as gemm_mma.cu (bias, GELU, position rows, residual, GLU).
+//
+// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
+//   warp 4  TMA producer : cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 128 rows x 64 k) for A and W into a
+//                          3-stage shared-memory ring, mbarrier complete_tx
+//   warp 5  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 x N128 x K16) from
+//                          shared-memory descriptors into a 128-column TMEM accumulator; tcgen05.commit releases ring
+//                          slots and finally signals the epilogue
+//   warps 0-3 epilogue   : tcgen05.ld 32x32b (warp w owns TMEM lanes 32w..32w+31 = output rows), epilogue math in
+//                          registers, 128-byte row segments stored to global
+// 96 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, so one tile's epilogue overlaps the other
+// tile's main loop. Out-of-range rows / the K tail are zero-filled by TMA.
+// All mbarrier waits are bounded (trap instead of hanging the GPU).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace dtk {
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
+constexpr int TC_THREADS = 192;
+constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = TBN * TBK * 2;       // 16 KB each
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TC_SMEM = TSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr long long TC_SPIN = 2000000000ll;
+
+DTK_DEV void tc_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
+DTK_DEV void tc_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory"); }
+DTK_DEV void tc_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && (++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TC_SPIN) __trap();
+    }
+  }
+}
+DTK_DEV void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1<<16 |
+// SBO = 1024 B (8 rows x 128 B) >> 4 at bit 32 | version 1 at bit 46 | layout SWIZZLE_128B (2) at bit 61
+DTK_DEV uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+DTK_DEV void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DTK_DEV void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+struct TcArgs {
+  GemmArgs g;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = sbase + TSTAGES * STAGE_BYTES;              // full[3] empty[3] tmem_full, tmem ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull = bars + 16 * TSTAGES, tptr = tfull + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  const int KT = (p.K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
+    tc_mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 5) {  // TMEM allocation: 128 fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tptr), "n"(TBN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tptr));
+
+  if (warp == 4) {
+    // ===== TMA producer
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES, use = kt / TSTAGES;
+        if (use > 0) tc_wait(empty0 + 8 * s, (use - 1) & 1);
+        const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
+        tc_expect_tx(full0 + 8 * s, STAGE_BYTES);
+        tma_load_2d(sa, &mapA, kt * TBK, m0, full0 + 8 * s);
+        tma_load_2d(sb, &mapB, kt * TBK, n0, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at bit 17, M>>4 at bit 24)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES, use = kt / TSTAGES;
+        tc_wait(full0 + 8 * s, use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TBK / 16; ++k) {
+          // advancing K by 16 elements (32 B) inside the 128-byte swizzle atom = +2 in the (>>4) start-address field
+          umma_f16(tmem, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (kt | k) != 0);
+        }
+        umma_commit(empty0 + 8 * s);          // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(tfull);                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 0..3: TMEM lanes 32w..32w+31 = rows m0 + 32w + lane
+    tc_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int m = m0 + warp * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < TBN; cb += 32) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(trow + (uint32_t)cb));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (m < p.M) {
+        const int nb = n0 + cb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int n = nb + j;
+          if (n >= p.N) break;
+          float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+          if (p.bias) {
+            const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.bias + n));
+            v0 += b.x; v1 += b.y;
+          }
+          if (p.act == ACT_GELU_TANH) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
+          else if (p.act == ACT_GELU_ERF) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+          if (p.glu) {
+            const float rr = silu(v0) * v1;
+            const int64_t o = (int64_t)m * p.ldo + (n >> 1);
+            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rr);
+            else p.out_f32[o] = rr;
+            continue;
+          }
+          if (p.rowbias) {
+            const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.rowbias + (int64_t)(m % p.rowbias_mod) * p.N + n));
+            v0 += b.x; v1 += b.y;
+          }
+          if (p.resid) {
+            const float2 rs = *reinterpret_cast<const float2*>(p.resid + (int64_t)m * p.ldr + n);
+            v0 += rs.x; v1 += rs.y;
+          }
+          const int64_t o = (int64_t)m * p.ldo + n;
+          if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + o) = pack_bf16x2(v0, v1);
+          else *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(v0, v1);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TBN));
+  }
+}
+
+// ---- tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda)
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)f;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (row stride ld elements), box 64 cols x 128 rows, 128-byte swizzle, zero OOB fill
+bool make_map(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& a) {
+  if (a.a_rows_per_batch > 0) return false;                       // batched A addressing: mma.sync path
+  if ((a.K & 7) || (a.N & 1) || (a.lda & 7) || (a.ldw & 7)) return false;
+  if (((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
+  return encode_fn() != nullptr;
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
+  CUtensorMap mapA, mapB;
+  if (!make_map(&mapA, a.A, a.M, a.K, a.lda) || !make_map(&mapB, a.W, a.N, a.K, a.ldw)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return e;
+  dim3 grid((a.N + TBN - 1) / TBN, (a.M + TBM - 1) / TBM);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mapA, mapB, a);
+  if (counter) ++*counter;
+  return cudaGetLastError();
+}
+
+}  // namespace dtk

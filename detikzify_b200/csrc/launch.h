@@ -32,7 +32,12 @@ struct GemmArgs {
   bf16* out_bf16;
   int64_t ldo;
 };
-cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter);   // dispatches tcgen05 / mma.sync
+cudaError_t launch_gemm_mma(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
+bool gemm_tc_supported(const GemmArgs& a);
+void set_gemm_impl(int impl);   // 0 = mma.sync everywhere, 1 = tcgen05 where supported (process-wide dev switch)
+int get_gemm_impl();
 
 // ---------------------------------------------------------------- flash attention (mma.sync)
 struct AttnArgs {

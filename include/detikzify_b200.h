@@ -170,6 +170,9 @@ DTK_API int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int 
 /* phase timestamps of the last persistent-kernel launch (option "mega_debug" = 1):
  * [grid CTAs][5*layers+1 phases][4] globaltimer (ns) stamps; returns the value count */
 DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values);
+/* select the dense GEMM implementation used by dtk_dbg_gemm and the engines of this process:
+ * 0 = mma.sync, 1 = tcgen05/TMEM where supported, -1 = query only; returns the current setting */
+DTK_API int dtk_dbg_gemm_impl(int impl);
 /* C = act(A[M,K] * W[N,K]^T + bias) (+resid); glu: out[m, n/2] = silu(c[m,n]) * c[m,n+1] */
 DTK_API int dtk_dbg_gemm(const void* A_bf16, const void* W_bf16, const void* bias_bf16,
                          const float* resid, int M, int N, int K, int act, int glu,

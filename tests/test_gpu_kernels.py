@@ -45,8 +45,19 @@ GEMM_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["mma_sync", "tcgen05"])
 @pytest.mark.parametrize("M,N,K,bias,act,resid,glu,obf", GEMM_SHAPES)
-def test_gemm_matches_torch(M, N, K, bias, act, resid, glu, obf):
+def test_gemm_matches_torch(M, N, K, bias, act, resid, glu, obf, impl):
+    """Both dense-GEMM implementations (mma.sync bring-up kernel, tcgen05/TMA/TMEM kernel) against torch fp32."""
+    prev = _lib().dtk_dbg_gemm_impl(-1)
+    _lib().dtk_dbg_gemm_impl(impl)
+    try:
+        _gemm_case(M, N, K, bias, act, resid, glu, obf)
+    finally:
+        _lib().dtk_dbg_gemm_impl(prev)
+
+
+def _gemm_case(M, N, K, bias, act, resid, glu, obf):
     torch.manual_seed(M * 131 + N * 7 + K)
     dev = "cuda"
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
