@@ -107,6 +107,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the committed `ncu --set full` capture
+    (profiles/r*_ncu_full_<kernel>.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob(f"r*_ncu_full_{kernel}.json")):
+        try:
+            d = json.loads(f.read_text())
+            best = {"bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"], "ctx": d.get("ctx"), "source": f"profiles/{f.name}"}
+        except (OSError, ValueError, KeyError):
+            continue
+    return best
+
+
 # ---------------------------------------------------------------------------------- CPU reference arm
 def cpu_decode_tokens_per_s(model_name: str, n_tokens: int, steps: int = 1, warmup: int = 0):
     """Oracle on host cores: ViT + 243-token prefill + n_tokens greedy KV-cached decode steps (fp32 eager).
@@ -276,6 +289,10 @@ def run_ours(args):
         bytes_dec = sum(eng.decode_bytes(P + 1 + i) for i in range(n_new - 1))
         peak, peak_src = peaks()
         achieved = bytes_dec * args.steps / t_dec / 1e9
+        persistent = eng.get_option("decode_persistent") == 1
+        kernel_name = ("decode_mega_kernel (persistent cooperative weight-streaming decode kernel, 1 launch per token) + sample_kernel"
+                       if persistent else "decode step (CUDA graph: fused RMSNorm+GEMV / split-K attention / sampler kernels of one token)")
+        traffic = ncu_traffic("decode_mega_kernel") if persistent else None
         line = {
             "metric": "TikZ tokens/sec/GPU (decode, 384px cond, 2k ctx)", "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3,
@@ -284,8 +301,8 @@ def run_ours(args):
                                    f"{P}-token prefill + {n_new} decoded tokens to total length {total}",
                        "l2": "inputs larger than L2: 2.56 GB of weights streamed per token (126 MB L2)",
                        "parallelism": f"figure-sharded dp{world}, 1 NCCL weight broadcast at load, no per-step collective"},
-            "roofline": {"bound": "hbm", "kernel": "decode step (CUDA graph: fused RMSNorm+GEMV / split-K attention / sampler kernels of one token)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "bytes_per_token_avg": bytes_dec / (n_new - 1),
                          "decode_ms_per_token": t_dec / args.steps / (n_new - 1) * 1e3},
             "gpu_launches": int(launches),

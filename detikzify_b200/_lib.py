@@ -60,6 +60,7 @@ SYMBOLS = {
     "dtk_gen_wait": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int32)]),
     "dtk_gen_end": (C.c_int, [_P]),
     "dtk_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "dtk_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "dtk_decode_bytes": (C.c_uint64, [C.POINTER(DtkConfig), C.c_int]),
     "dtk_launch_count": (C.c_uint64, [_P]),
     "dtk_dbg_stream_bench": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -957,6 +957,17 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   return DTK_ERR_INVALID;
 }
 
+int dtk_get_option(dtk_engine* eng, const char* key, int64_t* value) {
+  if (!eng || !key || !value) return DTK_ERR_INVALID;
+  if (std::strcmp(key, "decode_impl") == 0) { *value = eng->decode_impl; return DTK_OK; }
+  if (std::strcmp(key, "decode_persistent") == 0) { *value = (eng->decode_impl == 1 && eng->mega_ok) ? 1 : 0; return DTK_OK; }
+  if (std::strcmp(key, "gemm_impl") == 0) { *value = get_gemm_impl(); return DTK_OK; }
+  if (std::strcmp(key, "mega_flags") == 0) { *value = eng->mega_flags; return DTK_OK; }
+  if (std::strcmp(key, "mega_debug") == 0) { *value = eng->mega_debug; return DTK_OK; }
+  eng->err = std::string("unknown option ") + key;
+  return DTK_ERR_INVALID;
+}
+
 // ---- kernel-level test hooks ---------------------------------------------------------------
 int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values) {
   if (!eng || !out_host) return DTK_ERR_INVALID;

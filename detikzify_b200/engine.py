@@ -202,6 +202,11 @@ class Engine:
     def set_option(self, key: str, value: int):
         self._check(self.lib.dtk_set_option(self._h, key.encode(), int(value)), "dtk_set_option")
 
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        self._check(self.lib.dtk_get_option(self._h, key.encode(), C.byref(v)), "dtk_get_option")
+        return int(v.value)
+
     def decode_bytes(self, context_len: int) -> int:
         return int(self.lib.dtk_decode_bytes(C.byref(self.ccfg), context_len))
 

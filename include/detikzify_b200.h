@@ -155,6 +155,9 @@ DTK_API int dtk_gen_end(dtk_engine* eng);
 /* ---- engine options. "decode_impl": 1 = persistent weight-streaming decode kernel (default for
  *      B = 1), 0 = per-op kernels replayed from a CUDA graph (always used for B > 1). ----------- */
 DTK_API int dtk_set_option(dtk_engine* eng, const char* key, int64_t value);
+/*      Read back an option; the extra key "decode_persistent" reports whether B = 1 decode steps
+ *      actually run on the persistent kernel (option set AND the device can co-schedule its grid). */
+DTK_API int dtk_get_option(dtk_engine* eng, const char* key, int64_t* value);
 
 /* ---- introspection for benches: algorithmic HBM bytes of one decode step at context T ----- */
 DTK_API uint64_t dtk_decode_bytes(const dtk_config* cfg, int context_len);
