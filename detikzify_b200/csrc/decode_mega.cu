@@ -364,9 +364,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a
   // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows
+  // ---- L2 prefetch. The shared-memory ring covers ~4 us of streaming; the dependent chain of a layer (5 grid
+  // barriers, activation re-staging, attention) stalls the consumers for longer than that, and with the ring full HBM
+  // would idle. So when the consumers enter weight phase q, one thread pulls the CTA's tiles of phase q + l2_ahead into
+  // L2 (126 MB: about one layer of weights) with bulk prefetches; HBM then keeps streaming through the stalls and the
+  // ring refills at L2 speed. A CTA's tiles of one phase are contiguous in the re-tiled layout.
+  Walk wpf;
+  int pf_q = 0;                       // next weight phase to prefetch (4 per layer: qkv, o, gu, down; then lm_head)
+  auto prefetch_upto = [&](int q_end) {
+    const int q_last = 4 * p.L;
+    for (; pf_q <= q_end && pf_q <= q_last; ++pf_q) {
+      const int layer = pf_q >> 2, which = pf_q & 3;
+      const MegaMat& m = (pf_q == q_last) ? p.lm : (which == 0 ? p.qkv : which == 1 ? p.o : which == 2 ? p.gu : p.down);
+      int g0, cnt, nact;
+      phase_span(wpf, m.groups, g0, cnt, nact);
+      wpf.rot = (wpf.rot + (uint32_t)nact) % (uint32_t)G;
+      if (tid != CONSUMER_THREADS - 32) continue;     // (bulk instructions are warp-uniform: one lane issues)
+      const bf16* base = m.base + (pf_q == q_last ? 0 : (int64_t)layer * m.layer_stride) + (int64_t)g0 * m.tpg * MEGA_TILE_ELEMS;
+      const int nt = cnt * m.tpg;
+      for (int t = 0; t < nt; t += 4) {               // 4 tiles = 32 KB per instruction
+        const uint32_t bytes = (uint32_t)min(4, nt - t) * TILE_BYTES;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(base + (int64_t)t * MEGA_TILE_ELEMS), "r"(bytes) : "memory");
+      }
+    }
+  };
+  int wphase = 0;
   auto run_phase = [&](const MegaMat& m, int ph, int layer) {
     int g0, cnt, nact;
     phase_span(w, m.groups, g0, cnt, nact);
+    if (p.l2_ahead > 0) prefetch_upto(wphase + p.l2_ahead);
+    ++wphase;
     const uint32_t nb0 = w.nb, gb0 = w.gb;
     const int tpg = m.tpg;
     for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {

@@ -151,6 +151,7 @@ struct dtk_engine {
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
+  int mega_l2_ahead = 2;                // L2 prefetch distance of the persistent kernel, in weight phases
 };
 
 namespace {
@@ -372,6 +373,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
+    m.l2_ahead = eng->mega_l2_ahead;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -792,7 +794,7 @@ int dtk_sample(dtk_engine* eng, const float* logits, int B, const dtk_sampling* 
   DTK_CK(cudaSetDevice(eng->device));
   SampleArgs a;
   fill_sample_args(eng, a, logits, B, *params);
-  if (probs_out) a.scratch = probs_out;
+  if (probs_out) { a.scratch = probs_out; a.want_probs = 1; }
   a.out_ids = out_ids;
   for (int i = 0; i < B; ++i) {
     a.seq[i].suppress = suppress ? suppress[i] : 0;
@@ -945,8 +947,18 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     set_gemm_impl((int)value);
     return DTK_OK;
   }
+  if (std::strcmp(key, "sample_impl") == 0) {  // process-wide: 0 = register-resident sampler when V fits, 1 = generic kernel
+    DTK_REQUIRE(value == 0 || value == 1, "sample_impl must be 0 or 1");
+    set_sample_impl((int)value);
+    return DTK_OK;
+  }
   if (std::strcmp(key, "mega_flags") == 0) {  // dev only (timing experiments; results are garbage when set)
     eng->mega_flags = (int)value;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "mega_l2_ahead") == 0) {
+    DTK_REQUIRE(value >= 0 && value <= 8, "mega_l2_ahead must be in 0..8");
+    eng->mega_l2_ahead = (int)value;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_debug") == 0) {
@@ -962,8 +974,10 @@ int dtk_get_option(dtk_engine* eng, const char* key, int64_t* value) {
   if (std::strcmp(key, "decode_impl") == 0) { *value = eng->decode_impl; return DTK_OK; }
   if (std::strcmp(key, "decode_persistent") == 0) { *value = (eng->decode_impl == 1 && eng->mega_ok) ? 1 : 0; return DTK_OK; }
   if (std::strcmp(key, "gemm_impl") == 0) { *value = get_gemm_impl(); return DTK_OK; }
+  if (std::strcmp(key, "sample_impl") == 0) { *value = get_sample_impl(); return DTK_OK; }
   if (std::strcmp(key, "mega_flags") == 0) { *value = eng->mega_flags; return DTK_OK; }
   if (std::strcmp(key, "mega_debug") == 0) { *value = eng->mega_debug; return DTK_OK; }
+  if (std::strcmp(key, "mega_l2_ahead") == 0) { *value = eng->mega_l2_ahead; return DTK_OK; }
   eng->err = std::string("unknown option ") + key;
   return DTK_ERR_INVALID;
 }

@@ -134,6 +134,7 @@ struct SampleArgs {
   int top_k, do_sample, bad_token, bs_token;
   uint64_t seed;
   float* scratch;             // [B, V] fp32 work buffer (receives the final probability vector)
+  int want_probs;             // greedy only: also write softmax(masked logits) to scratch (sampling always writes it)
   int64_t* out_ids;           // device int64[B] or null
   // generation-loop state (all optional, device): when gen_tok != null the sampler also advances
   // the loop: gen_tok[b] = token, gen_pos[b] += 1, and publishes the token to the pinned host ring.
@@ -148,6 +149,8 @@ struct SampleArgs {
   SampleSeq seq[64];
 };
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s, uint64_t* counter);
+void set_sample_impl(int impl);   // 0 = register-resident kernel when V <= 32768 (default), 1 = generic kernel
+int get_sample_impl();
 
 // ---------------------------------------------------------------- persistent decode kernel (B = 1)
 // Decode-side weight copy: every matrix is re-tiled once at load into 8 KB tiles of 16 rows x 256 k that a
@@ -179,6 +182,7 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
+  int l2_ahead;                                               // L2 prefetch distance in weight phases (0 = off)
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
 };

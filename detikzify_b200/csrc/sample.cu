@@ -99,7 +99,7 @@ DTK_DEV float philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1) {
   return (float)(x0 >> 8) * (1.0f / 16777216.0f);
 }
 
-__global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
+__global__ void __launch_bounds__(ST) sample_generic_kernel(const SampleArgs p) {
   __shared__ RedScratch red;
   __shared__ float sm_scan[32];
   __shared__ int sm_choice;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
     }
     __syncthreads();
     if (sm_choice >= 0) token = sm_choice;  // else: rounding left u beyond the total mass -> argmax
-  } else {
+  } else if (p.want_probs) {
     // greedy: probability vector = softmax of the masked logits (for parity inspection only)
     float z = 0.f;
     for (int i = tid; i < V; i += ST) {
@@ -255,11 +255,217 @@ __global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
   }
 }
 
+
+// ---- register-resident path (V <= ST * VPT): every thread keeps its VPT strided entries i = tid + j * ST in
+// registers, so the 31 + 31 threshold-search passes of top-k / top-p touch no memory at all; block reductions use one
+// __syncthreads per pass (double-buffered partials, every warp re-reduces the 32 warp partials with the same butterfly,
+// so all threads get the bit-identical sum). Per-thread accumulation order and reduction tree are the same as in
+// sample_generic_kernel: both kernels produce identical tokens and probability vectors.
+constexpr int VPT = 32;
+
+struct Red2 {
+  float f[2][32];
+  int i[2][32];
+};
+DTK_DEV float allreduce_sum(float v, Red2& r, int& ph) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) r.f[ph][threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = warp_sum(r.f[ph][threadIdx.x & 31]);
+  ph ^= 1;
+  return t;
+}
+DTK_DEV int allreduce_sum_int(int v, Red2& r, int& ph) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) r.i[ph][threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = r.i[ph][threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  ph ^= 1;
+  return t;
+}
+
+__global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
+  __shared__ RedScratch red;
+  __shared__ Red2 red2;
+  __shared__ float sm_scan[32];
+  __shared__ int sm_choice;
+  const int b = blockIdx.x, tid = threadIdx.x, V = p.V;
+  const float* lg = p.logits + (int64_t)b * V;
+  float* w = p.scratch + (int64_t)b * V;
+  const SampleSeq sq = p.seq[b];
+  const bool sampling = p.do_sample && p.temperature > 0.f;
+  const float T = sampling ? p.temperature : 1.f;
+  unsigned long long gstep = p.gen_step ? *p.gen_step : 0ull;
+  int ph = 0;
+
+  // 1. masks + temperature, running (max, argmax); entries beyond V are -inf (probability 0 everywhere below)
+  float v[VPT];
+  float mx = -INFINITY;
+  int amx = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int i = tid + j * ST;
+    float x = -INFINITY;
+    if (i < V) {
+      x = __ldcg(lg + i);
+      if (i == p.bad_token || (sq.suppress && i == p.bs_token)) x = -INFINITY;
+      x = x / T;
+      if (x > mx) { mx = x; amx = i; }
+    }
+    v[j] = x;
+  }
+  block_argmax(mx, amx, red);
+  int token = amx;
+
+  if (sampling) {
+    // 2. top-k: keep scores >= k-th largest
+    if (p.top_k > 0 && p.top_k < V) {
+      uint32_t thr = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = thr | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) cnt += (tid + j * ST < V) && (fkey(v[j]) >= cand);
+        cnt = allreduce_sum_int(cnt, red2, ph);
+        if (cnt >= p.top_k) thr = cand;
+      }
+#pragma unroll
+      for (int j = 0; j < VPT; ++j)
+        if (fkey(v[j]) < thr) v[j] = -INFINITY;
+    }
+    // 3. softmax
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const float e = (tid + j * ST < V) ? __expf(v[j] - mx) : 0.f;
+      v[j] = e;
+      if (tid + j * ST < V) z += e;
+    }
+    z = allreduce_sum(z, red2, ph);
+    const float invz = 1.f / z;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) v[j] *= invz;
+    // 4. top-p: remove tokens whose ascending cumulative mass is <= 1 - top_p
+    float theta = -1.f;
+    if (p.top_p < 1.f) {
+      const float limit = p.top_p_limit;
+      uint32_t tb = 0;
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = tb | (1u << bit);
+        const float cf = __uint_as_float(cand);
+        float sacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+          if (tid + j * ST < V) sacc += (v[j] <= cf) ? v[j] : 0.f;
+        sacc = allreduce_sum(sacc, red2, ph);
+        if (sacc <= limit) tb = cand;
+      }
+      theta = __uint_as_float(tb);
+      const float pmax = invz;
+      if (theta >= pmax) theta = nextafterf(pmax, 0.f);  // min_tokens_to_keep = 1
+    }
+    // 5. renormalise over the nucleus; the final probability vector goes to the scratch row
+    float z2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (v[j] <= theta) v[j] = 0.f;
+      if (tid + j * ST < V) z2 += v[j];
+    }
+    z2 = allreduce_sum(z2, red2, ph);
+    const float invz2 = 1.f / z2;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      if (tid + j * ST < V) w[tid + j * ST] = v[j] * invz2;
+    __syncthreads();
+    // 6. inverse-CDF draw in index order (blocked ranges, read back from the scratch row)
+    const uint32_t ctr = sq.step + (uint32_t)gstep;
+    const float u = philox_uniform(p.seed, ctr, sq.seq_id);
+    const int per = (V + ST - 1) / ST;
+    const int i0 = tid * per, i1 = min(V, i0 + per);
+    float loc = 0.f;
+    for (int i = i0; i < i1; ++i) loc += w[i];
+    float inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) sm_scan[tid >> 5] = inc;
+    if (tid == 0) sm_choice = -1;
+    __syncthreads();
+    if (tid < 32) {
+      float sv = sm_scan[tid], t2 = sv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, t2, o);
+        if (tid >= o) t2 += t;
+      }
+      sm_scan[tid] = t2 - sv;
+    }
+    __syncthreads();
+    const float excl = sm_scan[tid >> 5] + inc - loc;
+    if (loc > 0.f && u >= excl && u < excl + loc) {
+      float c = excl;
+      int pick = -1;
+      for (int i = i0; i < i1; ++i) {
+        float pv = w[i];
+        if (pv > 0.f) {
+          pick = i;
+          c += pv;
+          if (u < c) break;
+        }
+      }
+      if (pick >= 0) atomicMax(&sm_choice, pick);
+    }
+    __syncthreads();
+    if (sm_choice >= 0) token = sm_choice;
+  } else if (p.want_probs) {
+    // greedy: probability vector = softmax of the masked logits (parity inspection only; skipped in the decode loop)
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const float e = (tid + j * ST < V) ? __expf(v[j] - mx) : 0.f;
+      v[j] = e;
+      if (tid + j * ST < V) z += e;
+    }
+    z = allreduce_sum(z, red2, ph);
+    const float invz = 1.f / z;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      if (tid + j * ST < V) w[tid + j * ST] = v[j] * invz;
+  }
+
+  if (tid == 0) {
+    if (p.out_ids) p.out_ids[b] = token;
+    if (p.gen_tok) {
+      p.gen_tok[b] = token;
+      p.gen_pos[b] = min(p.gen_pos[b] + 1, p.max_pos);
+      p.host_ring[(gstep % (unsigned long long)p.ring) * p.B + b] = token;
+      __threadfence_system();
+      unsigned prev = atomicAdd(p.done_counter, 1u);
+      if (prev == (unsigned)p.B - 1u) {
+        *p.done_counter = 0u;
+        *p.gen_step = gstep + 1ull;
+        __threadfence_system();
+        *p.host_flag = (long long)(gstep + 1ull);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+static int g_sample_impl = 0;  // 0 = register-resident kernel when the vocabulary fits, 1 = always the generic kernel (tests)
+void set_sample_impl(int impl) { g_sample_impl = impl; }
+int get_sample_impl() { return g_sample_impl; }
 
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.B <= 0 || a.B > 64) return cudaErrorInvalidValue;
-  sample_kernel<<<a.B, ST, 0, s>>>(a);
+  if (g_sample_impl == 0 && a.V <= ST * VPT) sample_kernel<<<a.B, ST, 0, s>>>(a);
+  else sample_generic_kernel<<<a.B, ST, 0, s>>>(a);
   if (counter) ++*counter;
   return cudaGetLastError();
 }

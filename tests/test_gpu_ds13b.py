@@ -66,3 +66,43 @@ def test_ds13b_prefill_decode_and_2k_context():
         assert (lg0 - ref_long[0, 2047]).abs().max() < TOL
     finally:
         eng.seq_free(slot)
+
+
+@pytest.mark.parametrize("top_p,top_k,temp,do_sample", [(0.95, 0, 0.8, True), (0.9, 50, 0.7, True), (1.0, 0, 1.0, False)])
+def test_sampler_kernels_agree_at_full_vocab(top_p, top_k, temp, do_sample):
+    """V = 32256: the register-resident sampler and the generic (memory-resident) sampler return bit-identical tokens and
+    probability vectors, and the probability vector matches the HF logits-processor chain of the oracle."""
+    cfg, sd, oracle = model_bundle(NAME)
+    eng = engine_for(NAME, max_seqs=2, max_batch=1)
+    V = cfg.vocab_size
+    g = torch.Generator().manual_seed(11)
+    params = eng.sampling(temperature=temp, top_p=top_p, top_k=top_k, do_sample=do_sample,
+                          bad_token=cfg.image_token_id, begin_suppress_token=cfg.eos_token_id, seed=99)
+    for trial in range(3):
+        logits = torch.randn(1, V, generator=g) * 3.0
+        logits[0, cfg.image_token_id] = 20.0
+        res = []
+        for impl in (0, 1):
+            eng.set_option("sample_impl", impl)
+            try:
+                out, probs = eng.sample(logits.cuda(), params, suppress=[trial % 2], steps=[trial], want_probs=True)
+                torch.cuda.synchronize()
+                res.append((int(out[0]), probs[0].cpu()))
+            finally:
+                eng.set_option("sample_impl", 0)
+        assert res[0][0] == res[1][0]
+        assert torch.equal(res[0][1], res[1][1])
+        ids = torch.zeros(1, 10 if trial % 2 else 13, dtype=torch.long)
+        if do_sample:
+            ref = oracle.processed_probs(ids, logits, 10, temperature=temp, top_p=top_p, top_k=top_k)[0]
+            got = res[0][1]
+            mism = ((ref > 0) != (got > 0)).sum()
+            assert mism <= 1, mism
+            if mism == 0:
+                assert (got - ref).abs().max() < 1e-5
+        else:
+            masked = logits[0].clone()
+            masked[cfg.image_token_id] = -float("inf")
+            if trial % 2:
+                masked[cfg.eos_token_id] = -float("inf")
+            assert res[0][0] == int(masked.argmax())

@@ -26,6 +26,10 @@ timeit("default")
 for flags in (1, 2, 4, 0):
     eng.set_option("mega_flags", flags)
     timeit(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive)")
+for ahead in (0, 1, 2, 3, 4):
+    eng.set_option("mega_l2_ahead", ahead)
+    timeit(f"l2_ahead={ahead}")
+eng.set_option("mega_l2_ahead", int(sys.argv[3]) if len(sys.argv) > 3 else 2)
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
