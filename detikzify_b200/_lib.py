@@ -88,7 +88,9 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m detikzify_b200.build` "
                 "(or __graft_entry__.build()). There is no CPU fallback.")
-    lib = C.CDLL(str(LIB_PATH))
+    import os
+    # dev aid for same-box A/B runs of two builds; the product path always loads the in-tree library
+    lib = C.CDLL(os.environ.get("DTK_B200_LIB", str(LIB_PATH)))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   if (warp >= NCW) {
     // =============================================================== PRODUCERS
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       Walk w;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   }
 
   // ================================================================= CONSUMERS
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
   unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
   Walk w;
   // visit own tiles of a phase; body(j, k, ks, smem address of the slot) runs after the bytes landed and must
@@ -364,53 +366,39 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a
   // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows
-  // ---- L2 prefetch. The shared-memory ring covers ~4 us of streaming; the dependent chain of a layer (5 grid
-  // barriers, activation re-staging, attention) stalls the consumers for longer than that, and with the ring full HBM
-  // would idle. So when the consumers enter weight phase q, one thread pulls the CTA's tiles of phase q + l2_ahead into
-  // L2 (126 MB: about one layer of weights) with bulk prefetches; HBM then keeps streaming through the stalls and the
-  // ring refills at L2 speed. A CTA's tiles of one phase are contiguous in the re-tiled layout.
-  Walk wpf;
-  int pf_q = 0;                       // next weight phase to prefetch (4 per layer: qkv, o, gu, down; then lm_head)
-  auto prefetch_upto = [&](int q_end) {
-    const int q_last = 4 * p.L;
-    for (; pf_q <= q_end && pf_q <= q_last; ++pf_q) {
-      const int layer = pf_q >> 2, which = pf_q & 3;
-      const MegaMat& m = (pf_q == q_last) ? p.lm : (which == 0 ? p.qkv : which == 1 ? p.o : which == 2 ? p.gu : p.down);
-      int g0, cnt, nact;
-      phase_span(wpf, m.groups, g0, cnt, nact);
-      wpf.rot = (wpf.rot + (uint32_t)nact) % (uint32_t)G;
-      if (tid != CONSUMER_THREADS - 32) continue;     // (bulk instructions are warp-uniform: one lane issues)
-      const bf16* base = m.base + (pf_q == q_last ? 0 : (int64_t)layer * m.layer_stride) + (int64_t)g0 * m.tpg * MEGA_TILE_ELEMS;
-      const int nt = cnt * m.tpg;
-      for (int t = 0; t < nt; t += 4) {               // 4 tiles = 32 KB per instruction
-        const uint32_t bytes = (uint32_t)min(4, nt - t) * TILE_BYTES;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(base + (int64_t)t * MEGA_TILE_ELEMS), "r"(bytes) : "memory");
-      }
-    }
-  };
-  int wphase = 0;
   auto run_phase = [&](const MegaMat& m, int ph, int layer) {
     int g0, cnt, nact;
     phase_span(w, m.groups, g0, cnt, nact);
-    if (p.l2_ahead > 0) prefetch_upto(wphase + p.l2_ahead);
-    ++wphase;
     const uint32_t nb0 = w.nb, gb0 = w.gb;
     const int tpg = m.tpg;
     for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!(p.dbg_flags & 1)) {
+      {
         const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
-        const uint4* xp = xb + (size_t)ks * 64 + (lane & 3);
+        // B operand: even columns of the 16 x 8 B tile carry the hi part of x, odd columns the lo part (column = lane >> 2),
+        // so ONE mma per k-step yields W.hi in accumulator column 0 and W.lo in column 1 (legacy HMMA issues only once
+        // per ~16 cycles per SM sub-partition on sm_100: the tensor pipe, not memory, paces the post-barrier burst in
+        // which a full ring is drained from shared memory). Two independent chains (k-step parity) hide the HMMA latency.
+        const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
+        float c1[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t a[16][4];
+        uint2 b[16];
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
-          uint32_t a[4];
-          ldmatrix_x4(a[0], a[1], a[2], a[3], ta + s * 512);
-          const uint4 b = xp[s * 4];
-          mma_bf16_16816(acc, a, b.x, b.y);
-          mma_bf16_16816(acc, a, b.z, b.w);
+          ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+          b[s] = xp[s * 8];
         }
+        release();   // every lane's shared-memory reads of the slot are issued; the arrive is ordered after them
+#pragma unroll
+        for (int s = 0; s < 16; s += 2) {
+          mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
+          mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
+        }
+        // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
+        acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
+        acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
       }
-      release();
+
       const uint32_t gslot = (gb0 + (uint32_t)k) % NG;
       if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
         // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the

@@ -151,7 +151,6 @@ struct dtk_engine {
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
   int mega_debug = 0;
   int mega_flags = 0;
-  int mega_l2_ahead = 2;                // L2 prefetch distance of the persistent kernel, in weight phases
 };
 
 namespace {
@@ -373,7 +372,6 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
-    m.l2_ahead = eng->mega_l2_ahead;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -956,11 +954,6 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->mega_flags = (int)value;
     return DTK_OK;
   }
-  if (std::strcmp(key, "mega_l2_ahead") == 0) {
-    DTK_REQUIRE(value >= 0 && value <= 8, "mega_l2_ahead must be in 0..8");
-    eng->mega_l2_ahead = (int)value;
-    return DTK_OK;
-  }
   if (std::strcmp(key, "mega_debug") == 0) {
     eng->mega_debug = value ? 1 : 0;
     return DTK_OK;
@@ -977,7 +970,6 @@ int dtk_get_option(dtk_engine* eng, const char* key, int64_t* value) {
   if (std::strcmp(key, "sample_impl") == 0) { *value = get_sample_impl(); return DTK_OK; }
   if (std::strcmp(key, "mega_flags") == 0) { *value = eng->mega_flags; return DTK_OK; }
   if (std::strcmp(key, "mega_debug") == 0) { *value = eng->mega_debug; return DTK_OK; }
-  if (std::strcmp(key, "mega_l2_ahead") == 0) { *value = eng->mega_l2_ahead; return DTK_OK; }
   eng->err = std::string("unknown option ") + key;
   return DTK_ERR_INVALID;
 }

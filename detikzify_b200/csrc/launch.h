@@ -182,7 +182,6 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
-  int l2_ahead;                                               // L2 prefetch distance in weight phases (0 = off)
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
 };

@@ -22,14 +22,13 @@ def timeit(label):
         eng.decode([slot], [ctx], tok)
     ev1.record(); torch.cuda.synchronize()
     print(f"{label}: ms/token {ev0.elapsed_time(ev1) / 10:.4f}")
+import subprocess
+print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 timeit("default")
 for flags in (1, 2, 4, 0):
     eng.set_option("mega_flags", flags)
     timeit(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive)")
-for ahead in (0, 1, 2, 3, 4):
-    eng.set_option("mega_l2_ahead", ahead)
-    timeit(f"l2_ahead={ahead}")
-eng.set_option("mega_l2_ahead", int(sys.argv[3]) if len(sys.argv) > 3 else 2)
+print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
 L = cfg.num_hidden_layers
