@@ -488,10 +488,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         asm volatile("prefetch.global.L2 [%0];\n" ::"l"(kb + p.kv_v_offset + (int64_t)i * 64));
       }
     }
-    for (int i = tid * 64; i < p.H; i += CONSUMER_THREADS * 64) {
+    for (int i = tid * 64; i < p.H; i += CONSUMER_THREADS * 64)
       asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.norm2_0 + no + i));
-      asm volatile("prefetch.global.L2 [%0];\n" ::"l"((l + 1 < p.L ? p.norm1_0 + no + p.norm_stride : p.final_norm) + i));
-    }
     // ---------------- P1: RMSNorm + qkv + RoPE + KV write
     stamp(0);
     stage_xb(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
@@ -654,6 +652,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     stamp(0);
     stage_xb(p.h, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
     stamp(1);
+    for (int i = tid * 64; i < p.H; i += CONSUMER_THREADS * 64)   // next stage's norm weights -> L2 (the stream evicted them since)
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"((l + 1 < p.L ? p.norm1_0 + no + p.norm_stride : p.final_norm) + i));
     run_phase(p.down, PH_DOWN, l);
     stamp(2);
     bar_target += G;

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_tn_kernel(const GemmArgs p)
 
 }  // namespace
 
-static int g_gemm_impl = 0;  // flipped to 1 by the engine once validated on the device (see dtk_set_option "gemm_impl")
+static int g_gemm_impl = 1;  // 1 = tcgen05/TMA/TMEM kernel for M >= 64 (default), 0 = mma.sync kernel everywhere (dtk_set_option "gemm_impl")
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 int get_gemm_impl() { return g_gemm_impl; }
 
