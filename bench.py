@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-tokens", type=int, default=32, help="decode tokens of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-vit-sweep", action="store_true")
     return ap.parse_args()
 
 
@@ -276,6 +277,25 @@ def run_ours(args):
             e2e_t = time.perf_counter() - t0
             barrier()
 
+        # ---- secondary metric of BASELINE.json ("ViT encode ms/img", configs[2]: batch sweep @384px), rank 0 only
+        vit = None
+        if rank == 0 and not args.no_vit_sweep:
+            vit = {}
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for B in (1, 8, 64):
+                pix_b = synthetic_pixels(B, cfg.vision_config.image_size, seed=7).to(dev)
+                for _ in range(2):
+                    eng.vit_encode(pix_b)
+                reps = 5 if B < 64 else 3
+                v0.record(stream)
+                for _ in range(reps):
+                    eng.vit_encode(pix_b)
+                v1.record(stream)
+                stream.synchronize()
+                vit[str(B)] = v0.elapsed_time(v1) / reps / B
+                del pix_b
+        barrier()
+
     # max over ranks
     vals = torch.tensor([t_all, t_dec, e2e_t or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -308,6 +328,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if vit:
+            line["vit_encode_ms_per_img"] = {"batch": vit, "note": "SigLIP-so400m/14@384 tokens + pooled output, pixels resident, CUDA events"}
         if e2e_t:
             line["e2e"] = {"value": world * args.steps * new_per_step / e2e_t, "unit": "tokens/s",
                            "h2d_bytes_per_step": int(pix_host.numel() * 4 + P * 8), "d2h_bytes_per_step": int(new_per_step * 4)}

@@ -127,10 +127,8 @@ struct dtk_engine {
   // generation loop
   int gen_B = 0;
   dtk_sampling gen_params{};
-  int* host_ring = nullptr;          // pinned, mapped
-  long long* host_flag = nullptr;    // pinned, mapped
-  int* dev_ring = nullptr;
-  long long* dev_flag = nullptr;
+  unsigned long long* host_ring = nullptr;   // pinned, mapped: [ring][64] entries ((step + 1) << 32) | token
+  unsigned long long* dev_ring = nullptr;
   int ring = 256;
   std::map<std::string, cudaGraphExec_t> graphs;
   cudaGraphExec_t gen_graph = nullptr;
@@ -592,11 +590,9 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       eng->mega_ok = true;
     }
   }
-  DTK_CK(cudaHostAlloc((void**)&eng->host_ring, (size_t)eng->ring * 64 * sizeof(int), cudaHostAllocMapped));
-  DTK_CK(cudaHostAlloc((void**)&eng->host_flag, sizeof(long long), cudaHostAllocMapped));
-  *eng->host_flag = 0;
+  DTK_CK(cudaHostAlloc((void**)&eng->host_ring, (size_t)eng->ring * 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+  std::memset(eng->host_ring, 0, (size_t)eng->ring * 64 * sizeof(unsigned long long));
   DTK_CK(cudaHostGetDevicePointer((void**)&eng->dev_ring, eng->host_ring, 0));
-  DTK_CK(cudaHostGetDevicePointer((void**)&eng->dev_flag, eng->host_flag, 0));
   DTK_CK(cudaDeviceSynchronize());
   return DTK_OK;
 }
@@ -613,7 +609,6 @@ int dtk_destroy(dtk_engine* eng) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
   if (eng->host_ring) cudaFreeHost(eng->host_ring);
-  if (eng->host_flag) cudaFreeHost(eng->host_flag);
   cudaGetLastError();
   delete eng;
   return DTK_OK;
@@ -823,7 +818,7 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
   eng->launches += 2;
   DTK_CK(cudaGetLastError());
   DTK_CK(cudaStreamSynchronize(s));
-  *eng->host_flag = 0;
+  std::memset(eng->host_ring, 0, (size_t)eng->ring * 64 * sizeof(unsigned long long));  // stamps restart at step 1
 
   eng->gen_B = B;
   eng->gen_params = *params;
@@ -833,7 +828,7 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     fill_sample_args(eng, a, eng->d_logits, B, *params);
     for (int i = 0; i < B; ++i) { a.seq[i].suppress = 0; a.seq[i].step = 1; a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i; }
     a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
-    a.host_ring = eng->dev_ring; a.host_flag = eng->dev_flag; a.ring = eng->ring;
+    a.host_ring = eng->dev_ring; a.ring = eng->ring;
     a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
   }
   eng->gen_mega = (B == 1 && eng->decode_impl == 1 && eng->mega_ok);
@@ -895,28 +890,36 @@ int dtk_gen_step(dtk_engine* eng, void* stream) {
 int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host) {
   if (!eng) return DTK_ERR_INVALID;
   DTK_REQUIRE(eng->gen_B > 0 && step >= 0 && tokens_out_host, "gen state/step/out");
-  volatile long long* flag = eng->host_flag;
+  // every sequence's entry of this step carries the stamp step + 1 in its upper half (one 8-byte device store)
+  volatile const unsigned long long* row = eng->host_ring + (size_t)(step % eng->ring) * eng->gen_B;
+  const unsigned long long want = (unsigned long long)(step + 1);
   auto t0 = std::chrono::steady_clock::now();
   uint64_t spins = 0;
-  while (*flag < step + 1) {
-    if ((++spins & 0x3ff) == 0) {
-      cudaError_t q = cudaStreamQuery(eng->gen_stream);
-      if (q != cudaSuccess && q != cudaErrorNotReady) {
-        eng->err = std::string("stream error while waiting for token: ") + cudaGetErrorString(q);
-        return DTK_ERR_CUDA;
-      }
-      if (q == cudaSuccess && *flag < step + 1) {
-        eng->err = "stream idle but requested step was never launched";
+  for (int i = 0; i < eng->gen_B; ++i) {
+    unsigned long long e;
+    while (((e = row[i]) >> 32) != want) {
+      if ((e >> 32) > want) {   // the device is a whole ring ahead: the token was overwritten
+        eng->err = "token ring overrun: dtk_gen_wait lagged more than the ring depth behind dtk_gen_step";
         return DTK_ERR_INVALID;
       }
-      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
-        eng->err = "timeout waiting for generated token";
-        return DTK_ERR_CUDA;
+      if ((++spins & 0x3ff) == 0) {
+        cudaError_t q = cudaStreamQuery(eng->gen_stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+          eng->err = std::string("stream error while waiting for token: ") + cudaGetErrorString(q);
+          return DTK_ERR_CUDA;
+        }
+        if (q == cudaSuccess && (row[i] >> 32) != want) {
+          eng->err = "stream idle but requested step was never launched";
+          return DTK_ERR_INVALID;
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+          eng->err = "timeout waiting for generated token";
+          return DTK_ERR_CUDA;
+        }
       }
     }
+    tokens_out_host[i] = (int32_t)(uint32_t)(e & 0xffffffffull);
   }
-  const int* row = eng->host_ring + (size_t)(step % eng->ring) * eng->gen_B;
-  for (int i = 0; i < eng->gen_B; ++i) tokens_out_host[i] = ((volatile const int*)row)[i];
   return DTK_OK;
 }
 

@@ -141,8 +141,7 @@ struct SampleArgs {
   int* gen_tok;
   int* gen_pos;
   unsigned long long* gen_step;   // single counter (device); RNG counter + ring row
-  int* host_ring;                 // mapped pinned int32 [ring, B]
-  volatile long long* host_flag;  // mapped pinned: last published step + 1
+  unsigned long long* host_ring;  // mapped pinned u64 [ring, B]: ((step + 1) << 32) | token, one store per token
   int ring;
   int max_pos;                    // gen_pos is clamped to this (max_len - 1)
   unsigned int* done_counter;     // device, zero-initialised, self-resetting

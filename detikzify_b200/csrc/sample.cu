@@ -242,14 +242,14 @@ __global__ void __launch_bounds__(ST) sample_generic_kernel(const SampleArgs p) 
     if (p.gen_tok) {
       p.gen_tok[b] = token;
       p.gen_pos[b] = min(p.gen_pos[b] + 1, p.max_pos);
-      p.host_ring[(gstep % (unsigned long long)p.ring) * p.B + b] = token;
-      __threadfence_system();
+      // ONE 8-byte store to the mapped pinned ring carries the token and its step stamp, so no ordering between two
+      // host-visible stores (and no system-scope fence, a PCIe round trip) is needed; the host polls the entry itself
+      const unsigned long long entry = ((gstep + 1ull) << 32) | (unsigned long long)(unsigned)token;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p.host_ring + (gstep % (unsigned long long)p.ring) * p.B + b), "l"(entry) : "memory");
       unsigned prev = atomicAdd(p.done_counter, 1u);
-      if (prev == (unsigned)p.B - 1u) {
+      if (prev == (unsigned)p.B - 1u) {   // last sequence of this step: advance the device-side step counter
         *p.done_counter = 0u;
         *p.gen_step = gstep + 1ull;
-        __threadfence_system();
-        *p.host_flag = (long long)(gstep + 1ull);
       }
     }
   }
@@ -443,14 +443,14 @@ __global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
     if (p.gen_tok) {
       p.gen_tok[b] = token;
       p.gen_pos[b] = min(p.gen_pos[b] + 1, p.max_pos);
-      p.host_ring[(gstep % (unsigned long long)p.ring) * p.B + b] = token;
-      __threadfence_system();
+      // ONE 8-byte store to the mapped pinned ring carries the token and its step stamp, so no ordering between two
+      // host-visible stores (and no system-scope fence, a PCIe round trip) is needed; the host polls the entry itself
+      const unsigned long long entry = ((gstep + 1ull) << 32) | (unsigned long long)(unsigned)token;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p.host_ring + (gstep % (unsigned long long)p.ring) * p.B + b), "l"(entry) : "memory");
       unsigned prev = atomicAdd(p.done_counter, 1u);
-      if (prev == (unsigned)p.B - 1u) {
+      if (prev == (unsigned)p.B - 1u) {   // last sequence of this step: advance the device-side step counter
         *p.done_counter = 0u;
         *p.gen_step = gstep + 1ull;
-        __threadfence_system();
-        *p.host_flag = (long long)(gstep + 1ull);
       }
     }
   }
