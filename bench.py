@@ -128,6 +128,13 @@ def cpu_decode_tokens_per_s(model_name: str, n_tokens: int, steps: int = 1, warm
     from detikzify_b200.model.configuration import preset
     from detikzify_b200.model.weights import random_init
     from oracle.hf_oracle import Oracle, synthetic_pixels
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        phys = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), int(os.environ.get("DTK_CPU_THREADS", phys))))
     cfg = preset(model_name)
     sd = random_init(cfg, seed=0)
     oracle = Oracle(cfg.to_dict(), sd)

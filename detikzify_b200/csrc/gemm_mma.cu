@@ -162,7 +162,8 @@ int get_gemm_impl() { return g_gemm_impl; }
 
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   // large-M dense contractions go to the tcgen05/TMEM kernel; tiny M (pool head, M = B) stays on mma.sync
-  if (g_gemm_impl == 1 && a.M >= 64 && gemm_tc_supported(a)) return launch_gemm_tc(a, s, counter);
+  // (M < 4: pool-head probes and other tiny products stay on mma.sync; 4 <= M < 64 takes the skinny tcgen05 tile)
+  if (g_gemm_impl == 1 && a.M >= 4 && gemm_tc_supported(a)) return launch_gemm_tc(a, s, counter);
   return launch_gemm_mma(a, s, counter);
 }
 

@@ -24,12 +24,19 @@
 namespace dtk {
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
+constexpr int TBM = 128, TBK = 64;
 constexpr int TC_THREADS = 192;
-constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = TBN * TBK * 2;       // 16 KB each
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TC_SMEM = TSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int A_BYTES = TBM * TBK * 2;                                // 16 KB
 constexpr long long TC_SPIN = 2000000000ll;
+// Two tile shapes: 128 x 128 (3 stages, two CTAs per SM) for M >= 64, and the SKINNY 128 x 32 (8 stages, one CTA per SM)
+// for the batched-decode GEMMs (M = number of rollouts <= 64): there the matrices are streamed once from HBM and what
+// matters is many CTAs (N / 32) with deep TMA pipelines, not tensor throughput.
+template <int TBN, int TSTAGES>
+struct TcCfg {
+  static constexpr int B_BYTES = TBN * TBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = TSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 DTK_DEV void tc_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
 DTK_DEV void tc_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -70,8 +77,10 @@ struct TcArgs {
   GemmArgs g;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+template <int TBN, int TSTAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                       const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+  constexpr int STAGE_BYTES = TcCfg<TBN, TSTAGES>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sraw = smem_u32(smem_raw);
   const uint32_t sbase = (sraw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024-byte alignment
@@ -203,13 +212,13 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (row stride ld elements), box 64 cols x 128 rows, 128-byte swizzle, zero OOB fill
-bool make_map(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t cols, int64_t ld) {
+// 2-D bf16 row-major [rows, cols] (row stride ld elements), box 64 cols x box_rows rows, 128-byte swizzle, zero OOB fill
+bool make_map(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -224,16 +233,27 @@ bool gemm_tc_supported(const GemmArgs& a) {
   return encode_fn() != nullptr;
 }
 
-cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
-  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
+template <int TBN, int TSTAGES, int MIN_CTAS>
+static cudaError_t launch_tc_variant(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   CUtensorMap mapA, mapB;
-  if (!make_map(&mapA, a.A, a.M, a.K, a.lda) || !make_map(&mapB, a.W, a.N, a.K, a.ldw)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-  if (e != cudaSuccess) return e;
+  if (!make_map(&mapA, a.A, a.M, a.K, a.lda, TBM) || !make_map(&mapB, a.W, a.N, a.K, a.ldw, TBN)) return cudaErrorInvalidValue;
+  constexpr int smem = TcCfg<TBN, TSTAGES>::SMEM;
+  static bool attr_done = false;   // (not re-issued per launch: launches may be captured into a CUDA graph)
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TBN, TSTAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
   dim3 grid((a.N + TBN - 1) / TBN, (a.M + TBM - 1) / TBM);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mapA, mapB, a);
+  gemm_tc_kernel<TBN, TSTAGES, MIN_CTAS><<<grid, TC_THREADS, smem, s>>>(mapA, mapB, a);
   if (counter) ++*counter;
   return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
+  if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
+  return launch_tc_variant<128, 3, 2>(a, s, counter);
 }
 
 }  // namespace dtk

@@ -72,6 +72,9 @@ cudaError_t launch_embed_splice(const int64_t* ids, int T, int start_pos, const 
                                 int image_token, const float* img, int img_start, int n_img, float* x,
                                 cudaStream_t s, uint64_t* counter);
 // prefill: qkv fp32 [T, qd+2kd] -> roped q bf16 [T, qd]; K/V bf16 into the cache at positions start_pos+t
+cudaError_t launch_rope_kv_decode(const float* qkv, int B, const int* slots, const int* pos, int heads, int kv_heads,
+                                  const float* rope_cs, float* q_out, bf16* kv_base, int64_t kv_slot_stride,
+                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter);
 cudaError_t launch_rope_kv_prefill(const float* qkv, int T, int start_pos, int heads, int kv_heads,
                                    const float* rope_cs, bf16* q_out, bf16* kcache, bf16* vcache,
                                    int max_len, cudaStream_t s, uint64_t* counter);

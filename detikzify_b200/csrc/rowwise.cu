@@ -148,6 +148,34 @@ __global__ void __launch_bounds__(64) rope_kv_prefill_kernel(const float* __rest
   }
 }
 
+// ---- batched-decode RoPE + KV-cache append: row b belongs to sequence slots[b] at position pos[b]
+//      (HF modeling_llama.py:124-168; DynamicCache.update). grid (B, heads + 2*kv_heads); 64 threads.
+__global__ void __launch_bounds__(64) rope_kv_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ slots,
+                                                            const int* __restrict__ posv, int heads, int kv_heads,
+                                                            const float* __restrict__ rope_cs, float* __restrict__ q_out,
+                                                            bf16* __restrict__ kv_base, int64_t kv_slot_stride,
+                                                            int64_t kv_v_offset, int max_len) {
+  const int b = blockIdx.x, hh = blockIdx.y, i = threadIdx.x;
+  const int qd = heads * 128, kd = kv_heads * 128;
+  const int pos = posv[b];
+  const float* src = qkv + (int64_t)b * (qd + 2 * kd) + hh * 128;
+  const float a = src[i], c = src[i + 64];
+  const float2 cs = *reinterpret_cast<const float2*>(rope_cs + ((int64_t)pos * 64 + i) * 2);
+  if (hh < heads) {
+    float* d = q_out + (int64_t)b * qd + hh * 128;
+    d[i] = a * cs.x - c * cs.y;
+    d[i + 64] = c * cs.x + a * cs.y;
+  } else if (hh < heads + kv_heads) {
+    bf16* d = kv_base + (int64_t)slots[b] * kv_slot_stride + ((int64_t)(hh - heads) * max_len + pos) * 128;
+    d[i] = __float2bfloat16_rn(a * cs.x - c * cs.y);
+    d[i + 64] = __float2bfloat16_rn(c * cs.x + a * cs.y);
+  } else {
+    bf16* d = kv_base + (int64_t)slots[b] * kv_slot_stride + kv_v_offset + ((int64_t)(hh - heads - kv_heads) * max_len + pos) * 128;
+    d[i] = __float2bfloat16_rn(a);
+    d[i + 64] = __float2bfloat16_rn(c);
+  }
+}
+
 // ---- SigLIP attention-pool head, single probe query over N tokens (HF modeling_siglip.py:628-654,
 //      nn.MultiheadAttention with a learned probe). grid (heads, B), 128 threads; head_dim 72.
 __global__ void __launch_bounds__(128) pool_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kv,
@@ -237,6 +265,15 @@ cudaError_t launch_rope_kv_prefill(const float* qkv, int T, int start_pos, int h
   dim3 grid(T, heads + 2 * kv_heads);
   rope_kv_prefill_kernel<<<grid, 64, 0, s>>>(qkv, T, start_pos, heads, kv_heads, rope_cs, q_out, kcache, vcache,
                                              max_len);
+  if (counter) ++*counter;
+  return cudaGetLastError();
+}
+cudaError_t launch_rope_kv_decode(const float* qkv, int B, const int* slots, const int* pos, int heads, int kv_heads,
+                                  const float* rope_cs, float* q_out, bf16* kv_base, int64_t kv_slot_stride,
+                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter) {
+  dim3 grid(B, heads + 2 * kv_heads);
+  rope_kv_decode_kernel<<<grid, 64, 0, s>>>(qkv, slots, pos, heads, kv_heads, rope_cs, q_out, kv_base, kv_slot_stride,
+                                            kv_v_offset, max_len);
   if (counter) ++*counter;
   return cudaGetLastError();
 }

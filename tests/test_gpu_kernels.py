@@ -42,6 +42,13 @@ GEMM_SHAPES = [
     (1, 1152, 1152, True, 0, False, False, False),      # M = 1 (pool head probe)
     (130, 264, 72, False, 0, False, False, False),      # ragged everything
     (300, 32256, 256, False, 0, False, False, False),   # wide N (lm_head all-logits path)
+    # batched decode (M = number of rollouts): the skinny 128 x 32 tcgen05 tile
+    (32, 6144, 2048, False, 0, False, False, False),    # qkv, 32 rollouts
+    (32, 2048, 5504, False, 0, True, False, False),     # down + residual, ragged K tile
+    (17, 11008, 2048, False, 0, False, True, True),     # gate/up GLU, odd M
+    (8, 32256, 2048, False, 0, False, False, False),    # lm_head, 8 rollouts
+    (6, 264, 72, False, 0, False, False, False),        # tiny-model shapes
+    (63, 1000, 264, True, 0, False, False, False),
 ]
 
 

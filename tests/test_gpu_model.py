@@ -179,6 +179,47 @@ def test_batched_decode_equals_single():
         assert torch.equal(batched[i], singles[i][0])
 
 
+def test_batched_gemm_decode_matches_single_and_oracle():
+    """B = 6 >= decode_gemm_min_batch: the batched step runs the dense matrices as tensor-core GEMMs (bf16-rounded
+    activations, like prefill). Logits must match the per-sequence decode and the fp32 oracle within the parity tolerance,
+    and the KV rows it appends must be the ones a later single-sequence step reads."""
+    cfg, sd, oracle = model_bundle("tiny")
+    eng = engine_for("tiny", max_seqs=8, max_batch=8)
+    assert eng.get_option("decode_gemm_min_batch") == 4
+    pix = _pixels(cfg, 1)
+    img = eng.image_embeds(pix.cuda())[0]
+    B = 6
+    slots = [eng.seq_alloc() for _ in range(B)]
+    twins = []
+    try:
+        lens, prompts = [], []
+        for i, s in enumerate(slots):
+            ids = _prompt(cfg, n_text=3 + 4 * i, seed=3000 + i)
+            eng.prefill(s, ids.cuda(), 0, img, 0)
+            lens.append(ids.numel()); prompts.append(ids)
+        toks = torch.arange(21, 21 + B, device="cuda")
+        eng.set_option("decode_gemm_min_batch", 0)
+        ref_rows = eng.decode(slots, lens, toks).clone()           # per-sequence GEMV kernels (fp32 activations)
+        eng.set_option("decode_gemm_min_batch", 4)
+        got = eng.decode(slots, lens, toks).clone()
+        torch.cuda.synchronize()
+        assert (got - ref_rows).abs().max().item() < 3e-2
+        for i in (0, B - 1):
+            full = torch.cat([prompts[i], toks[i:i + 1].cpu()])[None]
+            ref, _ = oracle.forward_logits(full, pix)
+            assert (got[i].cpu() - ref[0, -1]).abs().max().item() < 3e-2
+        # the appended KV rows serve the next step of every sequence
+        nxt = torch.arange(40, 40 + B, device="cuda")
+        step2 = eng.decode(slots, [n + 1 for n in lens], nxt).clone()
+        eng.set_option("decode_gemm_min_batch", 0)
+        step2_ref = eng.decode(slots, [n + 1 for n in lens], nxt).clone()
+        assert (step2 - step2_ref).abs().max().item() < 3e-2
+    finally:
+        eng.set_option("decode_gemm_min_batch", 4)
+        for s in slots:
+            eng.seq_free(s)
+
+
 # ---------------------------------------------------------------- sampler
 def _oracle_probs(oracle, ids, logits, prompt_len, **kw):
     return oracle.processed_probs(ids, logits, prompt_len, **kw)
