@@ -6,26 +6,30 @@
 // (measured 0.37 of the HBM roofline). Here the weight stream is decoupled from the dependency chain:
 //
 //   * grid = one CTA per SM, resident for the whole token (cooperative launch);
-//   * 4 PRODUCER warps per CTA walk the CTA's statically known list of weight tiles for ALL layers and
-//     phases and stream them with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a
-//     ~190 KB shared-memory ring of 8 KB slots, never waiting for activations — weights do not depend on
-//     them — so HBM stays busy across phase boundaries (measured: the ring sustains 7.2 TB/s);
-//   * 8 CONSUMER warps take tiles in order. A tile is 16 output rows x 256 k, pre-arranged in HBM
-//     (launch_retile, once at load) so that it lands in shared memory exactly in ldmatrix.x4 order; the
-//     dot products run on the tensor pipe (mma.sync m16n8k16, fp32 accumulate) with the activation vector
-//     split into bf16 hi + lo parts (x = hi + lo to 2^-17), i.e. fp32-grade GEMV at ~1/6 of the issue slots
-//     of a CUDA-core unpack+FMA loop (which measured consumer-bound);
+//   * 4 PRODUCER warps per CTA (one issuing lane each, registers handed back with setmaxnreg.dec) walk the
+//     CTA's statically known list of weight tiles for ALL layers and phases and stream them with 1-D TMA bulk
+//     copies (cp.async.bulk + mbarrier complete_tx) into a ~190 KB shared-memory ring of 8 KB slots, never
+//     waiting for activations — weights do not depend on them — so HBM stays busy across phase boundaries
+//     (measured: the ring sustains 7.2 TB/s);
+//   * 8 CONSUMER warps (setmaxnreg.inc 232: no spills, a whole tile in flight) take tiles in order. A tile is
+//     16 output rows x 256 k, pre-arranged in HBM (launch_retile, once at load) so that it lands in shared
+//     memory exactly in ldmatrix.x4 order; the dot products run on the tensor pipe (mma.sync m16n8k16, fp32
+//     accumulate) with the activation vector split into bf16 hi + lo parts (x = hi + lo to 2^-17) that occupy
+//     alternating columns of the B operand: one HMMA per k-step, fp32-grade GEMV; the ring slot is handed back
+//     as soon as its shared-memory reads are issued;
 //   * rows are grouped so that one thread's two accumulator rows (g, g+8) are a RoPE pair (i, i+64) or a
 //     SwiGLU pair (gate_i, up_i): RMSNorm prologue, RoPE + KV-cache write, SiLU*mul and residual add are
 //     all fused; partial sums of a group's k-tiles are combined in a fixed order (deterministic);
-//   * phases are separated by a hand-rolled grid barrier (release-reduction + acquire poll); the ring
-//     depth (~4 us of streaming per SM) covers the barrier + activation re-staging bubble;
-//   * 16-row groups are dealt round-robin over CTAs with a running offset across phases, so the cumulative
-//     bytes per CTA never differ by more than one group.
+//   * phases are separated by a hand-rolled grid barrier (release-reduction + acquire poll) among the
+//     consumer threads; the ring depth (~4 us of streaming per SM) covers part of the barrier + activation
+//     re-staging bubble;
+//   * a phase's 16-row groups are cut into equal blocks over as many CTAs as needed (the participating set
+//     rotates from phase to phase), so participants finish together and idle CTAs' producers run ahead.
 //
-// Per layer: P1 qkv(+RMSNorm, RoPE, KV write) | P2 split-KV attention (old keys streamed through the
-// same ring; the new key read after the barrier; last CTA of a head merges) | P3 o-proj + residual |
-// P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final RMSNorm).
+// Per layer: P1 qkv(+RMSNorm, RoPE, KV write) | P2 split-KV attention (the CTA's KV rows are L2-prefetched at
+// the start of the layer and read with plain loads; the last CTA of a head to arrive merges the partials) |
+// P3 o-proj + residual | P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final
+// RMSNorm). DESIGN.md section 4 lists the measured alternatives that were rejected.
 //
 // Replaces the per-token HF eager path (modeling_llama.py:303-333, ~900 launches per token).
 #include "common.cuh"
