@@ -4,13 +4,17 @@ TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry__.sm
 
 CPU oracle for the DeTikZify v1 image-conditioned decode path.
 
-PARITY STATUS: **unpinned by the reference** — the reference ships no tests, golden vectors or
-fixtures and its package does not import here (transformers 5.5.0 vs the
-pinned ~=4.52.4; timm/pymupdf/pdf2image absent). The arithmetic of the path lives in third-party
-modules (``transformers`` Llama + SigLIP/timm ViT, pinned transformers~=4.52.4 / timm~=1.0.11 in
-the reference's pyproject.toml:10-12,46-48). This oracle therefore (i) uses the *installed*
-``transformers`` 5.5.0 ``LlamaForCausalLM`` / ``SiglipVisionModel`` as the published algorithm
-and (ii) restates, line by line, the reference's own glue around them:
+PARITY STATUS: **pinned by the reference's own model code for everything except the ViT internals.** The reference ships
+no tests or golden vectors and its package ``__init__`` does not import here (transformers 5.5.0 vs
+the pinned ~=4.52.4; timm/pymupdf/pdf2image/datasets absent), but its v1 model module does run when loaded directly:
+``tests/golden/make_reference_golden.py`` executes ``detikzify/model/v1/modeling_detikzify.py`` from /root/reference
+(``DetikzifyForCausalLM.forward`` / ``prepare_inputs_for_generation`` / ``generate`` with the kwargs of
+infer/generate.py:218-227) on the tiny fixture weights and commits the outputs as ``tests/golden/reference_v1_tiny.pt``;
+``tests/test_cpu_oracle.py`` holds this oracle to them (logits 2e-5 in fp32, greedy ids equal). What remains unpinned: the
+ViT arithmetic — ``timm`` (pinned ~=1.0.11, pyproject.toml:10-12,46-48) is not installed, so both the golden script and this
+oracle use HF ``SiglipVisionModel``, the published SigLIP graph timm's ``vit_so400m_patch14_siglip_384`` implements.
+This oracle (i) uses the *installed* ``transformers`` 5.5.0 ``LlamaForCausalLM`` / ``SiglipVisionModel`` as the published
+algorithm and (ii) restates, line by line, the reference's own glue around them:
 
   * concat-3 of consecutive patch tokens  .. detikzify/model/v1/modeling_detikzify.py:132-137
   * biased projector ``mm_projector``     .. detikzify/model/v1/modeling_detikzify.py:82,163

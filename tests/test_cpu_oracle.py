@@ -98,3 +98,43 @@ def test_hf_generate_equals_oracle_loop():
     b = o.hf_generate(ids, pix, max_length=ids.shape[1] + 12, do_sample=False)
     assert torch.equal(a, b)
     assert a.shape[1] <= ids.shape[1] + 12   # max_length counts the prompt (reference quirk B.4)
+
+
+# ---------------------------------------------------------------- pinned by the reference's own model code
+REF_GOLD = torch.load(Path(__file__).parent / "golden" / "reference_v1_tiny.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_oracle_matches_reference_model_code(name):
+    """tests/golden/reference_v1_tiny.pt was produced by the reference's OWN ``DetikzifyForCausalLM`` (detikzify/model/v1/
+    modeling_detikzify.py executed from /root/reference by make_reference_golden.py; only the absent ``timm`` ViT is stood
+    in for by HF SigLIP): full-prompt logits with the image span in the middle of the prompt, the concat-3 vision features,
+    and one ``prepare_inputs_for_generation`` + KV-cache decode step. fp32 on both sides: agreement to summation-order noise."""
+    from oracle.hf_oracle import synthetic_pixels
+    cfg, sd, oracle = model_bundle(name)
+    g = REF_GOLD[name]
+    ids = g["input_ids"][None]
+    pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=g["pixel_seed"])
+    logits, cache = oracle.forward_logits(ids, pix, use_cache=True)
+    assert logits.shape[1:] == g["logits"].shape
+    assert (logits[0] - g["logits"]).abs().max().item() < 2e-5
+    assert int(logits[0, -1].argmax()) == g["next_id"]
+    dec, _ = oracle.decode_logits(torch.tensor([[g["next_id"]]]), cache)
+    assert (dec[0, -1] - g["decode_logits"]).abs().max().item() < 2e-5
+    # concat-3 order: the reference's get_vision_features output equals "last n*c tokens, c consecutive tokens per row"
+    tokens, _ = oracle.vision(pix)
+    n, c = cfg.num_patches, cfg.concat_patches
+    feats = tokens[:, tokens.shape[1] - n * c:].reshape(-1, n, tokens.shape[-1] * c)[0]
+    assert (feats - g["vision_features"]).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_oracle_generate_equals_reference_generate(name):
+    """Greedy ids of the reference's own ``DetikzifyForCausalLM.generate`` called with the kwargs of
+    detikzify/infer/generate.py:218-227 (bad_words_ids, begin_suppress_tokens, max_length) == the oracle's decode loop."""
+    from oracle.hf_oracle import synthetic_pixels
+    cfg, sd, oracle = model_bundle(name)
+    g = REF_GOLD[name]
+    pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=g["pixel_seed"])
+    out = oracle.generate(g["generate_prompt"][None], pix, max_length=g["generate_ids"].numel())
+    assert out[0].tolist() == g["generate_ids"].tolist()
