@@ -59,6 +59,7 @@ class ScriptedEngine:
         return SimpleNamespace(**kw)
 
     def sample(self, logits, params, suppress=None, steps=None, seq_ids=None, want_probs=False):
+        self.last_sampling = dict(vars(params))   # what the caller's generation kwargs became
         prev, n = int(logits[0]), int(logits[1])
         self.calls.append(("sample", bool(suppress and suppress[0])))
         return torch.tensor([self._next(prev, n, params, bool(suppress and suppress[0]))]), None

@@ -1,0 +1,142 @@
+"""
+Drop-in boundary: the REFERENCE's own inference driver — detikzify/infer/generate.py (DetikzifyGenerator,
+DetikzifyPipeline, WideNode, rollout streaming), detikzify/mcts/*, detikzify/util/{functools,generation}.py, loaded from
+/root/reference and executed unmodified — runs on top of the objects ``detikzify_b200`` returns (model with ``generate``,
+processor, tokenizer), with a scripted engine standing in for the GPU. This is the claim "only the ``load`` import changes".
+
+Stubbed because they are absent offline and outside the path: torchmetrics (base class only), the TeX toolchain
+(``infer/tikz.py``: pdf2image / pdfCropMargins / pymupdf → a TikzDocument that "compiles" everything), ``util/image.py``
+(pymupdf, requests → two small PIL helpers), ``model/adapter`` (``has_adapter`` → False), ``evaluate/imagesim`` (not used
+with metric="fast"). Skipped on boxes without the reference checkout (the GPU box).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import pytest
+import torch
+from PIL import Image, ImageDraw
+
+from scripted_engine import ScriptedEngine
+
+REF = "/root/reference/detikzify"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not available on this box")
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def reference_infer():
+    saved = {k: v for k, v in sys.modules.items() if k == "torchmetrics" or k.startswith("detikzify")}
+    for k in list(saved):
+        del sys.modules[k]
+    try:
+        tm = types.ModuleType("torchmetrics")
+        tm.Metric = type("Metric", (), {})
+        sys.modules["torchmetrics"] = tm
+        for pkg in ("detikzify", "detikzify.infer", "detikzify.mcts", "detikzify.util", "detikzify.model", "detikzify.evaluate"):
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+        # real reference modules
+        _load("detikzify.mcts.node", f"{REF}/mcts/node.py")
+        _load("detikzify.mcts.montecarlo", f"{REF}/mcts/montecarlo.py")
+        fn = _load("detikzify.util.functools", f"{REF}/util/functools.py")
+        gn = _load("detikzify.util.generation", f"{REF}/util/generation.py")
+        util = sys.modules["detikzify.util"]
+        for mod in (fn, gn):
+            for k, v in vars(mod).items():
+                if not k.startswith("_"):
+                    setattr(util, k, v)
+        util.load = lambda image: image.convert("RGB") if isinstance(image, Image.Image) else Image.open(image).convert("RGB")
+
+        def expand(image, size, do_trim=False):
+            canvas = Image.new("RGB", (size, size), "white")
+            canvas.paste(image, ((size - image.width) // 2, (size - image.height) // 2))
+            return canvas
+        util.expand = expand
+        # stubs for what is absent offline / outside the path
+        adapter = types.ModuleType("detikzify.model.adapter")
+        adapter.has_adapter = lambda model: False
+        sys.modules[adapter.__name__] = adapter
+        sim = types.ModuleType("detikzify.evaluate.imagesim")
+        sim.ImageSim = type("ImageSim", (), {})
+        sys.modules[sim.__name__] = sim
+        tikz = types.ModuleType("detikzify.infer.tikz")
+
+        class TikzDocument:
+            """Stand-in for the TeX toolchain: every program 'compiles'."""
+            def __init__(self, code, timeout=None):
+                self.code, self.timeout = code, timeout
+            is_rasterizable = True
+            compiled_with_errors = False
+            errors = {}
+
+            def rasterize(self):
+                return Image.new("RGB", (32, 32), "white")
+        tikz.TikzDocument = TikzDocument
+        sys.modules[tikz.__name__] = tikz
+        yield _load("detikzify.infer.generate", f"{REF}/infer/generate.py")
+    finally:
+        for k in [k for k in sys.modules if k == "torchmetrics" or k.startswith("detikzify.") or k == "detikzify"]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def _ours(eos_at=40):
+    from detikzify_b200.model import build_processor, preset
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    cfg = preset("tiny")
+    eng = ScriptedEngine(cfg, eos_at=eos_at)
+    return DetikzifyForCausalLM(cfg, engine=eng), build_processor(cfg), eng
+
+
+def _figure(size=90):
+    im = Image.new("RGB", (size, size + 20), "white")
+    d = ImageDraw.Draw(im)
+    d.line((10, 10, size - 10, size - 5), fill="black", width=3)
+    d.ellipse((20, 30, 50, 60), outline="black")
+    return im
+
+
+def test_reference_pipeline_sample_runs_on_our_model(reference_infer):
+    model, proc, eng = _ours(eos_at=30)
+    pipe = reference_infer.DetikzifyPipeline(model=model, processor=proc, metric="fast")
+    assert pipe.gen_kwargs["max_length"] == proc.tokenizer.model_max_length and pipe.gen_kwargs["do_sample"] is True
+    doc = pipe.sample(image=_figure())
+    assert isinstance(doc.code, str) and len(doc.code) > 0
+    # the reference passed its own generation kwargs straight into our generate() (infer/generate.py:218-227)
+    kw = eng.last_sampling
+    assert kw["bad_token"] == model.config.image_token_id and kw["begin_suppress_token"] == model.config.text_config.eos_token_id
+    assert kw["do_sample"] and abs(kw["temperature"] - 0.8) < 1e-6 and abs(kw["top_p"] - 0.95) < 1e-6
+
+
+def test_reference_mcts_simulate_runs_on_our_model(reference_infer):
+    model, proc, eng = _ours(eos_at=36)
+    pipe = reference_infer.DetikzifyPipeline(model=model, processor=proc, metric="fast")
+    results = list(pipe.simulate(image=_figure(), expansions=4))
+    assert len(results) == 4
+    for score, doc in results:
+        assert score == 1 and isinstance(doc.code, str)          # scorable - compiled_with_errors with the stub compiler
+    # rollouts went through the reference's ThreadPool + TokenStreamer + stopping-criteria path and our streaming contract
+    assert sum(1 for c in eng.calls if c[0] == "gen_begin") >= 4
+
+
+def test_reference_generator_abort_and_tree(reference_infer):
+    model, proc, eng = _ours(eos_at=60)
+    gen = reference_infer.DetikzifyGenerator(model=model, processor=proc, image=_figure(), metric=None,
+                                             max_length=proc.tokenizer.model_max_length, temperature=0.8, top_p=0.95, top_k=0,
+                                             do_sample=True)
+    out = [next(gen.simulate(expansions=1)) for _ in range(2)]
+    root = gen.montecarlo.root_node
+    assert root.visits >= 2 and root.children and root.children[0].is_widen_node
+    assert all(score == 1 for score, _ in out)
+    # newline bookkeeping of the reference works with our tokenizer (vocab / decode protocol)
+    assert gen.newlineinfo and all(v.num_lines >= 1 for v in gen.newlineinfo.values())
