@@ -6,8 +6,9 @@ processor, tokenizer), with a scripted engine standing in for the GPU. This is t
 
 Stubbed because they are absent offline and outside the path: torchmetrics (base class only), the TeX toolchain
 (``infer/tikz.py``: pdf2image / pdfCropMargins / pymupdf → a TikzDocument that "compiles" everything), ``util/image.py``
-(pymupdf, requests → two small PIL helpers), ``model/adapter`` (``has_adapter`` → False), ``evaluate/imagesim`` (not used
-with metric="fast"). Skipped on boxes without the reference checkout (the GPU box).
+(pymupdf, requests → two small PIL helpers), ``model/adapter`` (``has_adapter`` → False), POT's ``emd2`` (v1 models pool
+with "cos"). The reference's ``evaluate/imagesim.py`` (SelfSim reward) is loaded for real on a minimal ``torchmetrics.Metric``.
+Skipped on boxes without the reference checkout (the GPU box).
 """
 import importlib.util
 import os
@@ -34,7 +35,7 @@ def _load(name, path):
 
 @pytest.fixture()
 def reference_infer():
-    saved = {k: v for k, v in sys.modules.items() if k == "torchmetrics" or k.startswith("detikzify")}
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("torchmetrics", "ot", "detikzify")}
     for k in list(saved):
         del sys.modules[k]
     try:
@@ -66,9 +67,38 @@ def reference_infer():
         adapter = types.ModuleType("detikzify.model.adapter")
         adapter.has_adapter = lambda model: False
         sys.modules[adapter.__name__] = adapter
-        sim = types.ModuleType("detikzify.evaluate.imagesim")
-        sim.ImageSim = type("ImageSim", (), {})
-        sys.modules[sim.__name__] = sim
+        adapter.AdapterProcessor = type("AdapterProcessor", (), {})
+        adapter.CrossAttentionAdapterMixin = type("CrossAttentionAdapterMixin", (), {})
+        _load("detikzify.util.torch", f"{REF}/util/torch.py")
+        util.infer_device = sys.modules["detikzify.util.torch"].infer_device
+        # torchmetrics.Metric: the slice of its protocol the reference's ImageSim relies on (states, reset, device/dtype)
+        class Metric(torch.nn.Module):
+            def __init__(self, **kwargs):
+                super().__init__()
+                self._defaults, self._dtype = {}, torch.float32
+
+            def add_state(self, name, default, dist_reduce_fx=None):
+                self._defaults[name] = default
+                setattr(self, name, default.clone())
+
+            def reset(self):
+                for k, v in self._defaults.items():
+                    setattr(self, k, v.clone())
+
+            def set_dtype(self, dtype):
+                self._dtype = dtype
+                return self
+
+            device = property(lambda self: self._device)
+            dtype = property(lambda self: self._dtype)
+        tm.Metric = Metric
+        tmf = types.ModuleType("torchmetrics.functional")
+        tmf.pairwise_cosine_similarity = lambda a, b: torch.nn.functional.normalize(a, dim=-1) @ torch.nn.functional.normalize(b, dim=-1).T
+        sys.modules["torchmetrics.functional"] = tmf
+        ot, otlp = types.ModuleType("ot"), types.ModuleType("ot.lp")
+        otlp.emd2 = lambda **kw: (_ for _ in ()).throw(NotImplementedError("emd mode needs POT"))   # v1 models pool with "cos"
+        sys.modules["ot"], sys.modules["ot.lp"] = ot, otlp
+        _load("detikzify.evaluate.imagesim", f"{REF}/evaluate/imagesim.py")
         tikz = types.ModuleType("detikzify.infer.tikz")
 
         class TikzDocument:
@@ -85,7 +115,7 @@ def reference_infer():
         sys.modules[tikz.__name__] = tikz
         yield _load("detikzify.infer.generate", f"{REF}/infer/generate.py")
     finally:
-        for k in [k for k in sys.modules if k == "torchmetrics" or k.startswith("detikzify.") or k == "detikzify"]:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("torchmetrics", "ot", "detikzify")]:
             del sys.modules[k]
         sys.modules.update(saved)
 
@@ -140,3 +170,17 @@ def test_reference_generator_abort_and_tree(reference_infer):
     assert all(score == 1 for score, _ in out)
     # newline bookkeeping of the reference works with our tokenizer (vocab / decode protocol)
     assert gen.newlineinfo and all(v.num_lines >= 1 for v in gen.newlineinfo.values())
+
+
+def test_reference_selfsim_metric_runs_on_our_vision_model(reference_infer):
+    """metric="model": the reference's ImageSim.from_detikzify wraps OUR model.model.vision_model / image processor and
+    computes the SelfSim reward from pooler_output (evaluate/imagesim.py:60-125); MCTS then min-max-normalises it."""
+    model, proc, eng = _ours(eos_at=36)
+    pipe = reference_infer.DetikzifyPipeline(model=model, processor=proc, metric="model")
+    assert type(pipe.metric).__name__ == "ImageSim" and pipe.metric.mode == "cos"
+    pipe.metric.update(img1=_figure(), img2=_figure())
+    assert pipe.metric.compute() == pytest.approx(1.0)            # identical figures -> cosine 1
+    pipe.metric.reset()
+    results = list(pipe.simulate(image=_figure(), expansions=3))
+    assert len(results) == 3 and all(-1.0 <= score <= 1.0 + 1e-9 for score, _ in results)
+    assert any(c[0] == "vit_encode" for c in eng.calls)
