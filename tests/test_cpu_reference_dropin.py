@@ -184,3 +184,38 @@ def test_reference_selfsim_metric_runs_on_our_vision_model(reference_infer):
     results = list(pipe.simulate(image=_figure(), expansions=3))
     assert len(results) == 3 and all(-1.0 <= score <= 1.0 + 1e-9 for score, _ in results)
     assert any(c[0] == "vit_encode" for c in eng.calls)
+
+
+def test_image_processor_matches_reference_preprocess():
+    """§8 row a1: our host-side DetikzifyImageProcessor against the reference's own class
+    (detikzify/model/v1/processing_detikzify.py:162-253, loaded from /root/reference; only ``timm.data`` / ``timm.models``,
+    which its ``from_pretrained`` would consult for the SigLIP data config, are stubbed). The instance is built from the
+    dict ``from_pretrained`` assembles (:104-117) with timm's published config of vit_so400m_patch14_siglip_384:
+    input 3x384x384, mean = std = 0.5, bicubic."""
+    import numpy as np
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] == "timm"}
+    try:
+        timm = types.ModuleType("timm"); timm.__path__ = []
+        data, models = types.ModuleType("timm.data"), types.ModuleType("timm.models")
+        cfg = {"input_size": [3, 384, 384], "mean": (0.5, 0.5, 0.5), "std": (0.5, 0.5, 0.5), "crop_mode": "center"}
+        models.resolve_pretrained_cfg = lambda variant: types.SimpleNamespace(to_dict=lambda: dict(cfg))
+        data.resolve_data_config = lambda d: dict(d)
+        sys.modules.update({"timm": timm, "timm.data": data, "timm.models": models})
+        ref_mod = _load("ref_processing_detikzify", f"{REF}/model/v1/processing_detikzify.py")
+        ref = ref_mod.DetikzifyImageProcessor.from_pretrained("vit_so400m_patch14_siglip_384.webli")
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] == "timm"]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.modules.pop("ref_processing_detikzify", None)
+    from detikzify_b200.model.processing import DetikzifyImageProcessor
+    ours = DetikzifyImageProcessor(size=384)
+    assert ref.size == ours.size and list(ref.image_mean) == ours.image_mean and list(ref.image_std) == ours.image_std
+    assert int(ref.resample) == ours.resample == 3 and abs(ref.rescale_factor - ours.rescale_factor) < 1e-12
+    rng = np.random.default_rng(3)
+    images = [_figure(90), _figure(384).resize((384, 384)), Image.fromarray(rng.integers(0, 255, (200, 311, 3), dtype=np.uint8))]
+    for im in images:
+        a = ref(images=im, return_tensors="pt")["pixel_values"]
+        b = ours(im, return_tensors="pt")["pixel_values"]
+        assert a.shape == b.shape == (1, 3, 384, 384) and b.dtype == torch.float32
+        assert (a.float() - b).abs().max().item() < 1e-6
