@@ -170,12 +170,15 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
 cudaError_t launch_gemm_mma(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
   if ((a.K & 7) || (a.N & 1) || (a.lda & 7) || (a.ldw & 7)) return cudaErrorInvalidValue;
-  static bool attr_done = false;
+  static bool attr_done[64] = {};            // per device
   const int smem = STAGES * 2 * TILE_BYTES;  // 64 KB
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
   gemm_bf16_tn_kernel<<<grid, THREADS, smem, s>>>(a);

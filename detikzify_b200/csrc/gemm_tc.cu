@@ -238,11 +238,15 @@ static cudaError_t launch_tc_variant(const GemmArgs& a, cudaStream_t s, uint64_t
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, a.A, a.M, a.K, a.lda, TBM) || !make_map(&mapB, a.W, a.N, a.K, a.ldw, TBN)) return cudaErrorInvalidValue;
   constexpr int smem = TcCfg<TBN, TSTAGES>::SMEM;
-  static bool attr_done = false;   // (not re-issued per launch: launches may be captured into a CUDA graph)
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TBN, TSTAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // the attribute is per device; set once per device (not per launch: launches may be captured into a CUDA graph)
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(gemm_tc_kernel<TBN, TSTAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid((a.N + TBN - 1) / TBN, (a.M + TBM - 1) / TBM);
   gemm_tc_kernel<TBN, TSTAGES, MIN_CTAS><<<grid, TC_THREADS, smem, s>>>(mapA, mapB, a);
