@@ -376,7 +376,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
   }
   DTK_CK(launch_embed_tokens(tok64 ? nullptr : eng->d_tok, tok64, B, W(eng, "dec.embed"), H, c.vocab, eng->d_x, s, lc));
   const int nsplit = nsplit_for(c, B);
-  if (eng->decode_gemm_min_batch > 0 && B >= eng->decode_gemm_min_batch) {
+  if (eng->decode_gemm_min_batch > 0 && B >= eng->decode_gemm_min_batch && B <= c.max_len) {   // (B rows fit the prefill buffers)
     // ---- batched decode (MCTS rollouts / several figures): the B rows go through the dense matrices as ONE GEMM each, so
     // the weights are streamed once per step instead of once per sequence (the GEMV kernels below re-read them B times:
     // measured 59 ms/step for 32 ds-7b rollouts). Activations are rounded to bf16 GEMM operands exactly as in prefill
