@@ -354,5 +354,30 @@ class DetikzifyPipeline:
             **self.gen_kwargs, **gen_kwargs)
         yield from generator.simulate(expansions or None)
 
+    def sample_batch(self, images, preprocess: bool = True, samples_per_image: int = 1, **gen_kwargs) -> List[TikzDocument]:
+        """Extension (the reference samples one figure at a time): DeTikZify several figures — and/or draw several samples
+        per figure — in ONE lock-step batched decode (``model.generate_batch``): the decoder weights are streamed once per
+        step for the whole batch. Returns ``len(images) * samples_per_image`` documents, image-major. Needs a model loaded
+        with ``max_batch`` / ``max_seqs`` at least that large."""
+        if not hasattr(self.model, "generate_batch"):
+            raise TypeError("sample_batch needs a detikzify_b200 model (generate_batch)")
+        images = [self.load(im, preprocess=preprocess) for im in images]
+        kw = {**self.gen_kwargs, **gen_kwargs}
+        timeout = kw.pop("compile_timeout", 60)
+        prompts, pixels = [], []
+        for im in images:
+            enc = self.processor(images=im, text=None, return_tensors="pt")
+            for _ in range(samples_per_image):
+                prompts.append(enc.input_ids[0])
+                pixels.append(enc["pixel_values"][0])
+        outs = self.model.generate_batch(
+            prompts, pixel_values=torch.stack(pixels), bad_words_ids=[[self.model.config.image_token_id]],
+            begin_suppress_tokens=[self.model.config.text_config.eos_token_id], **kw)
+        docs = []
+        for ids, prompt in zip(outs, prompts):
+            code = self.processor.decode(token_ids=ids[len(prompt):], skip_special_tokens=True)
+            docs.append(TikzDocument(code=code, timeout=timeout))
+        return docs
+
     def __call__(self, *args, **kwargs) -> TikzDocument:
         return self.sample(*args, **kwargs)

@@ -246,6 +246,103 @@ class DetikzifyForCausalLM:
                 streamer.end()
             return out_buf[:, : T0 + len(new_tokens)].to(self.device)
 
+    # ---- batched generation (extension; the reference's generate() is batch-1) ---------------------
+    @torch.no_grad()
+    def generate_batch(self, input_ids: Sequence[torch.Tensor], pixel_values: Optional[torch.Tensor] = None, *,
+                       bad_words_ids=None, begin_suppress_tokens=None, temperature: Optional[float] = None,
+                       top_p: Optional[float] = None, top_k: Optional[int] = None, max_length: Optional[int] = None,
+                       max_new_tokens: Optional[int] = None, do_sample: Optional[bool] = None, seed: Optional[int] = None,
+                       eos_token_id: Optional[int] = None) -> List[torch.Tensor]:
+        """N independent sequences decoded in lock-step: parallel MCTS rollouts of one figure (``pixel_values`` [1,3,S,S]
+        shared) or N figures (``pixel_values`` [N,3,S,S]). One batched decode step per token — the decoder weights are
+        streamed once per step for all N sequences instead of once per sequence — with the same logits processors and
+        per-sequence RNG streams as N separate ``generate()`` calls (sequence i uses RNG stream i of ``seed``).
+        Every sequence stops at its own EOS / ``max_length``; returns a list of 1-D id tensors (prompt included).
+        N is bounded by the engine's ``max_batch`` and free KV slots (``load(..., max_seqs=, max_batch=)``)."""
+        cfg, eng = self.config, self.engine
+        gc = self.generation_config
+        temperature = gc.temperature if temperature is None else temperature
+        top_p = gc.top_p if top_p is None else top_p
+        top_k = gc.top_k if top_k is None else top_k
+        do_sample = gc.do_sample if do_sample is None else do_sample
+        eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+        prompts: List[List[int]] = [(p[0] if p.dim() == 2 else p).tolist() for p in input_ids]
+        N = len(prompts)
+        if N == 0:
+            return []
+        if any(len(p) == 0 for p in prompts):
+            raise ValueError("empty prompt")
+        limits = []
+        for p in prompts:
+            ml = max_length if max_length is not None else (len(p) + max_new_tokens if max_new_tokens is not None else gc.max_length)
+            limits.append(min(int(ml), eng.max_len))
+        patch = cfg.image_token_id
+
+        with self._lock, self._on_stream():
+            imgs = None
+            if pixel_values is not None:
+                pix = pixel_values.to(self.device, torch.float32)
+                if pix.dim() == 3:
+                    pix = pix[None]
+                if pix.shape[0] not in (1, N):
+                    raise ValueError("pixel_values must hold one image (shared) or one image per sequence")
+                imgs = eng.image_embeds(pix)
+            slots: List[int] = []
+            try:
+                for _ in range(N):
+                    slots.append(eng.seq_alloc())
+                last = []
+                for i, ids_host in enumerate(prompts):
+                    img, img_start = None, 0
+                    n_patch_tokens = ids_host.count(patch)
+                    if imgs is not None and n_patch_tokens > 0:   # splice validation (v1/modeling_detikzify.py:176-184)
+                        if n_patch_tokens != cfg.num_patches:
+                            raise ValueError("The number of image patch tokens should be the same as the number of image patches.")
+                        img_start = ids_host.index(patch)
+                        if ids_host[img_start: img_start + n_patch_tokens] != [patch] * n_patch_tokens:
+                            raise ValueError("The image patch tokens should be consecutive.")
+                        img = imgs[i if imgs.shape[0] == N else 0]
+                    ids_dev = torch.tensor(ids_host, dtype=torch.int64)
+                    if self.device.type == "cuda":
+                        ids_dev = ids_dev.pin_memory().to(self.device, non_blocking=True)
+                    lg, _ = eng.prefill(slots[i], ids_dev, 0, img, img_start)
+                    last.append(lg)
+                self._call_counter += 1
+                params = eng.sampling(
+                    temperature=temperature, top_p=top_p, top_k=top_k or 0, do_sample=bool(do_sample),
+                    bad_token=self._first(bad_words_ids), begin_suppress_token=self._first(begin_suppress_tokens),
+                    seed=(seed if seed is not None else torch.initial_seed() + self._call_counter))
+                seq_ids = list(range(N))
+                first, _ = eng.sample(torch.stack(last), params, suppress=[1] * N, steps=[0] * N, seq_ids=seq_ids)
+                toks = [int(t) for t in first.tolist()]
+                outs: List[List[int]] = [list(p) for p in prompts]
+                done = [len(p) >= lim for p, lim in zip(prompts, limits)]   # prompt already at max_length: nothing appended
+                for i in range(N):
+                    if not done[i]:
+                        outs[i].append(toks[i])
+                        done[i] = toks[i] == eos or len(outs[i]) >= limits[i]
+                max_steps = max(lim - len(p) for p, lim in zip(prompts, limits)) - 1
+                if not all(done) and max_steps > 0:
+                    eng.gen_begin(slots, [len(p) for p in prompts], toks, params, seq_ids)
+                    launched = waited = 0
+                    try:
+                        while not all(done) and waited < max_steps:
+                            while launched < waited + 2 and launched < max_steps:
+                                eng.gen_step()
+                                launched += 1
+                            row = eng.gen_wait(waited)
+                            waited += 1
+                            for i in range(N):
+                                if not done[i]:          # finished sequences keep decoding on the device; the host ignores them
+                                    outs[i].append(int(row[i]))
+                                    done[i] = row[i] == eos or len(outs[i]) >= limits[i]
+                    finally:
+                        eng.gen_end()
+                return [torch.tensor(o, dtype=torch.int64, device=self.device) for o in outs]
+            finally:
+                for s in slots:
+                    eng.seq_free(s)
+
     # ---- SelfSim helper: pooled features straight from the engine --------------------------------
     @torch.no_grad()
     def pooled_features(self, pixel_values: torch.Tensor) -> torch.Tensor:

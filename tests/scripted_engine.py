@@ -60,23 +60,29 @@ class ScriptedEngine:
 
     def sample(self, logits, params, suppress=None, steps=None, seq_ids=None, want_probs=False):
         self.last_sampling = dict(vars(params))   # what the caller's generation kwargs became
-        prev, n = int(logits[0]), int(logits[1])
-        self.calls.append(("sample", bool(suppress and suppress[0])))
-        return torch.tensor([self._next(prev, n, params, bool(suppress and suppress[0]))]), None
+        rows = logits.view(-1, 2)                  # one ("last token", "length") row per sequence
+        sup = list(suppress) if suppress else [0] * rows.shape[0]
+        self.calls.append(("sample", bool(sup[0])))
+        return torch.tensor([self._next(int(r[0]), int(r[1]), params, bool(sp)) for r, sp in zip(rows, sup)]), None
 
     def gen_begin(self, slots, positions, first_ids, params, seq_ids=None):
-        self.calls.append(("gen_begin", positions[0], first_ids[0]))
-        self._gen = dict(slot=slots[0], pos=positions[0], tok=first_ids[0], params=params, out=[])
+        self.calls.append(("gen_begin", positions[0], first_ids[0]) if len(slots) == 1 else ("gen_begin", tuple(positions), tuple(first_ids)))
+        self._gen = dict(slots=list(slots), pos=list(positions), tok=list(first_ids), params=params, out=[])
 
     def gen_step(self):
         g = self._gen
-        self._hist[g["slot"]] = self._hist[g["slot"]][: g["pos"]] + [g["tok"]]
-        nxt = self._next(g["tok"], g["pos"] + 1, g["params"], False)
-        g["pos"] += 1; g["tok"] = nxt; g["out"].append(nxt)
+        row = []
+        for b, slot in enumerate(g["slots"]):
+            pos = min(g["pos"][b], self.max_len - 1)          # the device clamps the position the same way
+            self._hist[slot] = self._hist.get(slot, [])[:pos] + [g["tok"][b]]
+            nxt = self._next(g["tok"][b], pos + 1, g["params"], False)
+            g["pos"][b] += 1; g["tok"][b] = nxt
+            row.append(nxt)
+        g["out"].append(row)
         self.calls.append(("gen_step",))
 
     def gen_wait(self, step):
-        return [self._gen["out"][step]]
+        return list(self._gen["out"][step])
 
     def gen_end(self):
         self.calls.append(("gen_end",))

@@ -260,3 +260,58 @@ def test_shard_and_interleave():
     items = list(range(11))
     chunks = [shard(items, r, 4) for r in range(4)]
     assert chunks[1] == [1, 5, 9] and interleave(chunks) == items
+
+
+# ------------------------------------------------------------------ batched generation (extension)
+def test_generate_batch_equals_separate_generate_calls():
+    """N sequences decoded in lock-step give what N batch-1 generate() calls give (same processors, own EOS / max_length
+    per sequence), with one gen loop over all slots and every KV slot handed back."""
+    model, proc, eng = _model(eos_at=40)
+    pix = torch.rand(1, 3, 56, 56)
+    prompts = []
+    for extra in (0, 3, 9):
+        enc = proc(images=_figure(), text=None, return_tensors="pt")
+        prompts.append(torch.cat([enc.input_ids[0], torch.arange(40, 40 + extra)]))
+    singles = [model.generate(input_ids=p[None], pixel_values=pix, max_length=60, do_sample=False,
+                              bad_words_ids=[[model.config.image_token_id]], begin_suppress_tokens=[model.config.eos_token_id])[0]
+               for p in prompts]
+    eng.calls.clear()
+    free_before = set(eng._slots)
+    outs = model.generate_batch(prompts, pixel_values=pix, max_length=60, do_sample=False,
+                                bad_words_ids=[[model.config.image_token_id]], begin_suppress_tokens=[model.config.eos_token_id])
+    assert [o.tolist() for o in outs] == [s.tolist() for s in singles]
+    assert len({len(o) - len(p) for o, p in zip(outs, prompts)}) == 3   # they really stopped at different steps
+    begins = [c for c in eng.calls if c[0] == "gen_begin"]
+    assert len(begins) == 1 and len(begins[0][1]) == 3            # ONE loop over the three slots
+    assert sum(1 for c in eng.calls if c[0] == "image_embeds") == 1
+    assert set(eng._slots) == free_before                          # slots released
+
+
+def test_generate_batch_limits_and_validation():
+    model, proc, eng = _model()
+    enc = proc(images=_figure(), text=None, return_tensors="pt")
+    ids = enc.input_ids[0]
+    pix2 = torch.rand(2, 3, 56, 56)
+    outs = model.generate_batch([ids, ids], pixel_values=pix2, max_new_tokens=5)
+    assert [len(o) for o in outs] == [len(ids) + 5] * 2
+    assert ("image_embeds", (2, 3, 56, 56)) in eng.calls
+    assert model.generate_batch([], pixel_values=None) == []
+    short = model.generate_batch([ids], pixel_values=pix2[:1], max_length=len(ids))      # prompt already at max_length
+    assert short[0].tolist() == ids.tolist()
+    with pytest.raises(ValueError):
+        model.generate_batch([ids[1:]], pixel_values=pix2[:1], max_new_tokens=3)         # wrong number of patch tokens
+    with pytest.raises(ValueError):
+        model.generate_batch([ids, ids, ids], pixel_values=pix2, max_new_tokens=3)       # 2 images for 3 sequences
+
+
+def test_pipeline_sample_batch(monkeypatch):
+    from detikzify_b200.infer import DetikzifyPipeline, TikzDocument
+    model, proc, eng = _model(eos_at=40)
+    monkeypatch.setattr(TikzDocument, "backend", staticmethod(_fake_renderer()))
+    pipe = DetikzifyPipeline(model, proc, metric="fast")
+    docs = pipe.sample_batch([_figure(), _figure(70)], samples_per_image=2)
+    assert len(docs) == 4 and all(isinstance(d, TikzDocument) and d.code for d in docs)
+    begins = [c for c in eng.calls if c[0] == "gen_begin"]
+    assert len(begins) == 1 and len(begins[0][1]) == 4            # one lock-step loop over the four sequences
+    assert ("image_embeds", (4, 3, 56, 56)) in eng.calls
+    assert eng.last_sampling["do_sample"] and abs(eng.last_sampling["temperature"] - 0.8) < 1e-9
