@@ -70,8 +70,12 @@ def build_processor(cfg: DetikzifyConfig, tokenizer=None) -> DetikzifyProcessor:
 def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bool = False, *,
          random_init_weights: Optional[bool] = None, seed: int = 0, state_dict: Optional[Dict[str, torch.Tensor]] = None,
          config: Optional[DetikzifyConfig] = None, max_seqs: int = 2, max_batch: int = 1, broadcast: bool = False,
-         **kwargs):
+         prefix_slots: Optional[int] = None, **kwargs):
     """Returns ``(model, processor)``.
+
+    ``max_seqs`` KV slots are preallocated (0.40 GB each for ds-1.3b at 2k context); ``generate()`` keeps a prefix cache
+    over ``prefix_slots`` of them (default ``max_seqs - max_batch``, at least 1) — for MCTS use e.g. ``max_seqs=8``;
+    ``generate_batch`` / ``sample_batch`` need ``max_batch`` (and as many free slots) >= the number of sequences.
 
     ``broadcast=True`` (multi-GPU, one process per GPU): only rank 0 materialises the weights; the
     packed arena is sent with ONE ``torch.distributed.broadcast`` over NCCL.
@@ -119,7 +123,8 @@ def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bo
         arena = arena.to(dev) if rank0 else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
         dist.broadcast(arena, src=0)  # the single collective of the whole path
 
-    model = DetikzifyForCausalLM(cfg, arena, device=device, dtype=dtype, max_seqs=max_seqs, max_batch=max_batch)
+    model = DetikzifyForCausalLM(cfg, arena, device=device, dtype=dtype, max_seqs=max_seqs, max_batch=max_batch,
+                                 prefix_slots=prefix_slots)
     return model, build_processor(cfg)
 
 

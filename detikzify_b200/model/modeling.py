@@ -73,9 +73,18 @@ class _Inner:
         self.vision_model = DetikzifyVisionModel(owner)
 
 
+class _KVSlot:
+    """One engine KV slot owned by generate(): the token history whose keys/values it holds, and an LRU tick."""
+    __slots__ = ("slot", "tokens", "tick")
+
+    def __init__(self, slot: int):
+        self.slot, self.tokens, self.tick = slot, [], 0
+
+
 class DetikzifyForCausalLM:
     def __init__(self, config: DetikzifyConfig, arena: Optional[torch.Tensor] = None, device=0, dtype=torch.bfloat16,
-                 max_seqs: int = 2, max_batch: int = 1, max_len: Optional[int] = None, engine=None):
+                 max_seqs: int = 2, max_batch: int = 1, max_len: Optional[int] = None, engine=None,
+                 prefix_slots: Optional[int] = None):
         self.config = config
         self.dtype = dtype
         self.name_or_path = config.name_or_path
@@ -90,11 +99,71 @@ class DetikzifyForCausalLM:
         self.model = _Inner(self)
         self._lock = threading.Lock()
         self._stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
-        self._slot = self.engine.seq_alloc()
-        self._slot_tokens: List[int] = []      # token history whose KV is valid in the working slot
-        self._slot_image_key = None
+        # KV prefix cache of generate(): up to ``prefix_slots`` engine slots, each remembering the token history whose KV
+        # it holds. An MCTS expansion prefills only what the best-matching slot does not already hold; when the prompt
+        # diverges from that slot's content the shared prefix is forked (one device copy) into the least recently used
+        # slot, so alternating between branches of the search tree does not thrash a single working slot. The reference
+        # recomputes the whole prompt on every rollout; results are unchanged.
+        self._kv_max = max(1, prefix_slots if prefix_slots is not None else max_seqs - max_batch)
+        self._kv: List[_KVSlot] = [_KVSlot(self.engine.seq_alloc())]
+        self._kv_cur = self._kv[0]
+        self._tick = 0
         self._img_cache = None                  # (pixel tensor on device, image embeds [P,H])
         self._call_counter = 0
+
+    # (kept for callers that reset the cache: ``model._slot_tokens = []`` forgets every cached prefix)
+    @property
+    def _slot_tokens(self) -> List[int]:
+        return self._kv_cur.tokens
+
+    @_slot_tokens.setter
+    def _slot_tokens(self, value: List[int]):
+        if not value:
+            for kv in self._kv:
+                kv.tokens = []
+        else:
+            self._kv_cur.tokens = list(value)
+
+    @property
+    def _slot(self) -> int:
+        return self._kv_cur.slot
+
+    def _pick_slot(self, ids_host: List[int], span_start: int, span_len: int) -> int:
+        """Choose the KV slot for this prompt and make it hold the longest reusable prefix; returns its length L
+        (tokens [0, L) are valid in ``self._kv_cur``; never splits the image span [span_start, span_start+span_len))."""
+        T0 = len(ids_host)
+
+        def lcp(tokens: List[int]) -> int:
+            n, lim = 0, min(len(tokens), T0 - 1)
+            while n < lim and tokens[n] == ids_host[n]:
+                n += 1
+            if span_len and n < span_start + span_len:
+                n = min(n, span_start)
+            return n
+        best = max(self._kv, key=lambda kv: (lcp(kv.tokens), kv.tick))
+        L = lcp(best.tokens)
+        use = best
+        if self._kv_max > 1 and L < len(best.tokens):
+            # the prompt leaves the slot's content: keep that content for later prompts and continue in another slot
+            victim = None
+            if len(self._kv) < self._kv_max:
+                try:
+                    victim = _KVSlot(self.engine.seq_alloc())
+                    self._kv.append(victim)
+                except Exception:        # the engine has no free slot left (other users): continue in place
+                    victim, self._kv_max = None, len(self._kv)
+            if victim is None:
+                others = [kv for kv in self._kv if kv is not best]
+                victim = min(others, key=lambda kv: kv.tick) if others else None
+            if victim is not None:
+                if L > 0:
+                    self.engine.seq_fork(best.slot, victim.slot, L)
+                victim.tokens = best.tokens[:L]
+                use = victim
+        self._tick += 1
+        use.tick = self._tick
+        self._kv_cur = use
+        return L
 
     def _on_stream(self):
         return torch.cuda.stream(self._stream) if self._stream is not None else nullcontext()
@@ -190,14 +259,8 @@ class DetikzifyForCausalLM:
                     streamer.end()
                 return ids2d.to(self.device)
 
-            # -- longest common prefix with the KV already in the working slot
-            hist = self._slot_tokens
-            L = 0
-            lim = min(len(hist), T0 - 1)
-            while L < lim and hist[L] == ids_host[L]:
-                L += 1
-            if img is not None and L < img_start + n_patch_tokens:
-                L = min(L, img_start)  # never split the image span
+            # -- longest common prefix with the KV already held by one of the cache slots
+            L = self._pick_slot(ids_host, img_start, n_patch_tokens if img is not None else 0)
             ids_dev = torch.tensor(ids_host[L:], dtype=torch.int64)
             if self.device.type == "cuda":
                 ids_dev = ids_dev.pin_memory().to(self.device, non_blocking=True)

@@ -30,10 +30,18 @@ class ScriptedEngine:
 
     # -- engine surface used by modeling.py -----------------------------------------------------
     def seq_alloc(self):
-        s = len(self._slots); self._slots.add(s); return s
+        s = 0
+        while s in self._slots:
+            s += 1
+        self._slots.add(s)
+        return s
 
     def seq_free(self, s):
         self._slots.discard(s)
+
+    def seq_fork(self, src, dst, length):
+        self.calls.append(("seq_fork", src, dst, length))
+        self._hist[dst] = list(self._hist.get(src, [])[:length])
 
     def image_embeds(self, pix):
         self.calls.append(("image_embeds", tuple(pix.shape)))

@@ -315,3 +315,58 @@ def test_pipeline_sample_batch(monkeypatch):
     assert len(begins) == 1 and len(begins[0][1]) == 4            # one lock-step loop over the four sequences
     assert ("image_embeds", (4, 3, 56, 56)) in eng.calls
     assert eng.last_sampling["do_sample"] and abs(eng.last_sampling["temperature"] - 0.8) < 1e-9
+
+
+# ------------------------------------------------------------------ KV prefix cache over several slots
+def _prefilled(eng):
+    return sum(c[3] for c in eng.calls if c[0] == "prefill")
+
+
+def test_prefix_cache_over_slots_avoids_thrashing():
+    """Alternating between two branches of a search tree: with one slot every switch re-prefills the branch, with a slot
+    cache only the new suffix is prefilled (the shared prefix is forked). Outputs are identical either way."""
+    from detikzify_b200.model import build_processor, preset
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    cfg = preset("tiny")
+    proc = build_processor(cfg)
+    base = proc(images=_figure(), text=None, return_tensors="pt").input_ids[0]
+    pix = torch.rand(1, 3, 56, 56)
+    A = torch.cat([base, torch.arange(40, 60)])
+    B = torch.cat([base, torch.arange(70, 90)])
+    A2 = torch.cat([A, torch.arange(100, 104)])
+    B2 = torch.cat([B, torch.arange(110, 114)])
+    A3 = torch.cat([A[:-5], torch.arange(120, 124)])       # leaves A's content in the middle
+    seq = [A, B, A2, B2, A3, A2]
+    runs = {}
+    for slots in (1, 4):
+        eng = ScriptedEngine(cfg, max_len=90)
+        model = DetikzifyForCausalLM(cfg, engine=eng, prefix_slots=slots)
+        outs = [model.generate(input_ids=p[None], pixel_values=pix, max_new_tokens=6)[0].tolist() for p in seq]
+        runs[slots] = (outs, _prefilled(eng), [c for c in eng.calls if c[0] == "seq_fork"])
+    assert runs[1][0] == runs[4][0]                          # same results
+    assert not runs[1][2] and runs[4][2]                     # forks only with the cache
+    assert runs[4][1] < 0.6 * runs[1][1], (runs[4][1], runs[1][1])
+    # every fork copies exactly the shared prefix and never splits the image span
+    P = cfg.num_patches
+    for _, src, dst, length in runs[4][2]:
+        assert src != dst and (length >= P or length == 0)
+
+
+def test_prefix_cache_invalidated_by_new_image_and_bounded_by_engine_slots():
+    from detikzify_b200.model import build_processor, preset
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    cfg = preset("tiny")
+    proc = build_processor(cfg)
+    ids = proc(images=_figure(), text=None, return_tensors="pt").input_ids
+    eng = ScriptedEngine(cfg, max_len=90)
+    model = DetikzifyForCausalLM(cfg, engine=eng, prefix_slots=3)
+    model.generate(input_ids=ids, pixel_values=torch.rand(1, 3, 56, 56), max_new_tokens=4)
+    n0 = _prefilled(eng)
+    model.generate(input_ids=ids, pixel_values=torch.rand(1, 3, 56, 56), max_new_tokens=4)   # another figure
+    assert _prefilled(eng) - n0 == ids.shape[1]              # nothing reused across images
+    assert len(model._kv) <= 3
+    # the engine refusing further slots only disables growth
+    eng.seq_alloc = lambda: (_ for _ in ()).throw(RuntimeError("no free KV slot"))
+    other = torch.cat([ids[0], torch.arange(50, 55)])[None]
+    out = model.generate(input_ids=other, pixel_values=None, max_new_tokens=3)
+    assert out.shape[1] == other.shape[1] + 3
