@@ -19,8 +19,9 @@ What is stubbed, and why (recorded in DESIGN.md §6):
     caches are always truthy, which would make ``generate()`` drop the prompt. The script restores the 4.x ``__len__`` on
     ``DynamicCache`` while it runs (a compatibility shim for the third-party library, the reference code is untouched).
 
-Run (in the build container, where /root/reference exists):  python tests/golden/make_reference_golden.py
-Writes tests/golden/reference_v1_tiny.pt (inputs + reference outputs; the test regenerates the weights from the seed).
+Run (in the build container, where /root/reference exists):  python tests/golden/make_reference_golden.py [--ds13b]
+Writes tests/golden/reference_v1_tiny.pt (inputs + reference outputs; the test regenerates the weights from the seed);
+with --ds13b, tests/golden/reference_v1_ds13b.pt at the real detikzify-ds-1.3b shape (last-row logits only).
 """
 import importlib.util
 import sys
@@ -165,5 +166,31 @@ def main():
     print("wrote", Path(__file__).with_name("reference_v1_tiny.pt"))
 
 
+@torch.no_grad()
+def main_ds13b():
+    """BASELINE.json configs[1] shape: the reference model code at the real detikzify-ds-1.3b dimensions (random-init weights
+    from the seed). Only the last-row logits of the prompt and of one cached decode step are kept (2 x 32256 floats)."""
+    restore_v4_cache_truthiness()
+    name = "nllg/detikzify-ds-1.3b"
+    cfg, model = build(name)
+    P = cfg.num_patches
+    g = torch.Generator().manual_seed(1313)
+    ids = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, 32000, (5,), generator=g)]).long()[None]
+    pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=13)
+    res = model(input_ids=ids, pixel_values=pix, use_cache=True, return_dict=True)
+    last = res.logits[0, -1].clone()
+    nxt = last.argmax()[None, None]
+    inputs = model.prepare_inputs_for_generation(torch.cat([ids, nxt], dim=1), past_key_values=res.past_key_values, use_cache=True,
+                                                 pixel_values=pix)
+    res2 = model(**{k: v for k, v in inputs.items() if v is not None}, return_dict=True)
+    out = {"input_ids": ids[0], "pixel_seed": 13, "seed": 0, "last_logits": last, "next_id": int(nxt),
+           "decode_logits": res2.logits[0, -1].clone()}
+    torch.save(out, Path(__file__).with_name("reference_v1_ds13b.pt"))
+    print("ds-1.3b: max|logit|", float(last.abs().max()), "next", int(nxt), "-> reference_v1_ds13b.pt")
+
+
 if __name__ == "__main__":
-    main()
+    if "--ds13b" in sys.argv:
+        main_ds13b()
+    else:
+        main()

@@ -138,3 +138,21 @@ def test_oracle_generate_equals_reference_generate(name):
     pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=g["pixel_seed"])
     out = oracle.generate(g["generate_prompt"][None], pix, max_length=g["generate_ids"].numel())
     assert out[0].tolist() == g["generate_ids"].tolist()
+
+
+def test_oracle_matches_reference_model_code_at_ds13b_shape():
+    """BASELINE.json configs[1] shape (detikzify-ds-1.3b: H 2048, 24 layers, RoPE theta 1e5 / linear x4, so400m ViT @384,
+    729 -> 243 image tokens): last-row logits of the prompt and of one KV-cached decode step from the reference's own
+    DetikzifyForCausalLM (tests/golden/make_reference_golden.py --ds13b) vs the oracle, fp32 on both sides. The GPU parity test
+    at this shape (tests/test_gpu_ds13b.py) compares the CUDA path with this same oracle."""
+    from oracle.hf_oracle import synthetic_pixels
+    gold = torch.load(Path(__file__).parent / "golden" / "reference_v1_ds13b.pt", weights_only=False)
+    cfg, sd, oracle = model_bundle("nllg/detikzify-ds-1.3b")
+    pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=gold["pixel_seed"])
+    logits, cache = oracle.forward_logits(gold["input_ids"][None], pix, use_cache=True)
+    d0 = (logits[0, -1] - gold["last_logits"]).abs().max().item()
+    assert d0 < 2e-4, d0
+    assert int(logits[0, -1].argmax()) == gold["next_id"]
+    dec, _ = oracle.decode_logits(torch.tensor([[gold["next_id"]]]), cache)
+    d1 = (dec[0, -1] - gold["decode_logits"]).abs().max().item()
+    assert d1 < 2e-4, d1
