@@ -95,3 +95,23 @@ def test_product_path_fails_loudly_without_cuda():
     from detikzify_b200.model import load
     with pytest.raises(EngineError):
         load("tiny", device_map=0)
+
+
+def test_plain_c_client_links_and_runs(tmp_path):
+    """The boundary is a real C ABI: a C99 program (no CUDA / torch headers) compiles against include/detikzify_b200.h, links
+    to the shared library and uses the host-only entry points (weight table, arena size, algorithmic decode bytes)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    from detikzify_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None or not _lib.LIB_PATH.exists():
+        pytest.skip("gcc or the built library is not available")
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "abi_client"
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", str(root / "include"), str(root / "tests" / "c" / "abi_client.c"),
+           "-o", str(exe), "-L", str(_lib.LIB_PATH.parent), "-ldtk_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok weights="), (r.returncode, r.stdout, r.stderr)
