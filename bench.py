@@ -336,7 +336,21 @@ def run_ours(args):
             "clocks": clocks,
         }
         if vit:
-            line["vit_encode_ms_per_img"] = {"batch": vit, "note": "SigLIP-so400m/14@384 tokens + pooled output, pixels resident, CUDA events"}
+            # tensor roofline of the ViT (dense contractions, SURVEY.md section 8 a2: 666 GFLOP per image at so400m/14@384)
+            vc = cfg.vision_config
+            n_tok = (vc.image_size // vc.patch_size) ** 2
+            D, Iv, Lv = vc.hidden_size, vc.intermediate_size, vc.num_hidden_layers
+            flop_img = Lv * (2 * n_tok * (4 * D * D + 2 * D * Iv) + 4 * n_tok * n_tok * D) + 2 * n_tok * D * 3 * vc.patch_size ** 2
+            tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+            pk = ROOT / "MEASURED_PEAKS.json"
+            if pk.exists() and json.loads(pk.read_text()).get("bf16_tflops_sustained"):
+                tpeak, tsrc = float(json.loads(pk.read_text())["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            best_b = min(vit, key=vit.get)
+            ach = flop_img / (vit[best_b] * 1e-3) / 1e12
+            line["vit_encode_ms_per_img"] = {
+                "batch": vit, "note": "SigLIP-so400m/14@384 tokens + pooled output, pixels resident, CUDA events",
+                "roofline": {"bound": "tensor", "gflop_per_img": flop_img / 1e9, "achieved": ach, "unit": "TFLOP/s", "at_batch": int(best_b),
+                             "peak": tpeak, "frac": ach / tpeak, "peak_source": tsrc}}
         if e2e_t:
             line["e2e"] = {"value": world * args.steps * new_per_step / e2e_t, "unit": "tokens/s",
                            "h2d_bytes_per_step": int(pix_host.numel() * 4 + P * 8), "d2h_bytes_per_step": int(new_per_step * 4)}
