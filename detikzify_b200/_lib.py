@@ -63,8 +63,8 @@ SYMBOLS = {
     "dtk_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "dtk_decode_bytes": (C.c_uint64, [C.POINTER(DtkConfig), C.c_int]),
     "dtk_launch_count": (C.c_uint64, [_P]),
-    "dtk_dbg_stream_bench": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dtk_dbg_mega_times": (C.c_int, [_P, C.POINTER(C.c_longlong), C.c_int]),
+    "dtk_dbg_mega_trace": (C.c_int, [_P, C.POINTER(C.c_longlong), C.c_int]),
     "dtk_dbg_gemm_impl": (C.c_int, [C.c_int]),
     "dtk_dbg_gemm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dtk_dbg_flash_attn": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

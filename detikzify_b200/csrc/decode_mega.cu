@@ -82,41 +82,93 @@ DTK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t ba
                : "memory");
 }
 DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_THREADS) : "memory"); }
-DTK_DEV float ldcg_f(const float* p) { return __ldcg(p); }
 
-// grid barrier over the consumer threads of all CTAs (producer warps never take part).
-// bar.sync makes the CTA's writes visible to thread 0 (cta scope); its release-reduction publishes them
-// cumulatively at gpu scope; the acquire poll + bar.sync orders every thread's later ld.cg reads.
-DTK_DEV void grid_barrier(unsigned long long* counter, unsigned long long target, int flags) {
+// ------------------------------------------------------------------ tagged activation words
+// Every activation value that crosses CTAs (residual stream, q, the new key/value row, attention partials and output,
+// the SwiGLU vector) travels as ONE 8-byte word {fp32 value, 32-bit phase tag} written with st.relaxed.gpu and read with
+// ld.relaxed.gpu: aligned 8-byte accesses are single-copy atomic, so a reader that sees the expected tag also sees the
+// value written with it — no release fence on the producer side and no acquire on the consumer side (the release fence
+// alone cost ~0.8 us of every phase: 0.919 -> 0.821 ms per token when it was dropped). The grid barrier below is
+// therefore only a HINT that says when polling is worthwhile; correctness rests on the tags. A buffer is overwritten one
+// layer later, after a chain of data dependencies that runs through every CTA which read it (write-after-read safe).
+typedef unsigned long long u64;
+DTK_DEV void st_tag(u64* p, float v, uint32_t tag) {
+  const u64 w = ((u64)tag << 32) | (u64)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(w) : "memory");
+}
+DTK_DEV ulonglong2 ld_tag2(const u64* p) {
+  ulonglong2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+  return r;
+}
+DTK_DEV u64 ld_tag1(const u64* p) {
+  u64 r;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+DTK_DEV bool tag_ok(u64 w, uint32_t tag) { return (uint32_t)(w >> 32) == tag; }
+DTK_DEV float tag_val(u64 w) { return __uint_as_float((uint32_t)w); }
+struct Spin {   // bounded polling: trap instead of hanging the GPU
+  uint32_t n = 0;
+  long long t0 = 0;
+  DTK_DEV void tick() {
+    if ((++n & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPIN_CYCLES) __trap();
+    }
+  }
+};
+// N consecutive tagged words (N even, 16-byte aligned) -> values; polls until every tag matches
+template <int N>
+DTK_DEV void ld_tagged(const u64* p, uint32_t tag, bool nowait, float (&out)[N]) {
+  ulonglong2 w[N / 2];
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) w[i] = ld_tag2(p + 2 * i);
+  Spin sp;
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i)
+      if (!(tag_ok(w[i].x, tag) && tag_ok(w[i].y, tag))) { ok = false; w[i] = ld_tag2(p + 2 * i); }
+    if (ok || nowait) break;
+    sp.tick();
+  }
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) { out[2 * i] = tag_val(w[i].x); out[2 * i + 1] = tag_val(w[i].y); }
+}
+DTK_DEV float ld_tagged1(const u64* p, uint32_t tag, bool nowait) {
+  u64 w = ld_tag1(p);
+  Spin sp;
+  while (!tag_ok(w, tag) && !nowait) { sp.tick(); w = ld_tag1(p); }
+  return tag_val(w);
+}
+
+// grid-wide arrival counter over the consumer threads of all CTAs (producer warps never take part): a HINT, not a memory
+// barrier — relaxed arrive, relaxed poll. It tells a CTA when the other CTAs have issued their tagged stores.
+DTK_DEV void hint_barrier(unsigned long long* counter, unsigned long long target, int flags) {
   consumer_sync();
   if (flags & 2) return;
   if (threadIdx.x == 0) {
-    if (flags & 4) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
-    else asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
-    uint32_t spins = 0;
-    long long t0 = 0;
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
+    Spin sp;
     unsigned long long v;
     do {
-      if (flags & 8) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
-      else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
-      if (v < target && (++spins & 1023u) == 0) {
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > SPIN_CYCLES) __trap();
-      }
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
+      if (v < target) sp.tick();
     } while (v < target);
   }
   consumer_sync();
 }
 
 // ------------------------------------------------------------------ work description
-enum { PH_QKV = 0, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_LM = 5 };
+enum { PH_QKV = 0, PH_ATTN = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_LM = 5 };
 
 // attention split: CTA c handles head c % heads, key range index c / heads (cph ranges per head)
 struct AttnSplit {
   int active, head, j0, j1, last;  // keys [j0, j1) among the OLD keys [0, pos); `last` also takes key `pos`
   int cph;                         // CTAs per head
-  int n_items;                     // 16-key items
+  int n_items;                     // 16-key ring items (K rows + V rows of 16 consecutive positions)
 };
 DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   AttnSplit a;
@@ -136,7 +188,7 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   return a;
 }
 
-// sum over the 256 consumer threads
+// sum over the 256 consumer threads (fixed order: identical in every CTA)
 DTK_DEV float consumer_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
@@ -148,85 +200,108 @@ DTK_DEV float consumer_sum(float v, float* red) {
   return t;
 }
 
-// Stage a K-vector (optionally RMS-normalised) into shared memory as the B operand of mma.m16n8k16:
+// Stage a K-vector into shared memory as the B operand of mma.m16n8k16:
 // entry [kstep S][t] (uint4) = { hi(x[16S+2t], x[16S+2t+1]), hi(x[16S+2t+8], +9), lo(..2t..), lo(..2t+8..) }
-// where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad
-// column reads entry t = lane & 3. Entries for k >= K (padding up to Kp) are zero.
-DTK_DEV void stage_xb(const float* src_f32, const bf16* src_bf16, int K, int Kp, const bf16* norm_w, float eps,
-                      uint4* xb, float* red) {
-  const int tid = threadIdx.x, nsteps = Kp >> 4;
-  constexpr int MAXS = 2;  // k-steps held in registers per thread when normalising (K <= 8192)
-  float v[MAXS][16];
-  float ss = 0.f;
-  if (norm_w) {
+// where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad column reads
+// entry t = lane & 3. Entries for k >= K (padding up to Kp) are zero.
+// The source is a tagged global vector (or, for layer 0, the bf16 embedding row). With norm_w the staged vector is
+// x * w (RMSNorm gain) WITHOUT the 1/rms factor: the GEMV is linear, so the consumers multiply their results by the
+// returned r = rsqrt(mean(x^2) + eps) in the epilogue — the reduction is off the critical path of the staging.
+// One thread handles half a k-step: elements [16S + 4a, +4) and [16S + 8 + 4a, +4) = entries t = 2a, 2a + 1.
+DTK_DEV float stage_vec(const u64* src, uint32_t tag, bool nowait, const bf16* src_bf16, int K, int Kp, const bf16* norm_w,
+                        float eps, uint4* xb, float* red) {
+  const int tid = threadIdx.x, nhalf = Kp >> 3;
+  constexpr int MAXH = 4;  // half k-steps per thread (K <= 8192)
+  float v[MAXH][8];
+  if (src) {
+    ulonglong2 w[MAXH][4];
 #pragma unroll
-    for (int u = 0; u < MAXS; ++u) {
-      const int S = tid + u * CONSUMER_THREADS;
-      if (S < nsteps) {
+    for (int u = 0; u < MAXH; ++u) {
+      const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
+      w[u][0] = w[u][1] = w[u][2] = w[u][3] = make_ulonglong2(0ull, 0ull);
+      if (hs < nhalf && k0 < K) { w[u][0] = ld_tag2(src + k0); w[u][1] = ld_tag2(src + k0 + 2); }
+      if (hs < nhalf && k0 + 8 < K) { w[u][2] = ld_tag2(src + k0 + 8); w[u][3] = ld_tag2(src + k0 + 10); }
+    }
+    Spin sp;
+    for (;;) {
+      bool ok = true;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int k = S * 16 + q4 * 4;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < K) {
-            if (src_bf16) {
-              const uint2 raw = *reinterpret_cast<const uint2*>(src_bf16 + k);
-              const float2 lo2 = unpack_bf16x2(raw.x), hi2 = unpack_bf16x2(raw.y);
-              a = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
-            } else {
-              a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
+      for (int u = 0; u < MAXH; ++u) {
+        const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
+        if (hs < nhalf) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (k0 + (i >> 1) * 8 < K && !(tag_ok(w[u][i].x, tag) && tag_ok(w[u][i].y, tag))) {
+              ok = false;
+              w[u][i] = ld_tag2(src + k0 + (i >> 1) * 8 + (i & 1) * 2);
             }
-            const uint2 wr = *reinterpret_cast<const uint2*>(norm_w + k);
-            const float2 w0 = unpack_bf16x2(wr.x), w1 = unpack_bf16x2(wr.y);
-            ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-            a.x *= w0.x; a.y *= w0.y; a.z *= w1.x; a.w *= w1.y;   // weight now, 1/rms after the reduction
-          }
-          v[u][q4 * 4 + 0] = a.x; v[u][q4 * 4 + 1] = a.y; v[u][q4 * 4 + 2] = a.z; v[u][q4 * 4 + 3] = a.w;
         }
       }
+      if (ok || nowait) break;
+      sp.tick();
     }
-    const float r = rsqrtf(consumer_sum(ss, red) / K + eps);
 #pragma unroll
-    for (int u = 0; u < MAXS; ++u) {
-      const int S = tid + u * CONSUMER_THREADS;
-      if (S < nsteps) {
-        // HF order is (x * rsqrt) * w; here (x * w) * rsqrt — same value up to one fp32 rounding
-        uint32_t hi[8], lo[8];
+    for (int u = 0; u < MAXH; ++u)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = v[u][2 * j] * r, b = v[u][2 * j + 1] * r;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-          hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-          lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
-      }
-    }
+      for (int i = 0; i < 4; ++i) { v[u][2 * i] = tag_val(w[u][i].x); v[u][2 * i + 1] = tag_val(w[u][i].y); }
   } else {
-    for (int S = tid; S < nsteps; S += CONSUMER_THREADS) {
-      float w16[16];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int k = S * 16 + q4 * 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < K) a = __ldcg(reinterpret_cast<const float4*>(src_f32 + k));
-        w16[q4 * 4 + 0] = a.x; w16[q4 * 4 + 1] = a.y; w16[q4 * 4 + 2] = a.z; w16[q4 * 4 + 3] = a.w;
+    for (int u = 0; u < MAXH; ++u) {
+      const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+      if (hs < nhalf && k0 < K) {
+        const uint2 a = *reinterpret_cast<const uint2*>(src_bf16 + k0);
+        const uint2 b = (k0 + 8 < K) ? *reinterpret_cast<const uint2*>(src_bf16 + k0 + 8) : make_uint2(0u, 0u);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y);
+        v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a1.x; v[u][3] = a1.y;
+        v[u][4] = b0.x; v[u][5] = b0.y; v[u][6] = b1.x; v[u][7] = b1.y;
       }
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a = w16[2 * j], b = w16[2 * j + 1];
-        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
     }
   }
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXH; ++u) {
+    const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
+    if (hs < nhalf) {
+      uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0, 0, 0);
+      if (k0 < K) {
+        float y[8];
+        if (norm_w) {
+          const uint2 wa = *reinterpret_cast<const uint2*>(norm_w + k0);
+          const uint2 wb = (k0 + 8 < K) ? *reinterpret_cast<const uint2*>(norm_w + k0 + 8) : make_uint2(0u, 0u);
+          const float2 a0 = unpack_bf16x2(wa.x), a1 = unpack_bf16x2(wa.y), b0 = unpack_bf16x2(wb.x), b1 = unpack_bf16x2(wb.y);
+          const float g[8] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ss += v[u][i] * v[u][i]; y[i] = v[u][i] * g[i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = v[u][i];
+        }
+        uint32_t hi[4], lo[4];   // pairs (0,1) (2,3) of the low quad, (4,5) (6,7) of the high quad
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = y[2 * j], b = y[2 * j + 1];
+          const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+          hi[j] = pack_bf16x2(ah, bh);
+          lo[j] = pack_bf16x2(a - ah, b - bh);
+        }
+        e0 = make_uint4(hi[0], hi[2], lo[0], lo[2]);   // entry t = 2a   : elements k0, k0+1 | k0+8, k0+9
+        e1 = make_uint4(hi[1], hi[3], lo[1], lo[3]);   // entry t = 2a+1 : elements k0+2, k0+3 | k0+10, k0+11
+      }
+      const int S = hs >> 1, a2 = (hs & 1) * 2;
+      xb[S * 4 + a2] = e0;
+      xb[S * 4 + a2 + 1] = e1;
+    }
+  }
+  float r = 1.f;
+  if (norm_w) r = rsqrtf(consumer_sum(ss, red) / K + eps);
   consumer_sync();
+  return r;
 }
 
+// DBG = true: dev instrumentation (phase stamps, per-tile trace, timing-experiment flags) compiled in
+template <bool DBG>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,6 +336,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
+  const bf16* kv_slot = p.kv + (int64_t)slot * p.kv_slot_stride;
 
   // ---- item ownership. The CTA's local TILE sequence (all phases, in order) is dealt to agents by index:
   // local tile n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
@@ -272,7 +348,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   };
   // A weight phase with `groups` 16-row groups is cut into equal blocks of per = ceil(groups / G) groups; only
   // ceil(groups / per) CTAs take part (same amount of work each, so they reach the barrier together), the others
-  // idle for that phase while their producers prefetch ahead. The participating set rotates from phase to phase.
+  // idle for that phase. The participating set rotates from phase to phase.
   auto phase_span = [&](const Walk& w, int groups, int& g0, int& cnt, int& nact) {
     const int per = (groups + G - 1) / G;
     nact = (groups + per - 1) / per;
@@ -305,23 +381,54 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         }
         w.nb += ntiles;
       };
+      long long* tr = nullptr;   // dev trace: row (local tile index within the traced layer), column 0 = issue clock
+      uint32_t tr_nb0 = 0;
       auto stream_phase = [&](const MegaMat& m, int layer) {
         int g0, cnt, nact;
         phase_span(w, m.groups, g0, cnt, nact);
         const bf16* base = m.base + (int64_t)layer * m.layer_stride;
+        const uint32_t nbp = w.nb;
         for_own(cnt * m.tpg, m.tpg, [&](int k, int ks, uint32_t dst, uint32_t fb) {
           mbar_expect_tx(fb, TILE_BYTES);
           bulk_g2s(dst, base + ((int64_t)(g0 + k) * m.tpg + ks) * MEGA_TILE_ELEMS, TILE_BYTES, fb);
+          if (DBG && tr) {
+            const uint32_t row = nbp + (uint32_t)(k * m.tpg + ks) - tr_nb0;
+            if (row < 160u) tr[row * 4] = clock64();
+          }
         });
         w.gb += cnt;
         w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
       };
+      // the CTA's share of the cached keys / values of this layer: item i = positions [j0 + 16 i, +16) of the CTA's
+      // kv head, K rows at slot offset 0 and V rows at 4096 (rows of one head are contiguous in the cache). They do
+      // not depend on this token, so they stream ahead like weights and the attention phase reads shared memory only.
+      auto stream_attn = [&](int layer) {
+        const bf16* kb = kv_slot + (int64_t)layer * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
+        const uint32_t nbp = w.nb;
+        for_own(as.n_items, 1, [&](int k, int, uint32_t dst, uint32_t fb) {
+          const int key0 = as.j0 + k * 16;
+          const uint32_t bytes = (uint32_t)min(16, p.max_len - key0) * 256u;
+          mbar_expect_tx(fb, 2 * bytes);
+          bulk_g2s(dst, kb + (int64_t)key0 * 128, bytes, fb);
+          bulk_g2s(dst + 4096, kb + p.kv_v_offset + (int64_t)key0 * 128, bytes, fb);
+          if (DBG && tr) {
+            const uint32_t row = nbp + (uint32_t)k - tr_nb0;
+            if (row < 160u) tr[row * 4] = clock64();
+          }
+        });
+      };
       for (int l = 0; l < p.L; ++l) {
+        if (DBG) {
+          tr = (p.dbg2 && l == p.dbg_layer) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
+          if (tr) tr_nb0 = w.nb;
+        }
         stream_phase(p.qkv, l);
+        stream_attn(l);
         stream_phase(p.o, l);
         stream_phase(p.gu, l);
         stream_phase(p.down, l);
       }
+      tr = nullptr;
       stream_phase(p.lm, 0);
     }
     return;
@@ -329,11 +436,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   // ================================================================= CONSUMERS
   asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-  unsigned long long bar_target = *p.bar_base;  // barriers completed before this launch (x G)
+  const int dflags = DBG ? p.dbg_flags : 0;
+  const bool nowait = (dflags & 2) != 0;
+  unsigned long long bar_target = p.bar_base[0];   // arrivals counted before this launch
+  const uint32_t epoch = (uint32_t)p.bar_base[1];  // tag of (layer l, phase ph) = epoch + 5 l + ph + 1
   Walk w;
   // visit own tiles of a phase; body(j, k, ks, smem address of the slot) runs after the bytes landed and must
   // finish READING the slot before calling release()
   uint32_t cur_slot = 0;
+  long long* ctr = nullptr;   // dev trace of one layer (see MegaArgs::dbg2)
+  uint32_t ctr_nb0 = 0;
   auto release = [&]() {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * cur_slot);
@@ -345,9 +457,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
       uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
       for (; (int)j < ntiles; j += NCW) {
+        long long* trow = nullptr;
+        if (DBG && ctr) {
+          const uint32_t row = w.nb + j - ctr_nb0;
+          if (row < 160u) trow = ctr + row * 4;
+        }
+        if (DBG && trow && lane == 0) trow[3] = clock64();
         mbar_wait(full0 + 8 * sl, use & 1);
+        if (DBG && trow && lane == 0) trow[1] = clock64();
         cur_slot = sl;
         body((int)j, (int)k, (int)ks, sl);
+        if (DBG && trow && lane == 0) trow[2] = clock64();
         sl += NCW;
         if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
         ks += NCW;
@@ -358,45 +478,66 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   };
 
   // optional phase timestamps (globaltimer ns, comparable across SMs): [CTA][phase][4] = {start, staged, items done, barrier done}
-  long long* dbg = p.dbg ? p.dbg + (int64_t)c * (p.L * 5 + 1) * 4 : nullptr;
+  long long* dbg = (DBG && p.dbg) ? p.dbg + (int64_t)c * (p.L * 5 + 1) * 4 : nullptr;
   int dbg_i = 0;
+  int ctr_ph = 0;
   auto stamp = [&](int k) {
+    if (!DBG) return;
     if (dbg && tid == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
       dbg[dbg_i * 4 + k] = (long long)t;
     }
+    if (ctr && tid == 0 && ctr_ph < 5) ctr[(160 + ctr_ph) * 4 + k] = clock64();
+    if (ctr && k == 3) ++ctr_ph;
   };
 
-  // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, LDS.128, 2 x mma); the warp that finishes a
-  // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows
-  auto run_phase = [&](const MegaMat& m, int ph, int layer) {
+  // tagged cross-CTA vectors (MegaArgs::tg): residual stream after attention (xa) / after the MLP (xb2), q, the new
+  // key and value rows, merged attention output, SwiGLU vector, per-CTA attention partials
+  u64* const t_xa = p.tg;
+  u64* const t_xb = t_xa + p.tg_H;
+  u64* const t_q = t_xb + p.tg_H;
+  u64* const t_kn = t_q + qd;
+  u64* const t_vn = t_kn + kd;
+  u64* const t_att = t_vn + kd;
+  u64* const t_h = t_att + qd;
+  u64* const t_part = t_h + p.tg_I;
+
+  // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, mma); the B fragments of the k-tile are loaded BEFORE the
+  // tile's ldmatrix, so that the first mma can issue as soon as its own A fragment has landed (shared-memory returns are in order: with the B loads queued behind
+  // the sixteen ldmatrix the tensor pipe used to idle until the whole tile had been read). The warp that finishes a
+  // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows; rn = 1/rms of the
+  // staged vector (RMSNorm folded into the epilogue, see stage_vec).
+  auto run_phase = [&](const MegaMat& m, int ph, int layer, float rn, uint32_t tag) {
     int g0, cnt, nact;
     phase_span(w, m.groups, g0, cnt, nact);
     const uint32_t nb0 = w.nb, gb0 = w.gb;
     const int tpg = m.tpg;
+    // residual source of the O / DOWN epilogues: previous value of the row in the other residual buffer
+    const u64* res_src = (ph == PH_O) ? t_xb : t_xa;
+    const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
     for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       {
         const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
         // B operand: even columns of the 16 x 8 B tile carry the hi part of x, odd columns the lo part (column = lane >> 2),
-        // so ONE mma per k-step yields W.hi in accumulator column 0 and W.lo in column 1 (legacy HMMA issues only once
-        // per ~16 cycles per SM sub-partition on sm_100: the tensor pipe, not memory, paces the post-barrier burst in
-        // which a full ring is drained from shared memory). Two independent chains (k-step parity) hide the HMMA latency.
+        // so ONE mma per k-step yields W.hi in accumulator column 0 and W.lo in column 1. Two independent chains
+        // (k-step parity) hide the HMMA latency.
         const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
-        float c1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t a[16][4];
         uint2 b[16];
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-          b[s] = xp[s * 8];
-        }
-        release();   // every lane's shared-memory reads of the slot are issued; the arrive is ordered after them
+        for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
+        float c1[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t a[16][4];
 #pragma unroll
-        for (int s = 0; s < 16; s += 2) {
-          mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
-          mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
+        for (int s = 0; s < 16; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+        release();   // every lane's shared-memory reads of the slot are issued; the arrive is ordered after them
+        if (!(dflags & 1)) {
+#pragma unroll
+          for (int s = 0; s < 16; s += 2) {
+            mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
+            mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
+          }
         }
         // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
         acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
@@ -406,11 +547,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t gslot = (gb0 + (uint32_t)k) % NG;
       if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
         // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
-        // critical path of the group's epilogue (the value is final: it was produced before the last barrier)
+        // critical path of the group's epilogue (the value was published two or more phases ago)
         const int row = (g0 + k) * 16 + lane;
-        float b = 0.f;
-        if (row < p.H) b = (ph == PH_O && layer == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row]) : ldcg_f(p.x + row);
-        rbuf[gslot * 16 + lane] = b;
+        float bres = 0.f;
+        if (row < p.H)
+          bres = (ph == PH_O && layer == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row]) : ld_tagged1(res_src + row, res_tag, nowait);
+        rbuf[gslot * 16 + lane] = bres;
       }
       const uint32_t n = nb0 + (uint32_t)j;
       if ((lane & 3) == 0) {
@@ -439,96 +581,87 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       if (ph == PH_QKV) {
         const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
         const int row0 = hb * 128 + i;
+        const float a0 = v * rn, a1 = v1 * rn;
         if (row0 < qd + kd) {
           const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-          const float y0 = v * csn.x - v1 * csn.y, y1 = v1 * csn.x + v * csn.y;
-          if (row0 < qd) { p.q[row0] = y0; p.q[row0 + 64] = y1; }
+          const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
+          if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
           else {
             const int kh = (row0 - qd) >> 7;
             bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-            dd[i] = __float2bfloat16_rn(y0);
-            dd[i + 64] = __float2bfloat16_rn(y1);
+            const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
+            dd[i] = z0;
+            dd[i + 64] = z1;
+            st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
+            st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
           }
         } else {
           const int kh = (row0 - qd - kd) >> 7;
           bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-          dd[i] = __float2bfloat16_rn(v);
-          dd[i + 64] = __float2bfloat16_rn(v1);
+          const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
+          dd[i] = z0;
+          dd[i + 64] = z1;
+          st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
+          st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
         }
-      } else if (ph == PH_O) {
+      } else if (ph == PH_O || ph == PH_DOWN) {
+        u64* dst = (ph == PH_O) ? t_xa : t_xb;
         const int r0 = gi * 16 + r, r1 = r0 + 8;
         const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
-        if (r0 < p.H) p.x[r0] = b0 + v;
-        if (r1 < p.H) p.x[r1] = b1 + v1;
+        if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
+        if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
       } else if (ph == PH_GU) {
         const int i = gi * 8 + r;
-        if (i < p.I) p.h[i] = silu(v) * v1;
-      } else if (ph == PH_DOWN) {
-        const int r0 = gi * 16 + r, r1 = r0 + 8;
-        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
-        if (r0 < p.H) p.x[r0] = b0 + v;
-        if (r1 < p.H) p.x[r1] = b1 + v1;
+        if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
       } else {
         const int r0 = gi * 16 + r, r1 = r0 + 8;
-        if (r0 < p.V) p.logits[r0] = v;
-        if (r1 < p.V) p.logits[r1] = v1;
+        if (r0 < p.V) p.logits[r0] = v * rn;
+        if (r1 < p.V) p.logits[r1] = v1 * rn;
       }
     });
     w.gb += cnt;
     w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
   };
+  // does this CTA own row groups of the matrix in the phase that starts at walk state w? (idle CTAs skip the staging)
+  auto has_work = [&](const MegaMat& m) {
+    int g0, cnt, nact;
+    phase_span(w, m.groups, g0, cnt, nact);
+    return cnt > 0;
+  };
 
   const int Hp = p.qkv.tpg * 256, Qp = p.o.tpg * 256, Ip = p.down.tpg * 256;
   for (int l = 0; l < p.L; ++l) {
     const int64_t no = (int64_t)l * p.norm_stride;
-    // Pull into L2 what the consumers will read with plain loads later in this layer: the CTA's KV rows (P2) and
-    // the layer's norm weights (P1/P4 staging) — their DRAM latency then hides behind P1 instead of sitting on the
-    // critical path after a barrier (126 MB L2 holds ~1.2 layers of weight stream, the lines stay resident).
-    if (as.active) {
-      const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + as.j0) * 128;
-      const int lines = (as.j1 - as.j0) * 2;   // 128-byte lines per K (and per V) range
-      for (int i = tid; i < lines; i += CONSUMER_THREADS) {
-        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(kb + (int64_t)i * 64));
-        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(kb + p.kv_v_offset + (int64_t)i * 64));
-      }
+    const uint32_t tag0 = epoch + (uint32_t)l * 5u + 1u;   // tag of this layer's phase ph = tag0 + ph
+    if (DBG) {
+      ctr = (p.dbg2 && l == p.dbg_layer) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
+      ctr_nb0 = w.nb; ctr_ph = 0;
     }
-    for (int i = tid * 64; i < p.H; i += CONSUMER_THREADS * 64)
-      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.norm2_0 + no + i));
-    // ---------------- P1: RMSNorm + qkv + RoPE + KV write
+    // ---------------- P1: RMSNorm + qkv + RoPE + KV write  (input: embedding row / previous layer's xb)
     stamp(0);
-    stage_xb(l == 0 ? nullptr : p.x, l == 0 ? p.embed + (int64_t)tok * p.H : nullptr, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
+    float rn = 1.f;
+    if (has_work(p.qkv))
+      rn = stage_vec(l == 0 ? nullptr : t_xb, tag0 - 1, nowait, p.embed + (int64_t)tok * p.H, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
     stamp(1);
-    run_phase(p.qkv, PH_QKV, l);
+    run_phase(p.qkv, PH_QKV, l, rn, tag0 + PH_QKV);
     stamp(2);
-    bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
     stamp(3); ++dbg_i;
 
-    // ---------------- P2: attention over this CTA's key range of its head
-    stamp(0); stamp(1);
+    // ---------------- P2: attention over this CTA's key range of its head. No grid-wide wait in front of it: the cached
+    // keys/values arrive through the ring, and q / the new key and value are polled as tagged words of this head only.
+    stamp(0);
     if (as.active) {
       const int hw = lane >> 4, l16 = lane & 15;
       const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
       float q[8];
-      {
-        const float* qp = p.q + as.head * 128 + l16 * 8;
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(qp)), b = __ldcg(reinterpret_cast<const float4*>(qp + 4));
-        q[0] = a.x * sl2; q[1] = a.y * sl2; q[2] = a.z * sl2; q[3] = a.w * sl2;
-        q[4] = b.x * sl2; q[5] = b.y * sl2; q[6] = b.z * sl2; q[7] = b.w * sl2;
-      }
-      // the key/value of the token being decoded (written in P1 of this launch): fetch early
-      uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
-      if (as.last && warp == 0) {
-        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kvh * p.max_len + pos) * 128;
-        knew = __ldcg(reinterpret_cast<const uint4*>(kb + l16 * 8));
-        vnew = __ldcg(reinterpret_cast<const uint4*>(kb + p.kv_v_offset + l16 * 8));
-      }
+      ld_tagged<8>(t_q + as.head * 128 + l16 * 8, tag0 + PH_QKV, nowait, q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] *= sl2;
+      stamp(1);
       float m = -INFINITY, lsum = 0.f, o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
-      auto key_update = [&](const uint4& kraw, const uint4& vraw, bool valid) {
-        float kf[8];
-        unpack8(kraw, kf);
+      auto key_update = [&](const float (&kf)[8], const float (&vf)[8], bool valid) {
         float s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
@@ -538,38 +671,41 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         if (valid) {
           const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
-          float vf[8];
-          unpack8(vraw, vf);
           lsum = lsum * alpha + pj;
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * vf[i];
           m = mn;
         }
       };
-      {
-        // keys j0 + hid, j0 + hid + 16, ... for half-warp hid (16 half-warps per CTA): the rows were pulled into L2
-        // at the start of the layer; up to 8 keys (16 loads) are in flight per lane, i.e. one L2 round trip per
-        // 128 keys of the range
-        const bf16* kb = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
-        const bf16* vb = kb + p.kv_v_offset;
-        const int hid = warp * 2 + hw;
-        for (int jb = as.j0; jb < as.j1; jb += 128) {   // warp-uniform trip count
-          uint4 kr[8], vr[8];
+      // ring items: 16 positions each; half-warp hw takes positions hw, hw + 2, ... of the item
+      for_own(as.n_items, 1, [&](int j, int, int, uint32_t sl) {
+        const uint32_t base = ring_u32 + sl * TILE_BYTES + l16 * 16;
+        const int key0 = as.j0 + j * 16;
+        uint4 kr[8], vr[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = jb + u * 16 + hid;
-            kr[u] = vr[u] = make_uint4(0, 0, 0, 0);
-            if (j < as.j1) {
-              kr[u] = __ldcg(reinterpret_cast<const uint4*>(kb + (int64_t)j * 128 + l16 * 8));
-              vr[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (int64_t)j * 128 + l16 * 8));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) key_update(kr[u], vr[u], jb + u * 16 + hid < as.j1);
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t a = base + (uint32_t)(u * 2 + hw) * 256u;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(kr[u].x), "=r"(kr[u].y), "=r"(kr[u].z), "=r"(kr[u].w) : "r"(a));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(vr[u].x), "=r"(vr[u].y), "=r"(vr[u].z), "=r"(vr[u].w) : "r"(a + 4096u));
         }
+        release();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float kf[8], vf[8];
+          unpack8(kr[u], kf);
+          unpack8(vr[u], vf);
+          key_update(kf, vf, key0 + u * 2 + hw < as.j1);
+        }
+      });
+      if (as.last && warp == 0) {   // the key / value of the token being decoded (published by P1 of this launch)
+        float kf[8], vf[8];
+        ld_tagged<8>(t_kn + kvh * 128 + l16 * 8, tag0 + PH_QKV, nowait, kf);
+        ld_tagged<8>(t_vn + kvh * 128 + l16 * 8, tag0 + PH_QKV, nowait, vf);
+        key_update(kf, vf, hw == 0);
       }
-      if (as.last && warp == 0) key_update(knew, vnew, hw == 0);
-      // merge the 16 half-warp states -> one partial per CTA
+      // merge the 16 half-warp states -> one partial per CTA (the scratch aliases the staged qkv input: slower warps of
+      // this CTA may still be reading it for their last P1 tiles, there is no CTA-wide sync between P1 and P2)
+      consumer_sync();
       float* sm_m = actf;            // [16]
       float* sm_l = actf + 16;       // [16]
       float* sm_o = actf + 32;       // [16][128]
@@ -578,6 +714,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 #pragma unroll
       for (int i = 0; i < 8; ++i) sm_o[hidx * 128 + l16 * 8 + i] = o[i];
       consumer_sync();
+      const uint32_t ptag = tag0 + PH_ATTN;
       if (tid < 128) {
         float M = -INFINITY;
 #pragma unroll
@@ -589,89 +726,122 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           Lt += sm_l[h] * wgt;
           O += sm_o[h * 128 + tid] * wgt;
         }
-        float* pp = p.part + (int64_t)c * 132;
-        pp[tid] = O;
-        if (tid == 0) { pp[128] = M; pp[129] = Lt; }
+        u64* pp = t_part + (int64_t)c * 132;
+        st_tag(pp + tid, O, ptag);
+        if (tid == 0) { st_tag(pp + 128, M, ptag); st_tag(pp + 129, Lt, ptag); }
       }
-      // the LAST CTA of this head to get here merges the head's partials into the normalised output
+      // the LAST CTA of this head to get here merges the head's partials into the normalised output (the partials are
+      // tagged, so the arrival counter needs no release / acquire)
       consumer_sync();
       if (tid == 0) {
         unsigned prev;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
+        asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
         red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
       }
       consumer_sync();
       if (red[8] != 0.f) {
         if (tid < 128) {
-          float ms[16], lv[16], ov[16];
+          // partials of the head's CTAs in batches of RB (all loads of a batch are independent: one L2 round trip),
+          // folded into a running (max, sum, output) in CTA order
+          constexpr int RB = 10;
+          float M = -INFINITY, Lt = 0.f, O = 0.f;
+          for (int rb = 0; rb < as.cph; rb += RB) {
+            u64 wm[RB], wl[RB], wo[RB];
 #pragma unroll
-          for (int r = 0; r < 16; ++r) {   // all loads are independent: one L2 round trip
-            const float* pp = p.part + (int64_t)(r * p.heads + as.head) * 132;
-            const bool ok = r < as.cph;
-            ms[r] = ok ? ldcg_f(pp + 128) : -INFINITY;
-            lv[r] = ok ? ldcg_f(pp + 129) : 0.f;
-            ov[r] = ok ? ldcg_f(pp + tid) : 0.f;
+            for (int r = 0; r < RB; ++r) {
+              const u64* pp = t_part + (int64_t)((rb + r) * p.heads + as.head) * 132;
+              if (rb + r < as.cph) { wm[r] = ld_tag1(pp + 128); wl[r] = ld_tag1(pp + 129); wo[r] = ld_tag1(pp + tid); }
+            }
+            Spin sp;
+            for (;;) {
+              bool ok = true;
+#pragma unroll
+              for (int r = 0; r < RB; ++r) {
+                if (rb + r < as.cph) {
+                  const u64* pp = t_part + (int64_t)((rb + r) * p.heads + as.head) * 132;
+                  if (!tag_ok(wm[r], ptag)) { ok = false; wm[r] = ld_tag1(pp + 128); }
+                  if (!tag_ok(wl[r], ptag)) { ok = false; wl[r] = ld_tag1(pp + 129); }
+                  if (!tag_ok(wo[r], ptag)) { ok = false; wo[r] = ld_tag1(pp + tid); }
+                }
+              }
+              if (ok || nowait) break;
+              sp.tick();
+            }
+            float Mb = M;
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+              if (rb + r < as.cph) Mb = fmaxf(Mb, tag_val(wm[r]));
+            const float sc = (M == -INFINITY) ? 0.f : exp2f(M - Mb);
+            Lt *= sc; O *= sc;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+              if (rb + r < as.cph) {
+                const float mr = tag_val(wm[r]);
+                const float wgt = (mr == -INFINITY) ? 0.f : exp2f(mr - Mb);
+                Lt += tag_val(wl[r]) * wgt;
+                O += tag_val(wo[r]) * wgt;
+              }
+            }
+            M = Mb;
           }
-          float M = -INFINITY;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) M = fmaxf(M, ms[r]);
-          float Lt = 0.f, O = 0.f;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const float wgt = (ms[r] == -INFINITY) ? 0.f : exp2f(ms[r] - M);
-            Lt += lv[r] * wgt;
-            O += ov[r] * wgt;
-          }
-          p.attn[as.head * 128 + tid] = O / Lt;
+          st_tag(t_att + as.head * 128 + tid, O / Lt, ptag);
         }
-        if (tid == 0) p.head_cnt[as.head] = 0u;  // self-resetting (next use is a grid barrier away)
+        if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p.head_cnt + as.head), "r"(0u) : "memory");  // next use is a layer away
       }
+    } else {
+      stamp(1);
     }
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
+    hint_barrier(p.bar_count, bar_target, dflags);
     stamp(3); ++dbg_i;
 
     // ---------------- P3: o-proj + residual on the merged attention output
     stamp(0);
-    stage_xb(p.attn, nullptr, qd, Qp, nullptr, 0.f, xb, red);
+    if (has_work(p.o)) stage_vec(t_att, tag0 + PH_ATTN, nowait, nullptr, qd, Qp, nullptr, 0.f, xb, red);
     stamp(1);
-    run_phase(p.o, PH_O, l);
+    run_phase(p.o, PH_O, l, 1.f, tag0 + PH_O);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
+    hint_barrier(p.bar_count, bar_target, dflags);
     stamp(3); ++dbg_i;
 
     // ---------------- P4: RMSNorm + gate/up + SiLU*mul
     stamp(0);
-    stage_xb(p.x, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red);
+    rn = 1.f;
+    if (has_work(p.gu)) rn = stage_vec(t_xa, tag0 + PH_O, nowait, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red);
     stamp(1);
-    run_phase(p.gu, PH_GU, l);
+    run_phase(p.gu, PH_GU, l, rn, tag0 + PH_GU);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
+    hint_barrier(p.bar_count, bar_target, dflags);
     stamp(3); ++dbg_i;
 
     // ---------------- P5: down + residual
     stamp(0);
-    stage_xb(p.h, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
+    if (has_work(p.down)) stage_vec(t_h, tag0 + PH_GU, nowait, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
     stamp(1);
-    for (int i = tid * 64; i < p.H; i += CONSUMER_THREADS * 64)   // next stage's norm weights -> L2 (the stream evicted them since)
-      asm volatile("prefetch.global.L2 [%0];\n" ::"l"((l + 1 < p.L ? p.norm1_0 + no + p.norm_stride : p.final_norm) + i));
-    run_phase(p.down, PH_DOWN, l);
+    run_phase(p.down, PH_DOWN, l, 1.f, tag0 + PH_DOWN);
     stamp(2);
     bar_target += G;
-    grid_barrier(p.bar_count, bar_target, p.dbg_flags);
+    hint_barrier(p.bar_count, bar_target, dflags);
     stamp(3); ++dbg_i;
   }
   // ---------------- final RMSNorm + lm_head
+  ctr = nullptr;
   stamp(0);
-  stage_xb(p.x, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red);
+  float rn = 1.f;
+  const uint32_t tagf = epoch + (uint32_t)p.L * 5u;   // = tag of the last layer's P5
+  if (has_work(p.lm)) rn = stage_vec(t_xb, tagf, nowait, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red);
   stamp(1);
-  run_phase(p.lm, PH_LM, 0);
+  run_phase(p.lm, PH_LM, 0, rn, 0u);
   stamp(2); stamp(3);
-  // publish the barrier epoch for the next launch (stream-ordered): every CTA executed 5L barriers
-  if (c == 0 && tid == 0 && !(p.dbg_flags & 2)) *p.bar_base = bar_target;
+  // publish the arrival count and the tag epoch for the next launch (stream-ordered): every CTA made 4L arrivals and
+  // the launch used tags epoch + 1 .. epoch + 5L
+  if (c == 0 && tid == 0 && !(dflags & 2)) {
+    p.bar_base[0] = bar_target;
+    p.bar_base[1] = (unsigned long long)(uint32_t)(epoch + (uint32_t)p.L * 5u);
+  }
 }
 
 // ------------------------------------------------------------------ one-time weight re-tiling
@@ -725,6 +895,8 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   if (actf < 32 + 16 * 128) actf = 32 + 16 * 128;  // attention merge scratch
   actf = (actf + 31) & ~31;
   a.act_floats = actf;
+  a.tg_H = pad(H);
+  a.tg_I = pad(I);
   if ((I + 255) / 256 > NT - 44) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
   const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
@@ -742,10 +914,12 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
 
 cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint64_t* counter) {
   const int smem = mega_smem_bytes(a);
-  cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const bool dbgk = a.dbg != nullptr || a.dbg2 != nullptr || a.dbg_flags != 0;
+  const void* fn = dbgk ? (const void*)decode_mega_kernel<true> : (const void*)decode_mega_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)decode_mega_kernel, dim3(grid), dim3(MEGA_THREADS), args, (size_t)smem, s);
+  e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, (size_t)smem, s);
   if (counter) ++*counter;
   return e;
 }

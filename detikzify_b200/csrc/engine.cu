@@ -142,12 +142,13 @@ struct dtk_engine {
   int decode_gemm_min_batch = 4;  // B >= this: batched decode runs the dense matrices as tensor-core GEMMs (weights once per step)
   bool gen_mega = false;
   SampleArgs gen_sample{};
-  float* d_part = nullptr;
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
   unsigned int* d_head_cnt = nullptr;
   bf16* d_tiled = nullptr;             // decode-side re-tiled copy of the decoder matrices
-  uint2* d_tagged = nullptr;           // {value, epoch} activation buffers of the persistent kernel
+  unsigned long long* d_tagged = nullptr;  // {fp32 value, phase tag} cross-CTA activation words of the persistent kernel
   long long* d_dbg = nullptr;           // phase timestamps of the persistent kernel (option mega_debug)
+  long long* d_dbg2 = nullptr;          // per-tile clock trace of one layer (option mega_trace_layer)
+  int mega_trace_layer = -1;
   int mega_debug = 0;
   int mega_flags = 0;
 };
@@ -371,6 +372,8 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
+    m.dbg2 = (eng->mega_debug && eng->mega_trace_layer >= 0) ? eng->d_dbg2 : nullptr;
+    m.dbg_layer = eng->mega_trace_layer;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
     return DTK_OK;
   }
@@ -612,18 +615,24 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
       m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
-      m.x = eng->d_x; m.q = eng->d_q; m.h = eng->d_h; m.logits = eng->d_logits;
-      DTK_ALLOC(eng->d_part, (int64_t)grid * 132);
-      DTK_ALLOC(eng->d_bar, 2);
-      DTK_CK(cudaMemset(eng->d_bar, 0, 2 * sizeof(unsigned long long)));
-      m.part = eng->d_part; m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
-      m.attn = eng->d_att;
+      m.logits = eng->d_logits;
+      {
+        const int64_t words = 2 * (int64_t)m.tg_H + 2 * (int64_t)qd + 2 * (int64_t)c.kv_heads * 128 + m.tg_I + (int64_t)grid * 132;
+        DTK_ALLOC(eng->d_tagged, words);
+        DTK_CK(cudaMemset(eng->d_tagged, 0, (size_t)words * sizeof(unsigned long long)));
+        m.tg = eng->d_tagged;
+      }
+      DTK_ALLOC(eng->d_bar, 4);
+      DTK_CK(cudaMemset(eng->d_bar, 0, 4 * sizeof(unsigned long long)));
+      m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
       DTK_ALLOC(eng->d_head_cnt, c.heads);
       DTK_CK(cudaMemset(eng->d_head_cnt, 0, c.heads * sizeof(unsigned int)));
       m.head_cnt = eng->d_head_cnt;
       DTK_ALLOC(eng->d_dbg, (int64_t)grid * (c.layers * 5 + 1) * 4);
       DTK_CK(cudaMemset(eng->d_dbg, 0, (size_t)grid * (c.layers * 5 + 1) * 4 * sizeof(long long)));
-      m.dbg = nullptr;
+      DTK_ALLOC(eng->d_dbg2, (int64_t)grid * MEGA_DBG2_ROWS * 4);
+      DTK_CK(cudaMemset(eng->d_dbg2, 0, (size_t)grid * MEGA_DBG2_ROWS * 4 * sizeof(long long)));
+      m.dbg = nullptr; m.dbg2 = nullptr; m.dbg_layer = -1;
       eng->mega_grid = grid;
       eng->mega_ok = true;
     }
@@ -642,7 +651,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_part, eng->d_bar, eng->d_dbg, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
@@ -1006,6 +1015,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->mega_debug = value ? 1 : 0;
     return DTK_OK;
   }
+  if (std::strcmp(key, "mega_trace_layer") == 0) {  // dev: per-tile clock trace of this layer (-1 = off); needs mega_debug
+    eng->mega_trace_layer = (int)value;
+    return DTK_OK;
+  }
   eng->err = std::string("unknown option ") + key;
   return DTK_ERR_INVALID;
 }
@@ -1031,6 +1044,16 @@ int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values) {
   DTK_CK(cudaSetDevice(eng->device));
   DTK_CK(cudaDeviceSynchronize());
   DTK_CK(cudaMemcpy(out_host, eng->d_dbg, (size_t)(n < max_values ? n : max_values) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int dtk_dbg_mega_trace(dtk_engine* eng, long long* out_host, int max_values) {
+  if (!eng || !out_host) return DTK_ERR_INVALID;
+  DTK_REQUIRE(eng->d_dbg2 != nullptr, "persistent kernel unavailable");
+  const int n = eng->mega_grid * MEGA_DBG2_ROWS * 4;
+  DTK_CK(cudaSetDevice(eng->device));
+  DTK_CK(cudaDeviceSynchronize());
+  DTK_CK(cudaMemcpy(out_host, eng->d_dbg2, (size_t)(n < max_values ? n : max_values) * sizeof(long long), cudaMemcpyDeviceToHost));
   return n;
 }
 

@@ -161,6 +161,7 @@ int get_sample_impl();
 // or a SwiGLU pair (gate_i, up_i).
 enum { TILE_SEQ = 0, TILE_ROPE = 1, TILE_GLU = 2 };
 constexpr int MEGA_TILE_ELEMS = 4096;  // 16 x 256 bf16 = 8 KB
+constexpr int MEGA_DBG2_ROWS = 168;     // dev trace: rows 0..159 = local tiles of the traced layer, 160..164 = phase stamps
 struct MegaMat {
   const bf16* base;       // tiled copy, layer 0
   int64_t layer_stride;   // elements between layers
@@ -179,13 +180,18 @@ struct MegaArgs {
   bf16* kv;
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
   const float* rope_cs;
-  float *x, *q, *h, *part, *logits;                           // part: [grid][132] attention partials
-  float* attn;                                                // [heads*128] merged attention output
+  float* logits;
+  // tagged cross-CTA activation words {fp32 value, phase tag} (zero-initialised): xa[tg_H] xb[tg_H] q[heads*128]
+  // knew[kv_heads*128] vnew[kv_heads*128] attn[heads*128] h[tg_I] part[grid][132]
+  unsigned long long* tg;
+  int tg_H, tg_I;                                             // H and I padded to the 256-column tile (mega_configure)
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
-  unsigned long long *bar_count, *bar_base;                   // grid-barrier counter / epoch
+  unsigned long long *bar_count, *bar_base;                   // arrival counter; bar_base[0] = arrivals, [1] = tag epoch of past launches
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
+  long long* dbg2;                                            // optional: [grid][MEGA_DBG2_ROWS][4] clock64 per-tile trace of layer dbg_layer
+  int dbg_layer;
 };
 int mega_smem_bytes(const MegaArgs& a);
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out);

@@ -144,6 +144,35 @@ def pack_arena(cfg: "DetikzifyConfig", sd: Dict[str, torch.Tensor], ccfg: Option
     return arena
 
 
+def random_arena_device(cfg: "DetikzifyConfig", device, seed: int = 0, ccfg: Optional[DtkConfig] = None) -> torch.Tensor:
+    """Synthetic weights generated directly in the device arena (benches only: seconds instead of minutes for ds-7b).
+    Same distribution as ``weights.random_init`` (matrices/biases N(0, 0.02^2), norm gains 1 + N(0, 0.02^2)) but a
+    different random stream — parity tests use the CPU-seeded ``random_init`` + ``pack_arena``, which the oracle shares."""
+    lib = _lib.load_library()
+    ccfg = ccfg or to_c_config(cfg)
+    nbytes = lib.dtk_arena_bytes(C.byref(ccfg))
+    if nbytes == 0:
+        raise EngineError("invalid engine configuration (dtk_arena_bytes)")
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    arena = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
+    step = 1 << 28
+    for o in range(0, arena.numel(), step):            # chunked: the fp32 temporary stays at 1 GiB
+        n = min(step, arena.numel() - o)
+        arena[o:o + n] = (torch.randn(n, device=dev, dtype=torch.float32, generator=g) * 0.02).to(torch.bfloat16)
+    gains = ("norm1", "norm2", "ln1_w", "ln2_w", "ln_w", "post_w")
+    for info in weight_table(ccfg):
+        name = info.name.decode()
+        if name == "dec.norm" or name.split(".")[-1] in gains:
+            sl = arena[info.offset // 2: info.offset // 2 + info.rows * info.cols]
+            sl.copy_((sl.float() + 1.0).to(torch.bfloat16))
+        elif name == "vit.patch_w":                    # K padding columns (588 -> 640) must be zero
+            vc = cfg.vision_config
+            k = vc.num_channels * vc.patch_size * vc.patch_size
+            arena[info.offset // 2: info.offset // 2 + info.rows * info.cols].view(info.rows, info.cols)[:, k:] = 0
+    return arena
+
+
 class Engine:
     """One engine per CUDA device. Not thread-safe: one generation thread at a time."""
 

@@ -70,12 +70,15 @@ def build_processor(cfg: DetikzifyConfig, tokenizer=None) -> DetikzifyProcessor:
 def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bool = False, *,
          random_init_weights: Optional[bool] = None, seed: int = 0, state_dict: Optional[Dict[str, torch.Tensor]] = None,
          config: Optional[DetikzifyConfig] = None, max_seqs: int = 2, max_batch: int = 1, broadcast: bool = False,
-         prefix_slots: Optional[int] = None, **kwargs):
+         prefix_slots: Optional[int] = None, device_init: bool = False, **kwargs):
     """Returns ``(model, processor)``.
 
     ``max_seqs`` KV slots are preallocated (0.40 GB each for ds-1.3b at 2k context); ``generate()`` keeps a prefix cache
     over ``prefix_slots`` of them (default ``max_seqs - max_batch``, at least 1) — for MCTS use e.g. ``max_seqs=8``;
     ``generate_batch`` / ``sample_batch`` need ``max_batch`` (and as many free slots) >= the number of sequences.
+
+    ``device_init=True`` (benches): synthetic weights are generated directly on the device (``random_arena_device``)
+    instead of on the host — seconds instead of minutes for ds-7b; the values differ from the CPU-seeded init.
 
     ``broadcast=True`` (multi-GPU, one process per GPU): only rank 0 materialises the weights; the
     packed arena is sent with ONE ``torch.distributed.broadcast`` over NCCL.
@@ -96,7 +99,10 @@ def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bo
         import torch.distributed as dist
         rank0 = dist.get_rank() == 0
     arena = None
-    if rank0:
+    if rank0 and device_init and state_dict is None:
+        from ..engine import random_arena_device
+        arena = random_arena_device(cfg, device, seed=seed)
+    elif rank0:
         sd = state_dict
         if sd is None and isinstance(model_name_or_path, str) and os.path.isdir(model_name_or_path) \
                 and glob(os.path.join(model_name_or_path, "*.safetensors")):

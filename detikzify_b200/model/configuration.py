@@ -113,6 +113,13 @@ def preset(name: str) -> DetikzifyConfig:
     if key in ("detikzify-ds-7b", "ds-7b"):
         return DetikzifyConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
                                num_attention_heads=32, num_key_value_heads=32, name_or_path=name)
+    if key in ("detikzify-ds-7b-2l", "ds-7b-2l"):
+        # parity-test shape: every ds-7b matrix shape (H 4096, I 11008, 32 heads, V 32256) with two decoder layers and a
+        # small vision tower, so that the fp32 CPU oracle fits in memory and finishes in seconds
+        return DetikzifyConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=2,
+                               num_attention_heads=32, num_key_value_heads=32, name_or_path=name,
+                               vision_config=VisionConfig(hidden_size=144, intermediate_size=176, num_hidden_layers=2,
+                                                          num_attention_heads=2, image_size=56, patch_size=14))
     if key == "tiny":
         return DetikzifyConfig(
             hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,

@@ -60,3 +60,58 @@ def broadcast_arena(arena: torch.Tensor | None, nbytes: int, device: torch.devic
     if world() > 1:
         dist.broadcast(buf, src=src)
     return buf
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa(device_index: int) -> dict:
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off (one process per GPU: the thread that polls the
+    mapped token ring and feeds streamers then never crosses the socket interconnect). Best effort: returns what was done."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set(_parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return info
+
+
+def host_threads() -> dict:
+    """CPU threads this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota (a container
+    on a 64-core host may own 8 of them; sizing a thread pool by the host's core count oversubscribes 8x)."""
+    import math
+    import os
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt and txt[0] != "max":
+            quota = float(txt[0]) / float(txt[1])
+    except (OSError, ValueError, IndexError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    use = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return {"affinity": aff, "cgroup_quota": quota, "host_logical": os.cpu_count(), "use": use}

@@ -166,13 +166,13 @@ DTK_API uint64_t dtk_launch_count(const dtk_engine* eng);
 
 /* ---- kernel-level test hooks (used only by tests/: shape sweeps at the real model sizes
  *      without instantiating a model). All pointers are device pointers. --------------------- */
-/* dev microbenchmark: stream `bytes` of `buf` with one persistent CTA per SM. mode 0 = TMA bulk ring
- * (chunk bytes per copy, nslots slots, ncw consumer / npw producer warps), mode 1 = 128-bit LDG. */
-DTK_API int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int chunk, int nslots, int ncw,
-                                 int npw, int read_smem, int hint, int grid, float* sink, void* stream);
 /* phase timestamps of the last persistent-kernel launch (option "mega_debug" = 1):
  * [grid CTAs][5*layers+1 phases][4] globaltimer (ns) stamps; returns the value count */
 DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_values);
+/* per-tile SM-clock trace of one layer (options "mega_debug" = 1, "mega_trace_layer" = l): [grid CTAs][168 rows][4];
+ * rows 0..159 = the CTA's local tiles of that layer {producer issue, bytes landed, tile done, consumer asked},
+ * rows 160..164 = the layer's five phases {start, staged, items done, barrier done}; returns the value count */
+DTK_API int dtk_dbg_mega_trace(dtk_engine* eng, long long* out_host, int max_values);
 /* select the dense GEMM implementation used by dtk_dbg_gemm and the engines of this process:
  * 0 = mma.sync, 1 = tcgen05/TMEM where supported, -1 = query only; returns the current setting */
 DTK_API int dtk_dbg_gemm_impl(int impl);

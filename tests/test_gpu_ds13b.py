@@ -55,6 +55,18 @@ def test_ds13b_prefill_decode_and_2k_context():
         # (c) the 2k-context end: 2047 cached positions, decode the token at position 2047
         long_ids = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, 32000, (2048 - P,), generator=g)]).long()
         ref_long, _ = oracle.forward_logits(long_ids[None], pix)
+        # context checkpoints where the decode kernel's split-KV ranges change shape (attn_split rounding): prefill T
+        # tokens, decode the token at position T on both implementations, compare with the oracle's row T
+        for T in (512, 1024, 1536):
+            eng.prefill(slot, long_ids[:T].cuda(), 0, img, 0)
+            for impl in (1, 0):
+                eng.set_option("decode_impl", impl)
+                lgT = eng.decode([slot], [T], long_ids[T:T + 1].cuda())[0].cpu()
+                assert (lgT - ref_long[0, T]).abs().max() < TOL, (T, impl)
+                top2 = ref_long[0, T].topk(2).values
+                if (top2[0] - top2[1]) > 2 * TOL:
+                    assert int(lgT.argmax()) == int(ref_long[0, T].argmax())
+            eng.set_option("decode_impl", 1)
         lastp, _ = eng.prefill(slot, long_ids[:2047].cuda(), 0, img, 0)
         assert (lastp.cpu() - ref_long[0, 2046]).abs().max() < TOL
         lg = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()

@@ -1,0 +1,111 @@
+"""
+BASELINE.json configs[3]/[4] shapes: every detikzify-ds-7b matrix shape (H 4096, I 11008, 32 heads x 128, V 32256) with two
+decoder layers ("ds-7b-2l", so the fp32 CPU oracle fits and finishes in seconds) —
+  * prefill last-row logits,
+  * batch-1 decode on the persistent kernel and on the per-op kernels (teacher-forced),
+  * the batched-GEMM decode step every B >= 4 rollout step takes (skinny tcgen05 tile at K = 4096 / 11008), B = 32 ragged
+    contexts, two consecutive steps (the second reads the KV rows the first appended),
+  * the nucleus sampler's post-processor probability vector on those batched logits (T 0.8, top-p 0.95: configs[3]),
+all against oracle/hf_oracle.py. Tolerance: logits max-abs 3e-2 (bf16 operands, fp32 accumulation).
+"""
+import pytest
+import torch
+
+from conftest import engine_for, model_bundle
+
+pytestmark = pytest.mark.gpu
+NAME = "ds-7b-2l"
+TOL = 3e-2
+B = 32
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle.hf_oracle import synthetic_pixels
+    cfg, sd, oracle = model_bundle(NAME)
+    eng = engine_for(NAME, max_seqs=B + 2, max_batch=B)
+    pix = synthetic_pixels(1, cfg.vision_config.image_size)
+    img = eng.image_embeds(pix.cuda())[0]
+    g = torch.Generator().manual_seed(7000)
+    P = cfg.num_patches
+    prompts = []
+    for i in range(B):   # ragged contexts: 40 + 3 i tokens
+        text = torch.randint(0, 32000, (40 + 3 * i - P,), generator=g)
+        prompts.append(torch.cat([torch.full((P,), cfg.patch_token_id), text]).long())
+    tok1 = torch.randint(0, 32000, (B,), generator=g)
+    tok2 = torch.randint(0, 32000, (B,), generator=g)
+    return cfg, oracle, eng, pix, img, prompts, tok1, tok2
+
+
+def test_ds7b_prefill_and_batch1_decode(setup):
+    cfg, oracle, eng, pix, img, prompts, tok1, tok2 = setup
+    assert (cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.vocab_size) == (4096, 11008, 32, 32256)
+    ids = prompts[5]
+    T0, steps = ids.numel(), 6
+    ref_ids = oracle.generate(ids[None], pix, max_length=T0 + steps, stop_on_eos=False)[0]
+    ref_all, _ = oracle.forward_logits(ref_ids[None], pix)
+    slot = eng.seq_alloc()
+    try:
+        for impl in (1, 0):
+            eng.set_option("decode_impl", impl)
+            if impl == 1:
+                assert eng.get_option("decode_persistent") == 1
+            last, _ = eng.prefill(slot, ids.cuda(), 0, img, 0)
+            worst = (last.cpu() - ref_all[0, T0 - 1]).abs().max().item()
+            for t in range(T0, T0 + steps - 1):
+                lg = eng.decode([slot], [t], ref_ids[t:t + 1].cuda())[0].cpu()
+                worst = max(worst, (lg - ref_all[0, t]).abs().max().item())
+                top2 = ref_all[0, t].topk(2).values
+                if (top2[0] - top2[1]) > 2 * TOL:
+                    assert int(lg.argmax()) == int(ref_all[0, t].argmax())
+            assert worst < TOL, (impl, worst)
+    finally:
+        eng.set_option("decode_impl", 1)
+        eng.seq_free(slot)
+
+
+def test_ds7b_batched_gemm_decode_b32_and_nucleus(setup):
+    cfg, oracle, eng, pix, img, prompts, tok1, tok2 = setup
+    assert eng.get_option("decode_gemm_min_batch") == 4
+    slots = [eng.seq_alloc() for _ in range(B)]
+    try:
+        lens = []
+        for s, ids in zip(slots, prompts):
+            eng.prefill(s, ids.cuda(), 0, img, 0)
+            lens.append(ids.numel())
+        step1 = eng.decode(slots, lens, tok1.cuda()).clone()
+        step2 = eng.decode(slots, [n + 1 for n in lens], tok2.cuda()).clone()
+        torch.cuda.synchronize()
+        checked = (0, 1, 7, 13, 16, 22, 30, 31)
+        refs = {}
+        for i in checked:
+            full = torch.cat([prompts[i], tok1[i:i + 1], tok2[i:i + 1]])[None]
+            ref, _ = oracle.forward_logits(full, pix)
+            refs[i] = ref[0]
+            assert (step1[i].cpu() - ref[0, -2]).abs().max().item() < TOL, i
+            assert (step2[i].cpu() - ref[0, -1]).abs().max().item() < TOL, i
+        # all 32 rows against the per-sequence GEMV kernels (fp32 activations) as a second witness
+        eng.set_option("decode_gemm_min_batch", 0)
+        try:
+            again = eng.decode(slots, [n + 1 for n in lens], tok2.cuda())
+            assert (again - step2).abs().max().item() < TOL
+        finally:
+            eng.set_option("decode_gemm_min_batch", 4)
+        # configs[3] sampler settings on the batched logits: post-processor probability vector vs the HF processor chain
+        params = eng.sampling(temperature=0.8, top_p=0.95, do_sample=True, bad_token=cfg.image_token_id,
+                              begin_suppress_token=cfg.eos_token_id, seed=3)
+        out, probs = eng.sample(step2, params, suppress=[0] * B, steps=list(range(B)), seq_ids=list(range(B)), want_probs=True)
+        torch.cuda.synchronize()
+        for i in checked:
+            n = lens[i] + 2
+            ref_p = oracle.processed_probs(torch.zeros(1, n, dtype=torch.long), step2[i:i + 1].cpu(), lens[i],
+                                           temperature=0.8, top_p=0.95, top_k=0)[0]
+            got = probs[i].cpu()
+            mism = ((ref_p > 0) != (got > 0)).sum()
+            assert mism <= 1, (i, mism)
+            if mism == 0:
+                assert (got - ref_p).abs().max() < 1e-5
+            assert got[int(out[i])] > 0 and got[cfg.image_token_id] == 0
+    finally:
+        for s in slots:
+            eng.seq_free(s)

@@ -1,0 +1,124 @@
+"""
+Oracle-backed parity of the paths round 1 only checked against the engine itself ("parity holes"):
+  * image span in the MIDDLE of the prompt through dtk_prefill, against the logits the REFERENCE's own
+    DetikzifyForCausalLM produced (tests/golden/reference_v1_tiny.pt, detikzify/model/v1/modeling_detikzify.py:157-200);
+  * dtk_seq_fork and suffix prefill against oracle.forward_logits;
+  * ImageSim.get_similarity on the CUDA vision tower against oracle.selfsim_cos (detikzify/evaluate/imagesim.py:91-125).
+Tolerances as in test_gpu_model.py: logits max-abs 3e-2 (bf16 operand storage, fp32 accumulation).
+"""
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import engine_for, model_bundle
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-2
+GOLD = Path(__file__).parent / "golden" / "reference_v1_tiny.pt"
+
+
+def _pixels(cfg, batch, seed=1000):
+    from oracle.hf_oracle import synthetic_pixels
+    return synthetic_pixels(batch, cfg.vision_config.image_size, seed)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["persistent", "per-op"])
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_mid_prompt_image_span_matches_reference_logits(name, impl):
+    """The reference's forward on a prompt [text, 243-style image span, text] (golden: all-position logits + one cached
+    decode step). The engine splices the projector rows at img_start > 0 inside dtk_prefill."""
+    gold = torch.load(GOLD, weights_only=False)[name]
+    cfg, sd, oracle = model_bundle(name, seed=gold["seed"])
+    eng = engine_for(name, seed=gold["seed"])
+    ids = gold["input_ids"].long()
+    pix = _pixels(cfg, 1, seed=gold["pixel_seed"])
+    start = int((ids == cfg.image_token_id).nonzero()[0])
+    assert start > 0 and int((ids == cfg.image_token_id).sum()) == cfg.num_patches
+    img = eng.image_embeds(pix.cuda())[0]
+    slot = eng.seq_alloc()
+    eng.set_option("decode_impl", impl)
+    try:
+        last, alll = eng.prefill(slot, ids.cuda(), 0, img, start, want_all_logits=True)
+        assert (alll.cpu() - gold["logits"]).abs().max().item() < TOL
+        assert (last.cpu() - gold["logits"][-1]).abs().max().item() < TOL
+        lg = eng.decode([slot], [ids.numel()], torch.tensor([gold["next_id"]], device="cuda"))[0].cpu()
+        assert (lg - gold["decode_logits"]).abs().max().item() < TOL
+    finally:
+        eng.set_option("decode_impl", 1)
+        eng.seq_free(slot)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_fork_and_suffix_prefill_against_oracle(name):
+    """MCTS prefix reuse: prefill(prefix) -> fork -> prefill(suffix, start_pos) -> decode. Every logits row is compared
+    with the oracle's full forward of the same token sequence (not with the engine's own full prefill)."""
+    cfg, sd, oracle = model_bundle(name)
+    eng = engine_for(name)
+    pix = _pixels(cfg, 1)
+    g = torch.Generator().manual_seed(4000)
+    P = cfg.num_patches
+    text = torch.randint(0, min(cfg.vocab_size, cfg.patch_token_id), (30,), generator=g)
+    ids = torch.cat([torch.full((P,), cfg.patch_token_id), text]).long()
+    alt = ids.clone()
+    alt[P + 12:] = torch.randint(0, min(cfg.vocab_size, cfg.patch_token_id), (18,), generator=g)  # a sibling branch
+    ref_a, _ = oracle.forward_logits(ids[None], pix)
+    ref_b, _ = oracle.forward_logits(alt[None], pix)
+    img = eng.image_embeds(pix.cuda())[0]
+    a, b = eng.seq_alloc(), eng.seq_alloc()
+    try:
+        cut = P + 12
+        eng.prefill(a, ids[:cut].cuda(), 0, img, 0)
+        eng.seq_fork(a, b, cut)
+        # branch a: suffix prefill with all-position logits
+        last_a, all_a = eng.prefill(a, ids[cut:].cuda(), cut, None, 0, want_all_logits=True)
+        assert (all_a.cpu() - ref_a[0, cut:]).abs().max().item() < TOL
+        # branch b (forked copy of the prefix): its own suffix, then one decode step
+        last_b, _ = eng.prefill(b, alt[cut:-1].cuda(), cut, None, 0)
+        assert (last_b.cpu() - ref_b[0, -2]).abs().max().item() < TOL
+        lg = eng.decode([b], [alt.numel() - 1], alt[-1:].cuda())[0].cpu()
+        assert (lg - ref_b[0, -1]).abs().max().item() < TOL
+        # the fork did not disturb branch a
+        assert (last_a.cpu() - ref_a[0, -1]).abs().max().item() < TOL
+    finally:
+        eng.seq_free(a)
+        eng.seq_free(b)
+
+
+@pytest.mark.parametrize("mode", ["cos", "cos_avg"])
+def test_imagesim_on_cuda_tower_matches_oracle(mode):
+    """SelfSim reward through the public ImageSim object (PIL in, float out) on the CUDA vision tower vs the oracle's
+    fp64 cosine of HF-SigLIP features of the same preprocessed pixels (evaluate/imagesim.py:91-125)."""
+    import torch.nn.functional as F
+    from PIL import Image, ImageDraw
+    from detikzify_b200.evaluate.imagesim import ImageSim
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    from detikzify_b200.model import build_processor
+    from detikzify_b200.util.image import expand, load
+    name = "tiny2"
+    cfg, sd, oracle = model_bundle(name)
+    model = DetikzifyForCausalLM(cfg, engine=engine_for(name))
+    proc = build_processor(cfg)
+    ims = []
+    for k in range(2):
+        im = Image.new("RGB", (200, 160), "white")
+        d = ImageDraw.Draw(im)
+        for j in range(6):
+            d.line([(10 + 25 * j, 20 + 9 * k * j), (180 - 20 * j, 140 - 15 * k)], fill="black", width=2 + k)
+        d.ellipse([60, 40 + 30 * k, 140, 120], outline="black", width=3)
+        ims.append(im)
+    sim = ImageSim.from_detikzify(model, proc, mode=mode)
+    got = sim.get_similarity(ims[0], ims[1])
+    feats = []
+    for im in ims:
+        im = expand(load(im), max(im.size), do_trim=True)
+        pix = proc.image_processor(images=im, return_tensors="pt")["pixel_values"]
+        tok, pool = oracle.vision(pix)
+        feats.append(pool.squeeze() if mode == "cos" else tok.squeeze().mean(dim=0))
+    ref = F.cosine_similarity(feats[0].double(), feats[1].double(), dim=0).item()
+    assert abs(got - ref) < 5e-3, (got, ref)
+    assert abs(sim.get_similarity(ims[0], ims[0]) - 1.0) < 1e-6
+    if mode == "cos":
+        p0 = proc.image_processor(images=expand(load(ims[0]), max(ims[0].size), do_trim=True), return_tensors="pt")["pixel_values"]
+        p1 = proc.image_processor(images=expand(load(ims[1]), max(ims[1].size), do_trim=True), return_tensors="pt")["pixel_values"]
+        assert abs(oracle.selfsim_cos(p0, p1) - ref) < 1e-9

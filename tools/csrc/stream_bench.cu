@@ -1,8 +1,7 @@
-// Dev microbenchmark (test hook only): how fast can one persistent CTA per SM stream a large buffer from
+// Dev microbenchmark (NOT part of libdtk_b200.so: built by tools/stream_bench.py into tools/libdtk_dev.so): how fast can one persistent CTA per SM stream a large buffer from
 // HBM, (mode 0) with 1-D TMA bulk copies into a shared-memory ring, or (mode 1) with 128-bit LDG by all
 // warps? Used to size the ring / chunking of the persistent decode kernel. Not on the product path.
-#include "common.cuh"
-#include "../../include/detikzify_b200.h"
+#include "../../detikzify_b200/csrc/common.cuh"
 
 namespace dtk {
 namespace {
@@ -91,13 +90,13 @@ __global__ void __launch_bounds__(512, 1) stream_bench_kernel(const uint8_t* __r
 }  // namespace
 }  // namespace dtk
 
-extern "C" int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int chunk, int nslots, int ncw, int npw,
+extern "C" __attribute__((visibility("default"))) int dtk_dbg_stream_bench(const void* buf, uint64_t bytes, int mode, int chunk, int nslots, int ncw, int npw,
                                      int read_smem, int hint, int grid, float* sink, void* stream) {
   using namespace dtk;
-  if (chunk <= 0 || (chunk & 15) || nslots <= 0 || ncw <= 0 || npw < 0 || (ncw + npw) * 32 > 512) return DTK_ERR_INVALID;
-  if (mode == 0 && ((nslots % ncw) || (nslots % npw))) return DTK_ERR_INVALID;  // fixed slot ownership
+  if (chunk <= 0 || (chunk & 15) || nslots <= 0 || ncw <= 0 || npw < 0 || (ncw + npw) * 32 > 512) return -1;
+  if (mode == 0 && ((nslots % ncw) || (nslots % npw))) return -1;  // fixed slot ownership
   const int smem = mode == 0 ? nslots * chunk + 2 * nslots * 8 + 64 : 0;
-  if (cudaFuncSetAttribute(stream_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 1024 ? smem : 1024) != cudaSuccess) return DTK_ERR_CUDA;
+  if (cudaFuncSetAttribute(stream_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 1024 ? smem : 1024) != cudaSuccess) return -2;
   stream_bench_kernel<<<grid, (ncw + npw) * 32, smem, (cudaStream_t)stream>>>((const uint8_t*)buf, bytes, mode, chunk, nslots, ncw, npw, read_smem, hint, sink);
-  return cudaGetLastError() == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -59,3 +59,53 @@ for layer in range(L):
         cnt[int(d.argmax())] += 1
 print("CTAs most often last to finish a phase:", cnt.most_common(12))
 
+
+# ---- per-tile SM-clock trace of one layer: where does the weight stream stall?
+TL = L // 2
+eng.set_option("mega_trace_layer", TL)
+eng.decode([slot], [ctx], tok)
+ROWS = 168
+buf2 = (C.c_longlong * (G * ROWS * 4))()
+got = eng.lib.dtk_dbg_mega_trace(eng._h, buf2, G * ROWS * 4)
+tr = torch.tensor(list(buf2[:got]), dtype=torch.float64).view(-1, ROWS, 4)
+import os
+os.makedirs("gpurun_out", exist_ok=True)
+torch.save({"trace": tr, "phases": t, "layer": TL}, "gpurun_out/mega_trace.pt")
+MHZ = 1965.0
+ntile = [24, 8, 40, 22] if "1.3b" in name else None
+print(f"\nper-tile trace of layer {TL} (us, SM clock at {MHZ:.0f} MHz, relative to the CTA's own layer start stamp)")
+print("columns per tile: issue(producer) landed asked done | landed-issue")
+for cta in (0, 1, 50, 100, 147):
+    d = tr[cta]
+    t0c = d[160, 0]
+    ph = (d[160:165] - t0c) / MHZ
+    print(f"CTA {cta}: phase stamps start/staged/done/bar: " + " | ".join(" ".join(f"{v:6.2f}" for v in ph[i]) for i in range(5)))
+    rows = [(i, d[i]) for i in range(160) if d[i, 1] > 0]
+    for i, r in rows:
+        v = (r - t0c) / MHZ
+        print(f"   tile {i:3d}: issue {v[0]:7.2f} landed {v[1]:7.2f} asked {v[3]:7.2f} done {v[2]:7.2f} | fetch {v[1]-v[0]:6.2f} proc {v[2]-v[1]:5.2f}")
+# aggregate: fetch latency distribution, and how many of a phase's tiles had landed before the phase was staged
+lat = []
+ready = collections.defaultdict(list)
+for cta in range(tr.shape[0]):
+    d = tr[cta]
+    rows = [i for i in range(160) if d[i, 1] > 0]
+    if not rows:
+        continue
+    for i in rows:
+        if d[i, 0] > 0:
+            lat.append(((d[i, 1] - d[i, 0]) / MHZ).item())
+    # phase boundaries by consumer order: tiles are consumed in index order; assign phase by 'asked' time vs stamps
+    for phi, stamp_row in ((0, 160), (2, 162), (3, 163), (4, 164)):
+        staged = d[stamp_row, 1]
+        nxt = d[stamp_row, 3]
+        mine = [i for i in rows if d[i, 3] >= d[stamp_row, 0] and d[i, 3] <= nxt]
+        if mine:
+            # a tile was "already in the ring" if its issue time precedes the staged stamp by > 1 us
+            ready[phi].append((sum(1 for i in mine if d[i, 0] > 0 and d[i, 0] < staged - 1.0 * MHZ), len(mine)))
+lat = torch.tensor(lat)
+print(f"fetch latency (issue -> consumer saw it), all CTAs: median {lat.median():.2f} us, p10 {lat.quantile(0.1):.2f}, p90 {lat.quantile(0.9):.2f}, max {lat.max():.2f}")
+for phi, nm in ((0, "qkv"), (2, "o"), (3, "gu"), (4, "down")):
+    if ready[phi]:
+        a = torch.tensor(ready[phi], dtype=torch.float64)
+        print(f"  {nm:5s}: tiles per CTA {a[:,1].mean():5.1f}; issued >1us before the phase was staged: {a[:,0].mean():5.1f}")
