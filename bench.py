@@ -15,12 +15,18 @@ up to a total length of 2048 (1805 new tokens). One "step" = one such figure.
   roofline = algorithmic HBM bytes of the decode steps (weights once per token + KV read at the running
            context; dtk_decode_bytes) / CUDA-event time of the decode region, vs MEASURED_PEAKS.json.
   cpu_baseline = the oracle (HF Llama+SigLIP wired like the reference; oracle/hf_oracle.py) on the host cores,
-           bounded sample.
+           bounded sample, through stock HF ``generate`` (BASELINE.md section 2 protocol).
+  ds7b     = BASELINE.json configs[3]/[4] shape as extra keys (detikzify-ds-7b random-init): batch-1 decode roofline, and
+           figure-sharded rollouts (8 figures per rank, 32 nucleus-sampled rollouts per figure forked off one prefilled
+           prompt, results gathered once) — tokens/s over all ranks, max-over-ranks device time.
 
 ``--impl reference`` times that CPU path alone (the reference package itself is pure Python glue over
-HF modules and does not import offline).
+HF modules and does not import offline): HF ``generate(do_sample=False, max_new_tokens=n)`` incl. ViT
+and the 243-token prefill, fp32 and bf16 probed in the warm-up, thread count = scheduler affinity capped by the cgroup
+quota.
 Multi-GPU: figures are independent -> one engine per rank, ONE NCCL broadcast of the weight arena at
-load, no per-step collective; scaling is weak (one figure per GPU per step).
+load, no per-step collective; scaling is weak (one figure per GPU per step); every rank is pinned to the NUMA node of
+its GPU.
 """
 from __future__ import annotations
 
@@ -47,7 +53,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="nllg/detikzify-ds-1.3b")
     ap.add_argument("--total-len", type=int, default=2048)
-    ap.add_argument("--cpu-tokens", type=int, default=32, help="decode tokens of the bounded CPU sample")
+    ap.add_argument("--cpu-tokens", type=int, default=64, help="new tokens of the bounded CPU sample inside our arm")
+    ap.add_argument("--ref-tokens", type=int, default=256, help="new tokens per step of --impl reference (BASELINE.md: 256)")
+    ap.add_argument("--no-7b", action="store_true", help="skip the ds-7b (configs[3]/[4]) block")
+    ap.add_argument("--figures-per-rank", type=int, default=8)
+    ap.add_argument("--rollouts", type=int, default=32)
+    ap.add_argument("--rollout-tokens", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vit-sweep", action="store_true")
@@ -122,61 +133,122 @@ def ncu_traffic(kernel: str):
 
 
 # ---------------------------------------------------------------------------------- CPU reference arm
-def cpu_decode_tokens_per_s(model_name: str, n_tokens: int, steps: int = 1, warmup: int = 0):
-    """Oracle on host cores: ViT + 243-token prefill + n_tokens greedy KV-cached decode steps (fp32 eager).
-    Returns (tok/s over the timed steps, seconds per step, cores)."""
-    from detikzify_b200.model.configuration import preset
-    from detikzify_b200.model.weights import random_init
-    from oracle.hf_oracle import Oracle, synthetic_pixels
-    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
-    try:
-        import psutil
-        phys = psutil.cpu_count(logical=False) or os.cpu_count() or 1
-    except Exception:
-        phys = os.cpu_count() or 1
-    torch.set_num_threads(max(torch.get_num_threads(), int(os.environ.get("DTK_CPU_THREADS", phys))))
-    cfg = preset(model_name)
-    sd = random_init(cfg, seed=0)
-    oracle = Oracle(cfg.to_dict(), sd)
-    del sd
-    pix = synthetic_pixels(1, cfg.vision_config.image_size)
-    ids = torch.full((1, cfg.num_patches), cfg.patch_token_id, dtype=torch.long)
-    cores = torch.get_num_threads()
+def synthetic_pixels(batch: int, image_size: int, seed: int = 1000) -> torch.Tensor:
+    """pixel_values = 2*U[0,1)-1 (range of the (x-0.5)/0.5 normalisation), SURVEY.md section 8d."""
+    out = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed + i)
+        out.append(2 * torch.rand(3, image_size, image_size, generator=g) - 1)
+    return torch.stack(out)
 
-    def one():
+
+class _Stamps:
+    """HF streamer protocol: records when the prompt and every new token reach the host."""
+
+    def __init__(self):
+        self.t = []
+
+    def put(self, value):
+        self.t.append(time.perf_counter())
+
+    def end(self):
+        pass
+
+
+class CpuArm:
+    """The reference's HF CPU path as closely as this container allows (oracle/hf_oracle.py: stock HF Llama + SigLIP wired
+    like detikzify/model/v1/modeling_detikzify.py). One step = one figure through stock ``GenerationMixin.generate``
+    (greedy, n new tokens) incl. ViT + projector + 243-token prefill; decode tokens/s is taken between the first and the
+    last new token as seen by a streamer (prefill excluded, as on the GPU arm's ``value``)."""
+
+    def __init__(self, model_name: str):
+        from detikzify_b200.model.configuration import preset
+        from detikzify_b200.model.weights import random_init
+        from detikzify_b200.parallel import host_threads
+        self.threads = host_threads()
+        # all usable host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+        torch.set_num_threads(int(os.environ.get("DTK_CPU_THREADS", self.threads["use"])))
+        self.cores = torch.get_num_threads()
+        self.cfg = preset(model_name)
+        self.sd = random_init(self.cfg, seed=0)
+        self.oracles = {}
+        self.pix = synthetic_pixels(1, self.cfg.vision_config.image_size)
+        self.ids = torch.full((1, self.cfg.num_patches), self.cfg.patch_token_id, dtype=torch.long)
+
+    def oracle(self, dtype):
+        from oracle.hf_oracle import Oracle
+        if dtype not in self.oracles:
+            self.oracles[dtype] = Oracle(self.cfg.to_dict(), self.sd, dtype=dtype)
+        return self.oracles[dtype]
+
+    def figure(self, dtype, n_new: int):
+        """-> dict(total_s, vit_s, prefill_s, decode_tok_s)"""
+        o = self.oracle(dtype)
+        P = self.cfg.num_patches
+        st = _Stamps()
         t0 = time.perf_counter()
-        logits, cache = oracle.forward_logits(ids, pix, use_cache=True)
-        nxt = logits[:, -1].argmax(-1, keepdim=True)
+        img = o.image_embeds(self.pix)
         t1 = time.perf_counter()
-        for _ in range(n_tokens):
-            logits, cache = oracle.decode_logits(nxt, cache)
-            nxt = logits[:, -1].argmax(-1, keepdim=True)
+        embeds = o.spliced_embeds(self.ids, img)
+        with torch.no_grad():
+            out = o.llm.generate(input_ids=self.ids, inputs_embeds=embeds, bad_words_ids=[[o.image_token_id]],
+                                 max_length=P + n_new, min_length=P + n_new, do_sample=False, streamer=st,
+                                 pad_token_id=self.cfg.pad_token_id)
         t2 = time.perf_counter()
-        return t2 - t1, t1 - t0
+        new = [t for t in st.t if t > t1]
+        # st.t[0] is the prompt (or absent with inputs_embeds); new tokens follow
+        first, last = new[-n_new], new[-1]
+        assert out.shape[1] >= n_new
+        return {"total_s": t2 - t0, "vit_s": t1 - t0, "prefill_s": first - t1, "decode_tok_s": (n_new - 1) / max(last - first, 1e-9)}
 
-    for _ in range(warmup):
-        one()
-    dec, pre = 0.0, 0.0
-    for _ in range(steps):
-        d, p = one()
-        dec += d; pre += p
-    return n_tokens * steps / dec, dec / steps, pre / steps, cores
+
+def cpu_reference(model_name: str, n_new: int, steps: int, warmup: int, probe_tokens: int = 12):
+    """Bounded CPU sample. The warm-up probes fp32 and bf16 (reference scripts load bf16; fp32 is often faster on CPU) and
+    the faster dtype runs the timed steps. Returns (summary dict for the JSON line, CpuArm)."""
+    arm = CpuArm(model_name)
+    probe = {}
+    for dt in (torch.float32, torch.bfloat16):
+        try:
+            probe[str(dt).split(".")[-1]] = arm.figure(dt, probe_tokens)
+        except Exception as e:  # a dtype the CPU kernels do not support
+            probe[str(dt).split(".")[-1]] = {"error": repr(e)[:120]}
+    ok = {k: v for k, v in probe.items() if "decode_tok_s" in v}
+    best = max(ok, key=lambda k: ok[k]["decode_tok_s"])
+    dtype = getattr(torch, best)
+    # keep one step near 40 s at most
+    n = max(16, min(n_new, int(40.0 * ok[best]["decode_tok_s"])))
+    for _ in range(max(0, warmup - 1)):
+        arm.figure(dtype, n)
+    runs = [arm.figure(dtype, n) for _ in range(steps)]
+    tps = [r["decode_tok_s"] for r in runs]
+    mean = sum(tps) / len(tps)
+    sd = (sum((x - mean) ** 2 for x in tps) / len(tps)) ** 0.5
+    return {
+        "value": mean, "stdev": sd, "dtype": best, "new_tokens": n, "runs": runs, "probe": probe,
+        "cores": arm.cores, "threads": arm.threads,
+        "sec_per_step": sum(r["total_s"] for r in runs) / len(runs),
+    }, arm
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = min(args.cpu_tokens, 16)
-    tps, sec, pre, cores = cpu_decode_tokens_per_s(args.model, n, steps=args.steps, warmup=min(args.warmup, 1))
-    sample = f"per step: 1 figure, ViT+243-token prefill ({pre:.2f}s, untimed) then {n} greedy KV-cached decode tokens at ctx 243..{243 + n}, fp32 HF eager"
+    r, arm = cpu_reference(args.model, args.ref_tokens, steps=args.steps, warmup=max(1, args.warmup))
+    P = arm.cfg.num_patches
+    sample = (f"per step: 1 figure through stock HF generate(do_sample=False): ViT ({r['runs'][0]['vit_s']:.2f}s) + {P}-token prefill "
+              f"({r['runs'][0]['prefill_s']:.2f}s) + {r['new_tokens']} greedy tokens at ctx {P}..{P + r['new_tokens']}, {r['dtype']} weights, "
+              f"{r['cores']} threads (affinity {r['threads']['affinity']}, cgroup quota {r['threads']['cgroup_quota']}, host {r['threads']['host_logical']}); "
+              f"value = decode tokens/s between first and last new token, mean of {args.steps} steps (stdev {r['stdev']:.2f}); "
+              f"probe fp32 {r['probe'].get('float32', {}).get('decode_tok_s', 'n/a')} / bf16 {r['probe'].get('bfloat16', {}).get('decode_tok_s', 'n/a')} tok/s")
     line = {
-        "impl": "reference", "metric": "TikZ tokens/sec/GPU (decode, 384px cond, 2k ctx)", "value": tps, "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} random-init, 1x384px synthetic figure, batch-1 greedy decode (bounded CPU sample)"},
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "TikZ tokens/sec/GPU (decode, 384px cond, 2k ctx)", "value": r["value"], "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if r["dtype"] == "float32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} random-init, 1x384px synthetic figure, batch-1 greedy generate (bounded CPU sample)"},
+        "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                         "stdev": r["stdev"], "vit_s": r["runs"][0]["vit_s"], "prefill_s": r["runs"][0]["prefill_s"]},
+        "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -193,7 +265,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     from detikzify_b200.model import load
-    from oracle.hf_oracle import synthetic_pixels  # input generator only (seeded uniform pixels)
+    from detikzify_b200.parallel import gather_results, pin_to_gpu_numa, shard
+    numa = pin_to_gpu_numa(local)
 
     model, processor = load(args.model, device_map=local, torch_dtype=torch.bfloat16, broadcast=world > 1, seed=0)
     cfg, eng = model.config, model.engine
@@ -303,11 +376,104 @@ def run_ours(args):
                 del pix_b
         barrier()
 
+    # ---- BASELINE.json configs[3] / configs[4] shape: detikzify-ds-7b, figures striped over the ranks, 32 nucleus-sampled
+    # rollouts per figure forked off one prefilled 243-token image prompt. Extra keys; the headline stays configs[1].
+    ds7b = None
+    t7 = torch.zeros(3, dtype=torch.float64)
+    if not args.no_7b:
+        eng.seq_free(slot)
+        del model, eng
+        torch.cuda.empty_cache()
+        R, F, NT7 = args.rollouts, args.figures_per_rank, args.rollout_tokens
+        name7 = "nllg/detikzify-ds-7b"
+        model7, _ = load(name7, device_map=local, torch_dtype=torch.bfloat16, broadcast=world > 1, seed=0, device_init=True,
+                         max_seqs=R + 1, max_batch=R)
+        e7, c7 = model7.engine, model7.config
+        P7 = c7.num_patches
+        figures = shard(list(range(F * world)), rank, world)           # global figure indices of this rank (striped)
+        pix7 = torch.cat([synthetic_pixels(1, c7.vision_config.image_size, seed=5000 + g) for g in figures]).to(dev)
+        ids7 = torch.full((P7,), c7.patch_token_id, dtype=torch.int64, device=dev)
+        slots7 = [e7.seq_alloc() for _ in range(R)]
+        nuc = e7.sampling(temperature=0.8, top_p=0.95, do_sample=True, bad_token=c7.image_token_id, begin_suppress_token=-1, seed=3)
+        grd = e7.sampling(do_sample=False, bad_token=c7.image_token_id, begin_suppress_token=-1)
+        with torch.cuda.stream(stream):
+            # (a) batch-1 decode at ctx 512 on the persistent kernel
+            ctx7 = 512
+            warm_ids = torch.randint(0, 30000, (ctx7,), generator=torch.Generator().manual_seed(1)).to(dev)
+            e7.prefill(slots7[0], warm_ids, 0, None, 0)
+            tok1 = torch.tensor([5], device=dev)
+            for _ in range(3):
+                e7.decode([slots7[0]], [ctx7], tok1)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(10):
+                e7.decode([slots7[0]], [ctx7], tok1)
+            a1.record(stream)
+            stream.synchronize()
+            b1_ms = a0.elapsed_time(a1) / 10
+
+            def figure7(fi: int):
+                """ViT + projector + prefill of figure fi, fork to R rollouts, NT7 sampled tokens each -> [R] last tokens"""
+                img = e7.image_embeds(pix7[fi:fi + 1])[0]
+                last, _ = e7.prefill(slots7[0], ids7, 0, img, 0)
+                for sl in slots7[1:]:
+                    e7.seq_fork(slots7[0], sl, P7)
+                first, _ = e7.sample(last[None].expand(R, -1).contiguous(), nuc, suppress=[0] * R, steps=[0] * R, seq_ids=list(range(R)))
+                e7.gen_begin(slots7, [P7] * R, [int(t) for t in first.tolist()], nuc, list(range(R)))
+                for _ in range(NT7 - 1):
+                    e7.gen_step()
+                out = e7.gen_wait(NT7 - 2)
+                e7.gen_end()
+                return out
+
+            figure7(0)                                                    # warm-up (graph capture)
+            barrier()
+            l0 = e7.launch_count
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            local_out = [figure7(fi) for fi in range(len(figures))]
+            g1.record(stream)
+            barrier()
+            roll_s = g0.elapsed_time(g1) / 1e3
+            launches7 = e7.launch_count - l0
+        gathered = gather_results([(g, o[:4]) for g, o in zip(figures, local_out)])   # one gather at the end (examples/eval.py:132)
+        t7 = torch.tensor([b1_ms, roll_s, float(len(gathered))], dtype=torch.float64)
+        kvb = e7.decode_bytes(1) - e7.decode_bytes(0)
+        ds7b_local = {"decode_bytes_ctx512": e7.decode_bytes(ctx7), "weights_bytes": e7.decode_bytes(0), "kv_bytes_per_pos": kvb,
+                      "launches": int(launches7), "persistent": e7.get_option("decode_persistent") == 1}
+        for sl in slots7:
+            e7.seq_free(sl)
+    barrier()
+
     # max over ranks
-    vals = torch.tensor([t_all, t_dec, e2e_t or 0.0], device=dev, dtype=torch.float64)
+    vals = torch.tensor([t_all, t_dec, e2e_t or 0.0, float(t7[0]), float(t7[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    t_all, t_dec, e2e_t = vals.tolist()
+    t_all, t_dec, e2e_t, b1_ms7, roll_s7 = vals.tolist()
+    if rank == 0 and not args.no_7b:
+        R, F, NT7 = args.rollouts, args.figures_per_rank, args.rollout_tokens
+        peak7, _src = peaks()
+        d = ds7b_local
+        # rollouts: bytes per decode step = weights once + the KV every rollout reads (private copies today) and the
+        # UNIQUE KV bytes (shared 243-token prefix counted once) that an ideal prefix-sharing cache would read
+        steps7 = NT7 - 1
+        kv_priv = sum(R * (243 + 1 + i) * d["kv_bytes_per_pos"] for i in range(steps7))
+        kv_uniq = sum((243 + R * (1 + i)) * d["kv_bytes_per_pos"] for i in range(steps7))
+        ds7b = {
+            "model": "nllg/detikzify-ds-7b random-init bf16 (device-side init)",
+            "b1_decode": {"ctx": 512, "ms_per_token": b1_ms7, "achieved_gbs": d["decode_bytes_ctx512"] / (b1_ms7 * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": d["decode_bytes_ctx512"] / (b1_ms7 * 1e-3) / 1e9 / peak7, "persistent_kernel": d["persistent"],
+                          "note": "max over ranks, CUDA events, 10 tokens after 3 warm-up"},
+            "rollouts": {"figures_per_rank": F, "figures_total": int(t7[2]) if world == 1 else F * world, "rollouts_per_figure": R, "new_tokens": NT7,
+                         "sampling": "temperature 0.8, top-p 0.95", "seconds": roll_s7,
+                         "tokens_per_s": world * F * R * NT7 / roll_s7, "ms_per_figure": roll_s7 / F * 1e3,
+                         "includes": "ViT + projector + 243-token prefill + fork to 32 KV slots + decode, per figure; max over ranks",
+                         "roofline_unique_kv": {"bytes_per_figure": d["weights_bytes"] * steps7 + kv_uniq,
+                                                "frac_of_hbm_peak": F * (d["weights_bytes"] * steps7 + kv_uniq) / roll_s7 / 1e9 / peak7},
+                         "roofline_private_kv": {"bytes_per_figure": d["weights_bytes"] * steps7 + kv_priv,
+                                                 "frac_of_hbm_peak": F * (d["weights_bytes"] * steps7 + kv_priv) / roll_s7 / 1e9 / peak7},
+                         "gpu_launches": d["launches"]},
+        }
 
     if rank == 0:
         new_per_step = n_new
@@ -354,13 +520,16 @@ def run_ours(args):
         if e2e_t:
             line["e2e"] = {"value": world * args.steps * new_per_step / e2e_t, "unit": "tokens/s",
                            "h2d_bytes_per_step": int(pix_host.numel() * 4 + P * 8), "d2h_bytes_per_step": int(new_per_step * 4)}
+        if ds7b:
+            line["ds7b"] = ds7b
+        line["host"] = {"numa": numa}
         if not args.no_cpu_baseline and world == 1:
-            tps, sec, pre, cores = cpu_decode_tokens_per_s(args.model, args.cpu_tokens)
-            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port",
-                                    "sample": f"1 figure: ViT+243-token prefill ({pre:.2f}s, untimed) then {args.cpu_tokens} greedy KV-cached decode tokens "
-                                              f"at ctx 243..{243 + args.cpu_tokens} ({sec:.2f}s), fp32 HF eager on {cores} threads"}
+            r, _ = cpu_reference(args.model, args.cpu_tokens, steps=1, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                                    "sample": f"1 figure through stock HF generate: ViT ({r['runs'][0]['vit_s']:.2f}s) + {P}-token prefill ({r['runs'][0]['prefill_s']:.2f}s) + "
+                                              f"{r['new_tokens']} greedy tokens at ctx {P}..{P + r['new_tokens']}, {r['dtype']} weights on {r['cores']} threads "
+                                              f"(affinity {r['threads']['affinity']}, cgroup quota {r['threads']['cgroup_quota']}); decode tokens/s between first and last new token"}
         print(json.dumps(line), flush=True)
-    eng.seq_free(slot)
     if world > 1:
         dist.destroy_process_group()
 

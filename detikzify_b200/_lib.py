@@ -17,6 +17,7 @@ class DtkConfig(C.Structure):
         ("hidden", C.c_int32), ("inter", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
         ("kv_heads", C.c_int32), ("head_dim", C.c_int32), ("vocab", C.c_int32), ("max_len", C.c_int32),
         ("rms_eps", C.c_float), ("rope_theta", C.c_float), ("rope_factor", C.c_float),
+        ("rope_type", C.c_int32), ("rope_low_freq", C.c_float), ("rope_high_freq", C.c_float), ("rope_orig_max_pos", C.c_int32),
         ("v_hidden", C.c_int32), ("v_inter", C.c_int32), ("v_layers", C.c_int32), ("v_heads", C.c_int32),
         ("v_image", C.c_int32), ("v_patch", C.c_int32), ("v_act", C.c_int32), ("v_eps", C.c_float),
         ("concat", C.c_int32), ("image_token_id", C.c_int32), ("eos_token_id", C.c_int32),
@@ -95,7 +96,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dtk_abi_version() != 1:
+    if lib.dtk_abi_version() != 2:
         raise RuntimeError("libdtk_b200.so ABI version mismatch")
     _lib = lib
     return lib

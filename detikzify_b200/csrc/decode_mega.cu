@@ -58,23 +58,31 @@ DTK_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 DTK_DEV void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
-DTK_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
+DTK_DEV uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// slow path of a wait, out of line (the hot loop stays small): bounded spin, trap instead of hanging the GPU
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
   long long t0 = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (++spins & 1023u) == 0) {
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > SPIN_CYCLES) __trap();
     }
   }
+}
+DTK_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 DTK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
@@ -85,33 +93,46 @@ DTK_DEV void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_T
 
 // ------------------------------------------------------------------ tagged activation words
 // Every activation value that crosses CTAs (residual stream, q, the new key/value row, attention partials and output,
-// the SwiGLU vector) travels as ONE 8-byte word {fp32 value, 32-bit phase tag} written with st.relaxed.gpu and read with
-// ld.relaxed.gpu: aligned 8-byte accesses are single-copy atomic, so a reader that sees the expected tag also sees the
-// value written with it — no release fence on the producer side and no acquire on the consumer side (the release fence
-// alone cost ~0.8 us of every phase: 0.919 -> 0.821 ms per token when it was dropped). The grid barrier below is
-// therefore only a HINT that says when polling is worthwhile; correctness rests on the tags. A buffer is overwritten one
-// layer later, after a chain of data dependencies that runs through every CTA which read it (write-after-read safe).
+// the SwiGLU vector) travels as ONE 8-byte word {fp32 value, 32-bit phase tag}: aligned 8-byte accesses are single-copy
+// atomic, so a reader that sees the expected tag also sees the value written with it — no release fence on the
+// producer side (it cost ~0.8 us of every phase) and no acquire on the consumer side. Writers use st.relaxed.gpu.
+// Readers first try a WEAK coalesced load (ld.cg: may be served by the SM's own L2 partition) and only re-read with
+// ld.relaxed.gpu the words whose tag is still old — a stale copy is harmless because it carries a stale tag.
+// The grid-wide counter below is therefore only a HINT that says when reading is worthwhile; correctness rests on the
+// tags. A buffer is overwritten one layer later, after a chain of data dependencies that runs through every CTA which
+// read it (write-after-read safe).
 typedef unsigned long long u64;
 DTK_DEV void st_tag(u64* p, float v, uint32_t tag) {
   const u64 w = ((u64)tag << 32) | (u64)__float_as_uint(v);
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(w) : "memory");
 }
-DTK_DEV ulonglong2 ld_tag2(const u64* p) {
+DTK_DEV ulonglong2 ld_strong2(const u64* p) {
   ulonglong2 r;
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
   return r;
 }
-DTK_DEV u64 ld_tag1(const u64* p) {
+DTK_DEV ulonglong2 ld_weak2(const u64* p) {
+  ulonglong2 r;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];\n" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+  return r;
+}
+DTK_DEV u64 ld_strong1(const u64* p) {
   u64 r;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(r) : "l"(p) : "memory");
   return r;
 }
+DTK_DEV u64 ld_weak1(const u64* p) {
+  u64 r;
+  asm volatile("ld.global.cg.u64 %0, [%1];\n" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
 DTK_DEV bool tag_ok(u64 w, uint32_t tag) { return (uint32_t)(w >> 32) == tag; }
 DTK_DEV float tag_val(u64 w) { return __uint_as_float((uint32_t)w); }
-struct Spin {   // bounded polling: trap instead of hanging the GPU
+struct Spin {   // bounded polling with a short back-off: trap instead of hanging the GPU
   uint32_t n = 0;
   long long t0 = 0;
   DTK_DEV void tick() {
+    __nanosleep(32);
     if ((++n & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -119,28 +140,29 @@ struct Spin {   // bounded polling: trap instead of hanging the GPU
     }
   }
 };
-// N consecutive tagged words (N even, 16-byte aligned) -> values; polls until every tag matches
-template <int N>
-DTK_DEV void ld_tagged(const u64* p, uint32_t tag, bool nowait, float (&out)[N]) {
-  ulonglong2 w[N / 2];
-#pragma unroll
-  for (int i = 0; i < N / 2; ++i) w[i] = ld_tag2(p + 2 * i);
+// make a (weakly loaded) pair valid: re-read with coherent loads until both tags match (slow path out of line)
+__device__ __noinline__ ulonglong2 poll2(const u64* p, uint32_t tag) {
   Spin sp;
   for (;;) {
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i)
-      if (!(tag_ok(w[i].x, tag) && tag_ok(w[i].y, tag))) { ok = false; w[i] = ld_tag2(p + 2 * i); }
-    if (ok || nowait) break;
+    const ulonglong2 w = ld_strong2(p);
+    if (tag_ok(w.x, tag) && tag_ok(w.y, tag)) return w;
     sp.tick();
   }
-#pragma unroll
-  for (int i = 0; i < N / 2; ++i) { out[2 * i] = tag_val(w[i].x); out[2 * i + 1] = tag_val(w[i].y); }
 }
-DTK_DEV float ld_tagged1(const u64* p, uint32_t tag, bool nowait) {
-  u64 w = ld_tag1(p);
+__device__ __noinline__ u64 poll1(const u64* p, uint32_t tag) {
   Spin sp;
-  while (!tag_ok(w, tag) && !nowait) { sp.tick(); w = ld_tag1(p); }
+  for (;;) {
+    const u64 w = ld_strong1(p);
+    if (tag_ok(w, tag)) return w;
+    sp.tick();
+  }
+}
+DTK_DEV float2 settle2(ulonglong2 w, const u64* p, uint32_t tag, bool nowait) {
+  if (!(tag_ok(w.x, tag) && tag_ok(w.y, tag)) && !nowait) w = poll2(p, tag);
+  return make_float2(tag_val(w.x), tag_val(w.y));
+}
+DTK_DEV float settle1(u64 w, const u64* p, uint32_t tag, bool nowait) {
+  if (!tag_ok(w, tag) && !nowait) w = poll1(p, tag);
   return tag_val(w);
 }
 
@@ -207,92 +229,79 @@ DTK_DEV float consumer_sum(float v, float* red) {
 // The source is a tagged global vector (or, for layer 0, the bf16 embedding row). With norm_w the staged vector is
 // x * w (RMSNorm gain) WITHOUT the 1/rms factor: the GEMV is linear, so the consumers multiply their results by the
 // returned r = rsqrt(mean(x^2) + eps) in the epilogue — the reduction is off the critical path of the staging.
-// One thread handles half a k-step: elements [16S + 4a, +4) and [16S + 8 + 4a, +4) = entries t = 2a, 2a + 1.
-DTK_DEV float stage_vec(const u64* src, uint32_t tag, bool nowait, const bf16* src_bf16, int K, int Kp, const bf16* norm_w,
-                        float eps, uint4* xb, float* red) {
-  const int tid = threadIdx.x, nhalf = Kp >> 3;
-  constexpr int MAXH = 4;  // half k-steps per thread (K <= 8192)
-  float v[MAXH][8];
+// Pass 1: coalesced 16-byte loads (one tagged pair per lane) -> fp32 vector in shared memory; pass 2: one thread per
+// k-step converts its 64 bytes in place (the fp32 k-step and its four B entries occupy the same bytes).
+// Deliberately NOT inlined: one copy keeps the whole per-token loop inside the 32 KB instruction cache.
+__device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int nowait, const bf16* src_bf16, int K, int Kp,
+                                        const bf16* norm_w, float eps, float* xs, float* red) {
+  const int tid = threadIdx.x;
+  // norm gains of this thread's first k-step: requested before the vector so that both L2 round trips overlap
+  uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
+  if (norm_w && tid * 16 < K) {
+    g0 = *reinterpret_cast<const uint4*>(norm_w + tid * 16);
+    if (tid * 16 + 8 < K) g1 = *reinterpret_cast<const uint4*>(norm_w + tid * 16 + 8);
+  }
   if (src) {
-    ulonglong2 w[MAXH][4];
+    const int npair = K >> 1;
+    float2* xs2 = reinterpret_cast<float2*>(xs);
+    for (int p0 = 0; p0 < npair; p0 += 4 * CONSUMER_THREADS) {
+      ulonglong2 w[4];
 #pragma unroll
-    for (int u = 0; u < MAXH; ++u) {
-      const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
-      w[u][0] = w[u][1] = w[u][2] = w[u][3] = make_ulonglong2(0ull, 0ull);
-      if (hs < nhalf && k0 < K) { w[u][0] = ld_tag2(src + k0); w[u][1] = ld_tag2(src + k0 + 2); }
-      if (hs < nhalf && k0 + 8 < K) { w[u][2] = ld_tag2(src + k0 + 8); w[u][3] = ld_tag2(src + k0 + 10); }
-    }
-    Spin sp;
-    for (;;) {
-      bool ok = true;
-#pragma unroll
-      for (int u = 0; u < MAXH; ++u) {
-        const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
-        if (hs < nhalf) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (k0 + (i >> 1) * 8 < K && !(tag_ok(w[u][i].x, tag) && tag_ok(w[u][i].y, tag))) {
-              ok = false;
-              w[u][i] = ld_tag2(src + k0 + (i >> 1) * 8 + (i & 1) * 2);
-            }
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int pi = p0 + u * CONSUMER_THREADS + tid;
+        if (pi < npair) w[u] = ld_weak2(src + 2 * pi);
       }
-      if (ok || nowait) break;
-      sp.tick();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pi = p0 + u * CONSUMER_THREADS + tid;
+        if (pi < npair) xs2[pi] = settle2(w[u], src + 2 * pi, tag, nowait != 0);
+      }
     }
-#pragma unroll
-    for (int u = 0; u < MAXH; ++u)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { v[u][2 * i] = tag_val(w[u][i].x); v[u][2 * i + 1] = tag_val(w[u][i].y); }
   } else {
-#pragma unroll
-    for (int u = 0; u < MAXH; ++u) {
-      const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-      if (hs < nhalf && k0 < K) {
-        const uint2 a = *reinterpret_cast<const uint2*>(src_bf16 + k0);
-        const uint2 b = (k0 + 8 < K) ? *reinterpret_cast<const uint2*>(src_bf16 + k0 + 8) : make_uint2(0u, 0u);
-        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y);
-        v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a1.x; v[u][3] = a1.y;
-        v[u][4] = b0.x; v[u][5] = b0.y; v[u][6] = b1.x; v[u][7] = b1.y;
-      }
+    for (int e = tid * 8; e < K; e += CONSUMER_THREADS * 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(src_bf16 + e), f);
+      *reinterpret_cast<float4*>(xs + e) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(xs + e + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
   }
+  for (int e = K + tid; e < Kp; e += CONSUMER_THREADS) xs[e] = 0.f;
+  consumer_sync();
   float ss = 0.f;
+  uint4* xb = reinterpret_cast<uint4*>(xs);
+  for (int S = tid; S < (Kp >> 4); S += CONSUMER_THREADS) {
+    float y[16];
 #pragma unroll
-  for (int u = 0; u < MAXH; ++u) {
-    const int hs = tid + u * CONSUMER_THREADS, k0 = (hs >> 1) * 16 + (hs & 1) * 4;
-    if (hs < nhalf) {
-      uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0, 0, 0);
-      if (k0 < K) {
-        float y[8];
-        if (norm_w) {
-          const uint2 wa = *reinterpret_cast<const uint2*>(norm_w + k0);
-          const uint2 wb = (k0 + 8 < K) ? *reinterpret_cast<const uint2*>(norm_w + k0 + 8) : make_uint2(0u, 0u);
-          const float2 a0 = unpack_bf16x2(wa.x), a1 = unpack_bf16x2(wa.y), b0 = unpack_bf16x2(wb.x), b1 = unpack_bf16x2(wb.y);
-          const float g[8] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { ss += v[u][i] * v[u][i]; y[i] = v[u][i] * g[i]; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = v[u][i];
-        }
-        uint32_t hi[4], lo[4];   // pairs (0,1) (2,3) of the low quad, (4,5) (6,7) of the high quad
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = y[2 * j], b = y[2 * j + 1];
-          const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-          hi[j] = pack_bf16x2(ah, bh);
-          lo[j] = pack_bf16x2(a - ah, b - bh);
-        }
-        e0 = make_uint4(hi[0], hi[2], lo[0], lo[2]);   // entry t = 2a   : elements k0, k0+1 | k0+8, k0+9
-        e1 = make_uint4(hi[1], hi[3], lo[1], lo[3]);   // entry t = 2a+1 : elements k0+2, k0+3 | k0+10, k0+11
-      }
-      const int S = hs >> 1, a2 = (hs & 1) * 2;
-      xb[S * 4 + a2] = e0;
-      xb[S * 4 + a2 + 1] = e1;
+    for (int i = 0; i < 4; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + S * 16 + i * 4);
+      y[4 * i] = a.x; y[4 * i + 1] = a.y; y[4 * i + 2] = a.z; y[4 * i + 3] = a.w;
     }
+    if (norm_w) {
+      if (S != tid) {   // later k-steps of this thread (K > 4096): gains fetched here
+        g0 = g1 = make_uint4(0, 0, 0, 0);
+        if (S * 16 < K) g0 = *reinterpret_cast<const uint4*>(norm_w + S * 16);
+        if (S * 16 + 8 < K) g1 = *reinterpret_cast<const uint4*>(norm_w + S * 16 + 8);
+      }
+      float g[16];
+      { float t8[8]; unpack8(g0, t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = t8[i];
+        unpack8(g1, t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[8 + i] = t8[i]; }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { ss += y[i] * y[i]; y[i] *= g[i]; }
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = y[2 * j], b = y[2 * j + 1];
+      const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+      hi[j] = pack_bf16x2(ah, bh);
+      lo[j] = pack_bf16x2(a - ah, b - bh);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
   }
   float r = 1.f;
   if (norm_w) r = rsqrtf(consumer_sum(ss, red) / K + eps);
@@ -300,7 +309,11 @@ DTK_DEV float stage_vec(const u64* src, uint32_t tag, bool nowait, const bf16* s
   return r;
 }
 
-// DBG = true: dev instrumentation (phase stamps, per-tile trace, timing-experiment flags) compiled in
+// DBG = true: dev instrumentation (phase stamps, per-tile trace, timing-experiment flags) compiled in.
+// Both roles run ONE rolled loop over the 5 L + 1 phases of the token (qkv | attention | o | gate/up | down per layer,
+// then lm_head) with a single copy of the tile code and a run-time phase switch in the epilogue: the per-token
+// instruction footprint of a warp stays inside the SM's 32 KB instruction cache (the fully specialised version was
+// ~160 KB, re-fetched from L2 every layer: the first tiles of every phase ran 3-6x slower than the steady state).
 template <bool DBG>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -316,6 +329,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   float* tpart = rope_s + 128;                                // [NT][16] per-tile partial sums
   int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] tiles finished per group
   float* rbuf = reinterpret_cast<float*>(gcnt + NG);          // [NG][16] residuals prefetched at a group's first tile
+  float* qkn = rbuf + NG * 16;                                // [3][128] q | new key | new value of the CTA's head
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -337,6 +351,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
   const bf16* kv_slot = p.kv + (int64_t)slot * p.kv_slot_stride;
+  const int nphase = 5 * p.L + 1;
 
   // ---- item ownership. The CTA's local TILE sequence (all phases, in order) is dealt to agents by index:
   // local tile n -> ring slot n % nslots, producer warp n % NPW, consumer warp n % NCW (nslots is a multiple of
@@ -347,8 +362,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     uint32_t rot = 0;    // rotation of the participating CTA set
   };
   // A weight phase with `groups` 16-row groups is cut into equal blocks of per = ceil(groups / G) groups; only
-  // ceil(groups / per) CTAs take part (same amount of work each, so they reach the barrier together), the others
-  // idle for that phase. The participating set rotates from phase to phase.
+  // ceil(groups / per) CTAs take part (same amount of work each, so they finish together), the others idle for that
+  // phase. The participating set rotates from phase to phase.
   auto phase_span = [&](const Walk& w, int groups, int& g0, int& cnt, int& nact) {
     const int per = (groups + G - 1) / G;
     nact = (groups + per - 1) / per;
@@ -356,6 +371,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     g0 = ci * per;
     cnt = (ci < nact) ? min(per, groups - g0) : 0;
   };
+  // phase it -> (layer, kind, matrix index into p.mat)
+  auto mat_of = [](int ph) { return ph == PH_QKV ? 0 : ph == PH_O ? 1 : ph == PH_GU ? 2 : ph == PH_DOWN ? 3 : 4; };
 
   if (warp >= NCW) {
     // =============================================================== PRODUCERS
@@ -363,73 +380,60 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       Walk w;
-      // visit own tiles j = j0, j0 + NPW, ... of a phase with `ntiles` local tiles (tpg tiles per group)
-      auto for_own = [&](int ntiles, int tpg, auto&& issue) {
+      long long* tr = nullptr;   // dev trace: row (local tile index within the traced layer), column 0 = issue clock
+      uint32_t tr_nb0 = 0;
+      int l = 0, ph = 0;
+      for (int it = 0; it < nphase; ++it) {
+        if (it == nphase - 1) { ph = PH_LM; l = 0; }
+        if (DBG && ph == 0) {
+          tr = (p.dbg2 && l == p.dbg_layer && it != nphase - 1) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
+          if (tr) tr_nb0 = w.nb;
+        }
+        // this phase's local tile list: weight tiles of the CTA's row groups, or (attention) the CTA's share of the
+        // cached keys / values of the layer: item i = positions [j0 + 16 i, +16) of the CTA's kv head, K rows at slot
+        // offset 0 and V rows at 4096 (rows of one head are contiguous in the cache). Neither depends on this token, so
+        // both stream ahead of the dependency chain and the phases read shared memory only.
+        const bool attn = ph == PH_ATTN;
+        const MegaMat& m = p.mat[mat_of(ph)];
+        int g0 = 0, cnt = 0, nact = 0;
+        if (!attn) phase_span(w, m.groups, g0, cnt, nact);
+        const int tpg = attn ? 1 : m.tpg;
+        const int ntiles = attn ? as.n_items : cnt * tpg;
+        const bf16* base = attn ? kv_slot + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128
+                                : m.base + (int64_t)l * m.layer_stride + (int64_t)g0 * tpg * MEGA_TILE_ELEMS;
+        // own tiles j = j0, j0 + NPW, ...
         uint32_t j = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
         if ((int)j < ntiles) {
           const uint32_t n0 = w.nb + j;
           uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
-          uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
           for (; (int)j < ntiles; j += NPW) {
             if (use > 0) mbar_wait(empty0 + 8 * sl, (use - 1) & 1);
-            issue((int)k, (int)ks, ring_u32 + sl * TILE_BYTES, full0 + 8 * sl);
+            const uint32_t dst = ring_u32 + sl * TILE_BYTES, fb = full0 + 8 * sl;
+            if (attn) {
+              const int key0 = as.j0 + (int)j * 16;
+              const uint32_t bytes = (uint32_t)min(16, p.max_len - key0) * 256u;
+              mbar_expect_tx(fb, 2 * bytes);
+              bulk_g2s(dst, base + (int64_t)key0 * 128, bytes, fb);
+              bulk_g2s(dst + 4096, base + p.kv_v_offset + (int64_t)key0 * 128, bytes, fb);
+            } else {
+              mbar_expect_tx(fb, TILE_BYTES);
+              bulk_g2s(dst, base + (int64_t)j * MEGA_TILE_ELEMS, TILE_BYTES, fb);
+            }
+            if (DBG && tr) {
+              const uint32_t row = w.nb + j - tr_nb0;
+              if (row < 160u) tr[row * 4] = clock64();
+            }
             sl += NPW;
             if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
-            ks += NPW;
-            while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
           }
         }
         w.nb += ntiles;
-      };
-      long long* tr = nullptr;   // dev trace: row (local tile index within the traced layer), column 0 = issue clock
-      uint32_t tr_nb0 = 0;
-      auto stream_phase = [&](const MegaMat& m, int layer) {
-        int g0, cnt, nact;
-        phase_span(w, m.groups, g0, cnt, nact);
-        const bf16* base = m.base + (int64_t)layer * m.layer_stride;
-        const uint32_t nbp = w.nb;
-        for_own(cnt * m.tpg, m.tpg, [&](int k, int ks, uint32_t dst, uint32_t fb) {
-          mbar_expect_tx(fb, TILE_BYTES);
-          bulk_g2s(dst, base + ((int64_t)(g0 + k) * m.tpg + ks) * MEGA_TILE_ELEMS, TILE_BYTES, fb);
-          if (DBG && tr) {
-            const uint32_t row = nbp + (uint32_t)(k * m.tpg + ks) - tr_nb0;
-            if (row < 160u) tr[row * 4] = clock64();
-          }
-        });
-        w.gb += cnt;
-        w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
-      };
-      // the CTA's share of the cached keys / values of this layer: item i = positions [j0 + 16 i, +16) of the CTA's
-      // kv head, K rows at slot offset 0 and V rows at 4096 (rows of one head are contiguous in the cache). They do
-      // not depend on this token, so they stream ahead like weights and the attention phase reads shared memory only.
-      auto stream_attn = [&](int layer) {
-        const bf16* kb = kv_slot + (int64_t)layer * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
-        const uint32_t nbp = w.nb;
-        for_own(as.n_items, 1, [&](int k, int, uint32_t dst, uint32_t fb) {
-          const int key0 = as.j0 + k * 16;
-          const uint32_t bytes = (uint32_t)min(16, p.max_len - key0) * 256u;
-          mbar_expect_tx(fb, 2 * bytes);
-          bulk_g2s(dst, kb + (int64_t)key0 * 128, bytes, fb);
-          bulk_g2s(dst + 4096, kb + p.kv_v_offset + (int64_t)key0 * 128, bytes, fb);
-          if (DBG && tr) {
-            const uint32_t row = nbp + (uint32_t)k - tr_nb0;
-            if (row < 160u) tr[row * 4] = clock64();
-          }
-        });
-      };
-      for (int l = 0; l < p.L; ++l) {
-        if (DBG) {
-          tr = (p.dbg2 && l == p.dbg_layer) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
-          if (tr) tr_nb0 = w.nb;
+        if (!attn) {
+          w.gb += cnt;
+          w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
         }
-        stream_phase(p.qkv, l);
-        stream_attn(l);
-        stream_phase(p.o, l);
-        stream_phase(p.gu, l);
-        stream_phase(p.down, l);
+        if (++ph == 5) { ph = 0; ++l; }
       }
-      tr = nullptr;
-      stream_phase(p.lm, 0);
     }
     return;
   }
@@ -439,60 +443,29 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const int dflags = DBG ? p.dbg_flags : 0;
   const bool nowait = (dflags & 2) != 0;
   unsigned long long bar_target = p.bar_base[0];   // arrivals counted before this launch
-  const uint32_t epoch = (uint32_t)p.bar_base[1];  // tag of (layer l, phase ph) = epoch + 5 l + ph + 1
+  const uint32_t epoch = (uint32_t)p.bar_base[1];  // tag of phase it = epoch + it + 1
   Walk w;
-  // visit own tiles of a phase; body(j, k, ks, smem address of the slot) runs after the bytes landed and must
-  // finish READING the slot before calling release()
   uint32_t cur_slot = 0;
-  long long* ctr = nullptr;   // dev trace of one layer (see MegaArgs::dbg2)
-  uint32_t ctr_nb0 = 0;
-  auto release = [&]() {
+  auto release = [&]() {   // hand the ring slot back: every lane's shared-memory reads of it are issued, the arrive is ordered after them
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * cur_slot);
   };
-  auto for_own = [&](int ntiles, int tpg, auto&& body) {
-    uint32_t j = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
-    if ((int)j < ntiles) {
-      const uint32_t n0 = w.nb + j;
-      uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
-      uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-      for (; (int)j < ntiles; j += NCW) {
-        long long* trow = nullptr;
-        if (DBG && ctr) {
-          const uint32_t row = w.nb + j - ctr_nb0;
-          if (row < 160u) trow = ctr + row * 4;
-        }
-        if (DBG && trow && lane == 0) trow[3] = clock64();
-        mbar_wait(full0 + 8 * sl, use & 1);
-        if (DBG && trow && lane == 0) trow[1] = clock64();
-        cur_slot = sl;
-        body((int)j, (int)k, (int)ks, sl);
-        if (DBG && trow && lane == 0) trow[2] = clock64();
-        sl += NCW;
-        if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
-        ks += NCW;
-        while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
-      }
-    }
-    w.nb += ntiles;
-  };
-
   // optional phase timestamps (globaltimer ns, comparable across SMs): [CTA][phase][4] = {start, staged, items done, barrier done}
-  long long* dbg = (DBG && p.dbg) ? p.dbg + (int64_t)c * (p.L * 5 + 1) * 4 : nullptr;
-  int dbg_i = 0;
-  int ctr_ph = 0;
+  long long* dbg = (DBG && p.dbg) ? p.dbg + (int64_t)c * nphase * 4 : nullptr;
+  long long* ctr = nullptr;   // dev trace of one layer (see MegaArgs::dbg2)
+  uint32_t ctr_nb0 = 0;
+  int it = 0, l = 0, ph = 0;
   auto stamp = [&](int k) {
     if (!DBG) return;
     if (dbg && tid == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-      dbg[dbg_i * 4 + k] = (long long)t;
+      dbg[it * 4 + k] = (long long)t;
     }
-    if (ctr && tid == 0 && ctr_ph < 5) ctr[(160 + ctr_ph) * 4 + k] = clock64();
-    if (ctr && k == 3) ++ctr_ph;
+    if (ctr && tid == 0 && ph < 5) ctr[(160 + ph) * 4 + k] = clock64();
   };
 
-  // tagged cross-CTA vectors (MegaArgs::tg): residual stream after attention (xa) / after the MLP (xb2), q, the new
+  // tagged cross-CTA vectors (MegaArgs::tg): residual stream after attention (xa) / after the MLP (xb), q, the new
   // key and value rows, merged attention output, SwiGLU vector, per-CTA attention partials
   u64* const t_xa = p.tg;
   u64* const t_xb = t_xa + p.tg_H;
@@ -503,344 +476,361 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   u64* const t_h = t_att + qd;
   u64* const t_part = t_h + p.tg_I;
 
-  // one weight phase: every tile = 16 k-steps of (ldmatrix.x4, mma); the B fragments of the k-tile are loaded BEFORE the
-  // tile's ldmatrix, so that the first mma can issue as soon as its own A fragment has landed (shared-memory returns are in order: with the B loads queued behind
-  // the sixteen ldmatrix the tensor pipe used to idle until the whole tile had been read). The warp that finishes a
-  // group's last tile sums the group's partials in k order and runs the epilogue for its 16 rows; rn = 1/rms of the
-  // staged vector (RMSNorm folded into the epilogue, see stage_vec).
-  auto run_phase = [&](const MegaMat& m, int ph, int layer, float rn, uint32_t tag) {
-    int g0, cnt, nact;
-    phase_span(w, m.groups, g0, cnt, nact);
-    const uint32_t nb0 = w.nb, gb0 = w.gb;
-    const int tpg = m.tpg;
-    // residual source of the O / DOWN epilogues: previous value of the row in the other residual buffer
-    const u64* res_src = (ph == PH_O) ? t_xb : t_xa;
-    const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
-    for_own(cnt * tpg, tpg, [&](int j, int k, int ks, uint32_t sl) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
-        // B operand: even columns of the 16 x 8 B tile carry the hi part of x, odd columns the lo part (column = lane >> 2),
-        // so ONE mma per k-step yields W.hi in accumulator column 0 and W.lo in column 1. Two independent chains
-        // (k-step parity) hide the HMMA latency.
-        const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
-        uint2 b[16];
-#pragma unroll
-        for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
-        float c1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t a[16][4];
-#pragma unroll
-        for (int s = 0; s < 16; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-        release();   // every lane's shared-memory reads of the slot are issued; the arrive is ordered after them
-        if (!(dflags & 1)) {
-#pragma unroll
-          for (int s = 0; s < 16; s += 2) {
-            mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
-            mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
-          }
-        }
-        // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
-        acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
-        acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
-      }
-
-      const uint32_t gslot = (gb0 + (uint32_t)k) % NG;
-      if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
-        // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
-        // critical path of the group's epilogue (the value was published two or more phases ago)
-        const int row = (g0 + k) * 16 + lane;
-        float bres = 0.f;
-        if (row < p.H)
-          bres = (ph == PH_O && layer == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row]) : ld_tagged1(res_src + row, res_tag, nowait);
-        rbuf[gslot * 16 + lane] = bres;
-      }
-      const uint32_t n = nb0 + (uint32_t)j;
-      if ((lane & 3) == 0) {
-        float* tp = tpart + (n % NT) * 16;
-        tp[lane >> 2] = acc[0];
-        tp[(lane >> 2) + 8] = acc[2];
-      }
-      __syncwarp();
-      int last = 0;
-      if (lane == 0) {
-        __threadfence_block();
-        last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (!last) return;
-      __threadfence_block();
-      // ---- group epilogue (this warp saw the last tile of group k)
-      const uint32_t n0 = nb0 + (uint32_t)k * tpg;
-      float v = 0.f;
-      if (lane < 16)
-        for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
-      const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
-      if (lane == 0) gcnt[gslot] = 0;
-      if (lane >= 8) return;
-      const int gi = g0 + k, r = lane;
-      if (ph == PH_QKV) {
-        const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
-        const int row0 = hb * 128 + i;
-        const float a0 = v * rn, a1 = v1 * rn;
-        if (row0 < qd + kd) {
-          const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-          const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
-          if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
-          else {
-            const int kh = (row0 - qd) >> 7;
-            bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-            const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
-            dd[i] = z0;
-            dd[i + 64] = z1;
-            st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
-            st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-          }
-        } else {
-          const int kh = (row0 - qd - kd) >> 7;
-          bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)layer * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-          const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
-          dd[i] = z0;
-          dd[i + 64] = z1;
-          st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
-          st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-        }
-      } else if (ph == PH_O || ph == PH_DOWN) {
-        u64* dst = (ph == PH_O) ? t_xa : t_xb;
-        const int r0 = gi * 16 + r, r1 = r0 + 8;
-        const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
-        if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
-        if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
-      } else if (ph == PH_GU) {
-        const int i = gi * 8 + r;
-        if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
-      } else {
-        const int r0 = gi * 16 + r, r1 = r0 + 8;
-        if (r0 < p.V) p.logits[r0] = v * rn;
-        if (r1 < p.V) p.logits[r1] = v1 * rn;
-      }
-    });
-    w.gb += cnt;
-    w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
-  };
-  // does this CTA own row groups of the matrix in the phase that starts at walk state w? (idle CTAs skip the staging)
-  auto has_work = [&](const MegaMat& m) {
-    int g0, cnt, nact;
-    phase_span(w, m.groups, g0, cnt, nact);
-    return cnt > 0;
-  };
-
-  const int Hp = p.qkv.tpg * 256, Qp = p.o.tpg * 256, Ip = p.down.tpg * 256;
-  for (int l = 0; l < p.L; ++l) {
-    const int64_t no = (int64_t)l * p.norm_stride;
-    const uint32_t tag0 = epoch + (uint32_t)l * 5u + 1u;   // tag of this layer's phase ph = tag0 + ph
-    if (DBG) {
-      ctr = (p.dbg2 && l == p.dbg_layer) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
-      ctr_nb0 = w.nb; ctr_ph = 0;
+  for (it = 0; it < nphase; ++it) {
+    if (it == nphase - 1) { ph = PH_LM; l = 0; }
+    const uint32_t tag = epoch + (uint32_t)it + 1u;   // tags of this phase's outputs; its inputs carry tag - 1
+    if (DBG && ph == 0) {
+      ctr = (p.dbg2 && l == p.dbg_layer && it != nphase - 1) ? p.dbg2 + (int64_t)c * MEGA_DBG2_ROWS * 4 : nullptr;
+      ctr_nb0 = w.nb;
     }
-    // ---------------- P1: RMSNorm + qkv + RoPE + KV write  (input: embedding row / previous layer's xb)
     stamp(0);
-    float rn = 1.f;
-    if (has_work(p.qkv))
-      rn = stage_vec(l == 0 ? nullptr : t_xb, tag0 - 1, nowait, p.embed + (int64_t)tok * p.H, p.H, Hp, p.norm1_0 + no, p.eps, xb, red);
-    stamp(1);
-    run_phase(p.qkv, PH_QKV, l, rn, tag0 + PH_QKV);
-    stamp(2);
-    stamp(3); ++dbg_i;
-
-    // ---------------- P2: attention over this CTA's key range of its head. No grid-wide wait in front of it: the cached
-    // keys/values arrive through the ring, and q / the new key and value are polled as tagged words of this head only.
-    stamp(0);
-    if (as.active) {
-      const int hw = lane >> 4, l16 = lane & 15;
-      const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
-      float q[8];
-      ld_tagged<8>(t_q + as.head * 128 + l16 * 8, tag0 + PH_QKV, nowait, q);
+    if (ph == PH_ATTN) {
+      // ---------------- attention over this CTA's key range of its head. No grid-wide wait in front of it: the cached
+      // keys/values arrive through the ring, and q / the new key and value are polled (by one warp) as tagged words of
+      // this head only.
+      if (as.active) {
+        const int hw = lane >> 4, l16 = lane & 15;
+        if (warp == 0) {
+          const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
+          float2* q2 = reinterpret_cast<float2*>(qkn);
+          const u64* qsrc = t_q + as.head * 128;
+          ulonglong2 wq[2], wk[2], wv[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] *= sl2;
-      stamp(1);
-      float m = -INFINITY, lsum = 0.f, o[8];
+          for (int u = 0; u < 2; ++u) wq[u] = ld_weak2(qsrc + 2 * (lane + 32 * u));
+          if (as.last) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = 0.f;
-      auto key_update = [&](const float (&kf)[8], const float (&vf)[8], bool valid) {
-        float s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-        if (valid) {
-          const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
-          lsum = lsum * alpha + pj;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * vf[i];
-          m = mn;
-        }
-      };
-      // ring items: 16 positions each; half-warp hw takes positions hw, hw + 2, ... of the item
-      for_own(as.n_items, 1, [&](int j, int, int, uint32_t sl) {
-        const uint32_t base = ring_u32 + sl * TILE_BYTES + l16 * 16;
-        const int key0 = as.j0 + j * 16;
-        uint4 kr[8], vr[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t a = base + (uint32_t)(u * 2 + hw) * 256u;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(kr[u].x), "=r"(kr[u].y), "=r"(kr[u].z), "=r"(kr[u].w) : "r"(a));
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(vr[u].x), "=r"(vr[u].y), "=r"(vr[u].z), "=r"(vr[u].w) : "r"(a + 4096u));
-        }
-        release();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float kf[8], vf[8];
-          unpack8(kr[u], kf);
-          unpack8(vr[u], vf);
-          key_update(kf, vf, key0 + u * 2 + hw < as.j1);
-        }
-      });
-      if (as.last && warp == 0) {   // the key / value of the token being decoded (published by P1 of this launch)
-        float kf[8], vf[8];
-        ld_tagged<8>(t_kn + kvh * 128 + l16 * 8, tag0 + PH_QKV, nowait, kf);
-        ld_tagged<8>(t_vn + kvh * 128 + l16 * 8, tag0 + PH_QKV, nowait, vf);
-        key_update(kf, vf, hw == 0);
-      }
-      // merge the 16 half-warp states -> one partial per CTA (the scratch aliases the staged qkv input: slower warps of
-      // this CTA may still be reading it for their last P1 tiles, there is no CTA-wide sync between P1 and P2)
-      consumer_sync();
-      float* sm_m = actf;            // [16]
-      float* sm_l = actf + 16;       // [16]
-      float* sm_o = actf + 32;       // [16][128]
-      const int hidx = warp * 2 + hw;
-      if (l16 == 0) { sm_m[hidx] = m; sm_l[hidx] = lsum; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sm_o[hidx * 128 + l16 * 8 + i] = o[i];
-      consumer_sync();
-      const uint32_t ptag = tag0 + PH_ATTN;
-      if (tid < 128) {
-        float M = -INFINITY;
-#pragma unroll
-        for (int h = 0; h < 16; ++h) M = fmaxf(M, sm_m[h]);
-        float Lt = 0.f, O = 0.f;
-#pragma unroll
-        for (int h = 0; h < 16; ++h) {
-          const float wgt = (sm_m[h] == -INFINITY) ? 0.f : exp2f(sm_m[h] - M);
-          Lt += sm_l[h] * wgt;
-          O += sm_o[h * 128 + tid] * wgt;
-        }
-        u64* pp = t_part + (int64_t)c * 132;
-        st_tag(pp + tid, O, ptag);
-        if (tid == 0) { st_tag(pp + 128, M, ptag); st_tag(pp + 129, Lt, ptag); }
-      }
-      // the LAST CTA of this head to get here merges the head's partials into the normalised output (the partials are
-      // tagged, so the arrival counter needs no release / acquire)
-      consumer_sync();
-      if (tid == 0) {
-        unsigned prev;
-        asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
-        red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
-      }
-      consumer_sync();
-      if (red[8] != 0.f) {
-        if (tid < 128) {
-          // partials of the head's CTAs in batches of RB (all loads of a batch are independent: one L2 round trip),
-          // folded into a running (max, sum, output) in CTA order
-          constexpr int RB = 10;
-          float M = -INFINITY, Lt = 0.f, O = 0.f;
-          for (int rb = 0; rb < as.cph; rb += RB) {
-            u64 wm[RB], wl[RB], wo[RB];
-#pragma unroll
-            for (int r = 0; r < RB; ++r) {
-              const u64* pp = t_part + (int64_t)((rb + r) * p.heads + as.head) * 132;
-              if (rb + r < as.cph) { wm[r] = ld_tag1(pp + 128); wl[r] = ld_tag1(pp + 129); wo[r] = ld_tag1(pp + tid); }
+            for (int u = 0; u < 2; ++u) {
+              wk[u] = ld_weak2(t_kn + kvh * 128 + 2 * (lane + 32 * u));
+              wv[u] = ld_weak2(t_vn + kvh * 128 + 2 * (lane + 32 * u));
             }
-            Spin sp;
-            for (;;) {
-              bool ok = true;
+          }
 #pragma unroll
-              for (int r = 0; r < RB; ++r) {
-                if (rb + r < as.cph) {
-                  const u64* pp = t_part + (int64_t)((rb + r) * p.heads + as.head) * 132;
-                  if (!tag_ok(wm[r], ptag)) { ok = false; wm[r] = ld_tag1(pp + 128); }
-                  if (!tag_ok(wl[r], ptag)) { ok = false; wl[r] = ld_tag1(pp + 129); }
-                  if (!tag_ok(wo[r], ptag)) { ok = false; wo[r] = ld_tag1(pp + tid); }
+          for (int u = 0; u < 2; ++u) {
+            const float2 v = settle2(wq[u], qsrc + 2 * (lane + 32 * u), tag - 1, nowait);
+            q2[lane + 32 * u] = make_float2(v.x * sl2, v.y * sl2);
+          }
+          if (as.last) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              q2[64 + lane + 32 * u] = settle2(wk[u], t_kn + kvh * 128 + 2 * (lane + 32 * u), tag - 1, nowait);
+              q2[128 + lane + 32 * u] = settle2(wv[u], t_vn + kvh * 128 + 2 * (lane + 32 * u), tag - 1, nowait);
+            }
+          }
+        }
+        consumer_sync();   // q is staged; every warp is past its last qkv tile (the merge scratch below aliases the staged vector)
+        stamp(1);
+        float q[8];
+        {
+          const float4 a = *reinterpret_cast<const float4*>(qkn + l16 * 8), b = *reinterpret_cast<const float4*>(qkn + l16 * 8 + 4);
+          q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+        }
+        float m = -INFINITY, lsum = 0.f, o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        auto key_update = [&](const float (&kf)[8], const float (&vf)[8], bool valid) {
+          float s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          if (valid) {
+            const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
+            lsum = lsum * alpha + pj;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * vf[i];
+            m = mn;
+          }
+        };
+        // ring items: 16 positions each; half-warp hw takes positions hw, hw + 2, ... of the item
+        {
+          uint32_t j = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
+          if ((int)j < as.n_items) {
+            const uint32_t n0 = w.nb + j;
+            uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
+            for (; (int)j < as.n_items; j += NCW) {
+              long long* trow = nullptr;
+              if (DBG && ctr) {
+                const uint32_t row = w.nb + j - ctr_nb0;
+                if (row < 160u) trow = ctr + row * 4;
+              }
+              if (DBG && trow && lane == 0) trow[3] = clock64();
+              mbar_wait(full0 + 8 * sl, use & 1);
+              if (DBG && trow && lane == 0) trow[1] = clock64();
+              cur_slot = sl;
+              const uint32_t base = ring_u32 + sl * TILE_BYTES + l16 * 16;
+              const int key0 = as.j0 + (int)j * 16;
+              uint4 kr[8], vr[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t a = base + (uint32_t)(u * 2 + hw) * 256u;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(kr[u].x), "=r"(kr[u].y), "=r"(kr[u].z), "=r"(kr[u].w) : "r"(a));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(vr[u].x), "=r"(vr[u].y), "=r"(vr[u].z), "=r"(vr[u].w) : "r"(a + 4096u));
+              }
+              release();
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                float kf[8], vf[8];
+                unpack8(kr[u], kf);
+                unpack8(vr[u], vf);
+                key_update(kf, vf, key0 + u * 2 + hw < as.j1);
+              }
+              if (DBG && trow && lane == 0) trow[2] = clock64();
+              sl += NCW;
+              if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+            }
+          }
+          w.nb += as.n_items;
+        }
+        if (as.last && warp == 0) {   // the key / value of the token being decoded (published by the qkv phase of this launch)
+          float kf[8], vf[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { kf[i] = qkn[128 + l16 * 8 + i]; vf[i] = qkn[256 + l16 * 8 + i]; }
+          key_update(kf, vf, hw == 0);
+        }
+        // merge the 16 half-warp states -> one partial per CTA
+        float* sm_m = actf;            // [16]
+        float* sm_l = actf + 16;       // [16]
+        float* sm_o = actf + 32;       // [16][128]
+        const int hidx = warp * 2 + hw;
+        if (l16 == 0) { sm_m[hidx] = m; sm_l[hidx] = lsum; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm_o[hidx * 128 + l16 * 8 + i] = o[i];
+        consumer_sync();
+        if (tid < 128) {
+          float M = -INFINITY;
+#pragma unroll
+          for (int h = 0; h < 16; ++h) M = fmaxf(M, sm_m[h]);
+          float Lt = 0.f, O = 0.f;
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const float wgt = (sm_m[h] == -INFINITY) ? 0.f : exp2f(sm_m[h] - M);
+            Lt += sm_l[h] * wgt;
+            O += sm_o[h * 128 + tid] * wgt;
+          }
+          u64* pp = t_part + (int64_t)c * 132;
+          st_tag(pp + tid, O, tag);
+          if (tid == 0) { st_tag(pp + 128, M, tag); st_tag(pp + 129, Lt, tag); }
+        }
+        // the LAST CTA of this head to get here merges the head's partials into the normalised output (the partials are
+        // tagged, so the arrival counter needs no release / acquire)
+        consumer_sync();
+        if (tid == 0) {
+          unsigned prev;
+          asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
+          red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
+        }
+        consumer_sync();
+        if (red[8] != 0.f) {
+          // the head's partials -> shared memory (coalesced, validated), then 128 threads fold them in CTA order
+          float* mg = actf + 32 + 16 * 128;   // [cph][132]
+          const int nw = as.cph * 130;
+          for (int i0 = 0; i0 < nw; i0 += 2 * CONSUMER_THREADS) {
+            u64 wv2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = i0 + u * CONSUMER_THREADS + tid;
+              if (i < nw) wv2[u] = ld_weak1(t_part + (int64_t)((i / 130) * p.heads + as.head) * 132 + (i % 130));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = i0 + u * CONSUMER_THREADS + tid;
+              if (i < nw) mg[(i / 130) * 132 + (i % 130)] = settle1(wv2[u], t_part + (int64_t)((i / 130) * p.heads + as.head) * 132 + (i % 130), tag, nowait);
+            }
+          }
+          consumer_sync();
+          if (tid < 128) {
+            float M = -INFINITY;
+            for (int r = 0; r < as.cph; ++r) M = fmaxf(M, mg[r * 132 + 128]);
+            float Lt = 0.f, O = 0.f;
+#pragma unroll 1
+            for (int r = 0; r < as.cph; ++r) {
+              const float mr = mg[r * 132 + 128];
+              const float wgt = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
+              Lt += mg[r * 132 + 129] * wgt;
+              O += mg[r * 132 + tid] * wgt;
+            }
+            st_tag(t_att + as.head * 128 + tid, O / Lt, tag);
+          }
+          if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p.head_cnt + as.head), "r"(0u) : "memory");  // next use is a layer away
+        }
+      } else {
+        stamp(1);
+      }
+      stamp(2);
+    } else {
+      // ---------------- weight phase: stage the input vector, multiply the CTA's row groups, fused epilogue
+      const MegaMat& m = p.mat[mat_of(ph)];
+      int g0, cnt, nact;
+      phase_span(w, m.groups, g0, cnt, nact);
+      const int tpg = m.tpg;
+      float rn = 1.f;
+      if (cnt > 0) {   // idle CTAs skip the staging
+        const int64_t no = (int64_t)l * p.norm_stride;
+        const u64* src = ph == PH_QKV ? (l == 0 ? nullptr : t_xb) : ph == PH_O ? t_att : ph == PH_GU ? t_xa : ph == PH_DOWN ? t_h : t_xb;
+        const int K = ph == PH_O ? qd : ph == PH_DOWN ? p.I : p.H;
+        const bf16* nw = ph == PH_QKV ? p.norm1_0 + no : ph == PH_GU ? p.norm2_0 + no : ph == PH_LM ? p.final_norm : nullptr;
+        rn = stage_vec(src, tag - 1, nowait ? 1 : 0, p.embed + (int64_t)tok * p.H, K, tpg * 256, nw, p.eps, actf, red);
+      }
+      stamp(1);
+      const uint32_t nb0 = w.nb, gb0 = w.gb;
+      // residual source of the O / DOWN epilogues: the row's previous value in the other residual buffer
+      const u64* res_src = (ph == PH_O) ? t_xb : t_xa;
+      const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
+      const int ntiles = cnt * tpg;
+      uint32_t j = ((uint32_t)warp + NCW - (nb0 & (NCW - 1))) & (NCW - 1);
+      if ((int)j < ntiles) {
+        const uint32_t n00 = nb0 + j;
+        uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
+        uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
+        for (; (int)j < ntiles; j += NCW) {
+          long long* trow = nullptr;
+          if (DBG && ctr) {
+            const uint32_t row = nb0 + j - ctr_nb0;
+            if (row < 160u) trow = ctr + row * 4;
+          }
+          if (DBG && trow && lane == 0) trow[3] = clock64();
+          mbar_wait(full0 + 8 * sl, use & 1);
+          if (DBG && trow && lane == 0) trow[1] = clock64();
+          cur_slot = sl;
+          // ---- one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
+          // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
+          // column 0 and W.lo in column 1. The B fragments are loaded first and the A fragments in batches of four
+          // k-steps interleaved with the mma of earlier batches, so that the tensor pipe starts while the rest of the
+          // tile is still being read (shared-memory returns are in order; all 16 ldmatrix in front of the first mma made
+          // the two pipes take turns: 0.53 us per tile, the sum of both).
+          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          {
+            const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
+            const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
+            uint2 b[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
+            uint32_t a[16][4];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+#pragma unroll
+            for (int bq = 0; bq < 4; ++bq) {
+              if (bq < 2) {
+#pragma unroll
+                for (int s = 8 + 4 * bq; s < 12 + 4 * bq; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+              }
+              if (bq == 1) release();
+              if (!(dflags & 1)) {
+#pragma unroll
+                for (int s = 4 * bq; s < 4 * bq + 4; s += 2) {
+                  mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
+                  mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
                 }
               }
-              if (ok || nowait) break;
-              sp.tick();
             }
-            float Mb = M;
-#pragma unroll
-            for (int r = 0; r < RB; ++r)
-              if (rb + r < as.cph) Mb = fmaxf(Mb, tag_val(wm[r]));
-            const float sc = (M == -INFINITY) ? 0.f : exp2f(M - Mb);
-            Lt *= sc; O *= sc;
-#pragma unroll
-            for (int r = 0; r < RB; ++r) {
-              if (rb + r < as.cph) {
-                const float mr = tag_val(wm[r]);
-                const float wgt = (mr == -INFINITY) ? 0.f : exp2f(mr - Mb);
-                Lt += tag_val(wl[r]) * wgt;
-                O += tag_val(wo[r]) * wgt;
+            // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
+            acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
+            acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
+          }
+          const uint32_t gslot = (gb0 + k) % NG;
+          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+            // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
+            // critical path of the group's epilogue (the value was published two or more phases ago)
+            const int row = (g0 + (int)k) * 16 + lane;
+            float bres = 0.f;
+            if (row < p.H)
+              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
+                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
+            rbuf[gslot * 16 + lane] = bres;
+          }
+          const uint32_t n = nb0 + j;
+          if ((lane & 3) == 0) {
+            float* tp = tpart + (n % NT) * 16;
+            tp[lane >> 2] = acc[0];
+            tp[(lane >> 2) + 8] = acc[2];
+          }
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            __threadfence_block();
+            // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
+            const uint32_t n0 = nb0 + k * tpg;
+            float v = 0.f;
+            if (lane < 16)
+              for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
+            const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
+            if (lane == 0) gcnt[gslot] = 0;
+            if (lane < 8) {
+              const int gi = g0 + (int)k, r = lane;
+              if (ph == PH_QKV) {
+                const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
+                const int row0 = hb * 128 + i;
+                const float a0 = v * rn, a1 = v1 * rn;
+                if (row0 < qd + kd) {
+                  const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+                  const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
+                  if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
+                  else {
+                    const int kh = (row0 - qd) >> 7;
+                    bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
+                    const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
+                    dd[i] = z0;
+                    dd[i + 64] = z1;
+                    st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
+                    st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                  }
+                } else {
+                  const int kh = (row0 - qd - kd) >> 7;
+                  bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
+                  const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
+                  dd[i] = z0;
+                  dd[i + 64] = z1;
+                  st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
+                  st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                }
+              } else if (ph == PH_O || ph == PH_DOWN) {
+                u64* dst = (ph == PH_O) ? t_xa : t_xb;
+                const int r0 = gi * 16 + r, r1 = r0 + 8;
+                const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+                if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
+                if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
+              } else if (ph == PH_GU) {
+                const int i = gi * 8 + r;
+                if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
+              } else {
+                const int r0 = gi * 16 + r, r1 = r0 + 8;
+                if (r0 < p.V) p.logits[r0] = v * rn;
+                if (r1 < p.V) p.logits[r1] = v1 * rn;
               }
             }
-            M = Mb;
           }
-          st_tag(t_att + as.head * 128 + tid, O / Lt, ptag);
+          if (DBG && trow && lane == 0) trow[2] = clock64();
+          sl += NCW;
+          if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+          ks += NCW;
+          while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
         }
-        if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p.head_cnt + as.head), "r"(0u) : "memory");  // next use is a layer away
       }
-    } else {
-      stamp(1);
+      w.nb += ntiles;
+      w.gb += cnt;
+      w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
+      stamp(2);
     }
-    stamp(2);
-    bar_target += G;
-    hint_barrier(p.bar_count, bar_target, dflags);
-    stamp(3); ++dbg_i;
-
-    // ---------------- P3: o-proj + residual on the merged attention output
-    stamp(0);
-    if (has_work(p.o)) stage_vec(t_att, tag0 + PH_ATTN, nowait, nullptr, qd, Qp, nullptr, 0.f, xb, red);
-    stamp(1);
-    run_phase(p.o, PH_O, l, 1.f, tag0 + PH_O);
-    stamp(2);
-    bar_target += G;
-    hint_barrier(p.bar_count, bar_target, dflags);
-    stamp(3); ++dbg_i;
-
-    // ---------------- P4: RMSNorm + gate/up + SiLU*mul
-    stamp(0);
-    rn = 1.f;
-    if (has_work(p.gu)) rn = stage_vec(t_xa, tag0 + PH_O, nowait, nullptr, p.H, Hp, p.norm2_0 + no, p.eps, xb, red);
-    stamp(1);
-    run_phase(p.gu, PH_GU, l, rn, tag0 + PH_GU);
-    stamp(2);
-    bar_target += G;
-    hint_barrier(p.bar_count, bar_target, dflags);
-    stamp(3); ++dbg_i;
-
-    // ---------------- P5: down + residual
-    stamp(0);
-    if (has_work(p.down)) stage_vec(t_h, tag0 + PH_GU, nowait, nullptr, p.I, Ip, nullptr, 0.f, xb, red);
-    stamp(1);
-    run_phase(p.down, PH_DOWN, l, 1.f, tag0 + PH_DOWN);
-    stamp(2);
-    bar_target += G;
-    hint_barrier(p.bar_count, bar_target, dflags);
-    stamp(3); ++dbg_i;
+    // hint barrier after every phase except qkv (the attention phase polls its head's q itself) and lm_head
+    if (ph != PH_QKV && ph != PH_LM) {
+      bar_target += G;
+      hint_barrier(p.bar_count, bar_target, dflags);
+    }
+    stamp(3);
+    if (++ph == 5) { ph = 0; ++l; }
   }
-  // ---------------- final RMSNorm + lm_head
-  ctr = nullptr;
-  stamp(0);
-  float rn = 1.f;
-  const uint32_t tagf = epoch + (uint32_t)p.L * 5u;   // = tag of the last layer's P5
-  if (has_work(p.lm)) rn = stage_vec(t_xb, tagf, nowait, nullptr, p.H, Hp, p.final_norm, p.eps, xb, red);
-  stamp(1);
-  run_phase(p.lm, PH_LM, 0, rn, 0u);
-  stamp(2); stamp(3);
   // publish the arrival count and the tag epoch for the next launch (stream-ordered): every CTA made 4L arrivals and
-  // the launch used tags epoch + 1 .. epoch + 5L
+  // the launch used tags epoch + 1 .. epoch + 5L + 1
   if (c == 0 && tid == 0 && !(dflags & 2)) {
     p.bar_base[0] = bar_target;
-    p.bar_base[1] = (unsigned long long)(uint32_t)(epoch + (uint32_t)p.L * 5u);
+    p.bar_base[1] = (unsigned long long)(uint32_t)(epoch + (uint32_t)nphase);
   }
 }
 
@@ -885,20 +875,20 @@ cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cu
 }
 
 int mega_smem_bytes(const MegaArgs& a) {
-  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4;
+  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4;
 }
 
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out) {
   auto pad = [](int k) { return (k + 255) / 256 * 256; };
   int actf = pad(H) > pad(I) ? pad(H) : pad(I);
   if (pad(heads * 128) > actf) actf = pad(heads * 128);
-  if (actf < 32 + 16 * 128) actf = 32 + 16 * 128;  // attention merge scratch
+  if (actf < 32 + 16 * 128 + 16 * 132) actf = 32 + 16 * 128 + 16 * 132;  // attention merge scratch (half-warp states + the head's partials)
   actf = (actf + 31) & ~31;
   a.act_floats = actf;
   a.tg_H = pad(H);
   a.tg_I = pad(I);
   if ((I + 255) / 256 > NT - 44) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
-  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 64;
+  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4 + 64;
   int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
   if (nslots > 32) nslots = 32;
   // every ring slot must always be filled by the same producer warp and drained by the same consumer warp
@@ -907,7 +897,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   nslots &= ~(NCW - 1);
   if (nslots < NCW) return cudaErrorInvalidValue;
   a.nslots = nslots;
-  if (heads > num_sms || H > 8192) return cudaErrorInvalidValue;  // normed vector is register-staged (K <= 8192)
+  if (heads > num_sms) return cudaErrorInvalidValue;
   *grid_out = num_sms;
   return cudaSuccess;
 }

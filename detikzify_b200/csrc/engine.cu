@@ -84,6 +84,8 @@ bool config_ok(const dtk_config& c, std::string& why) {
   if (c.head_dim != 128) return bad("decoder head_dim must be 128");
   if (c.heads % c.kv_heads) return bad("heads % kv_heads != 0");
   if ((c.hidden & 7) || (c.inter & 7)) return bad("hidden/inter must be multiples of 8");
+  if (c.rope_type != 0 && c.rope_type != 1) return bad("rope_type must be 0 (linear) or 1 (llama3)");
+  if (c.rope_type == 1 && (c.rope_low_freq <= 0.f || c.rope_high_freq <= c.rope_low_freq || c.rope_orig_max_pos <= 0)) return bad("bad llama3 rope parameters");
   if (c.max_len <= 0 || c.max_seqs <= 0 || c.max_batch <= 0 || c.max_batch > 64) return bad("bad max_len/max_seqs/max_batch (max_batch <= 64)");
   if (c.v_hidden <= 0 || c.v_heads <= 0 || c.v_hidden % c.v_heads) return bad("bad vision dims");
   if (c.v_hidden / c.v_heads != 72) return bad("vision head_dim must be 72 (SigLIP so400m)");
@@ -210,8 +212,9 @@ __global__ void set_state_kernel(StateArgs a, int* slots, int* pos, int* tok) {
 __global__ void tok64_to_32_kernel(const int64_t* in, int* out, int n) {
   if ((int)threadIdx.x < n) out[threadIdx.x] = (int)in[threadIdx.x];
 }
-__global__ void reset_gen_kernel(unsigned long long* gen, unsigned int* done) {
+__global__ void reset_gen_kernel(unsigned long long* gen, unsigned int* done, unsigned long long seed) {
   gen[0] = 0ull;
+  gen[1] = seed;   // read by the sampler of the generation loop (not baked into the captured graph)
   *done = 0u;
 }
 
@@ -546,7 +549,18 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
     std::vector<float> tab((size_t)T * 64 * 2);
     for (int i = 0; i < 64; ++i) {
       float inv = 1.0f / powf(c.rope_theta, (float)(2 * i) / 128.0f);
-      inv = inv / c.rope_factor;
+      if (c.rope_type == 1) {   // llama3 (HF modeling_rope_utils.py _compute_llama3_parameters), fp32 like HF
+        const float old_len = (float)c.rope_orig_max_pos;
+        const float low_wl = old_len / c.rope_low_freq, high_wl = old_len / c.rope_high_freq;
+        const float wl = 2.0f * 3.14159265358979323846f / inv;
+        if (wl > low_wl) inv = inv / c.rope_factor;
+        else if (!(wl < high_wl)) {
+          const float smooth = (old_len / wl - c.rope_low_freq) / (c.rope_high_freq - c.rope_low_freq);
+          inv = (1.0f - smooth) * inv / c.rope_factor + smooth * inv;
+        }
+      } else {
+        inv = inv / c.rope_factor;
+      }
       for (int64_t p = 0; p < T; ++p) {
         float ang = (float)p * inv;
         tab[((size_t)p * 64 + i) * 2] = (float)cos((double)ang);
@@ -594,14 +608,14 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       // decode-side tiled weight copy (one-time, on device): [layer][qkv | o | gu | down] ... [lm_head]
       const int qkvN = (c.heads + 2 * c.kv_heads) * 128, qd = c.heads * 128;
       struct Spec { MegaMat* mm; const char* name; int N, K, mode; } specs[4] = {
-          {&m.qkv, "wqkv", qkvN, c.hidden, TILE_ROPE}, {&m.o, "wo", c.hidden, qd, TILE_SEQ},
-          {&m.gu, "wgu", 2 * c.inter, c.hidden, TILE_GLU}, {&m.down, "wd", c.hidden, c.inter, TILE_SEQ}};
+          {&m.mat[0], "wqkv", qkvN, c.hidden, TILE_ROPE}, {&m.mat[1], "wo", c.hidden, qd, TILE_SEQ},
+          {&m.mat[2], "wgu", 2 * c.inter, c.hidden, TILE_GLU}, {&m.mat[3], "wd", c.hidden, c.inter, TILE_SEQ}};
       int64_t per_layer = 0, off[4];
       for (int i = 0; i < 4; ++i) {
         off[i] = per_layer;
         per_layer += mega_tiled_elems(specs[i].N, specs[i].K, specs[i].mode, &specs[i].mm->groups, &specs[i].mm->tpg);
       }
-      const int64_t lm_elems = mega_tiled_elems(c.vocab, c.hidden, TILE_SEQ, &m.lm.groups, &m.lm.tpg);
+      const int64_t lm_elems = mega_tiled_elems(c.vocab, c.hidden, TILE_SEQ, &m.mat[4].groups, &m.mat[4].tpg);
       DTK_ALLOC(eng->d_tiled, per_layer * c.layers + lm_elems);
       for (int i = 0; i < 4; ++i) {
         MegaMat& mm = *specs[i].mm;
@@ -610,7 +624,7 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
           DTK_CK(launch_retile(W(eng, LN("dec.L", l, specs[i].name)), specs[i].N, specs[i].K, specs[i].mode,
                                eng->d_tiled + (int64_t)l * per_layer + off[i], 0));
       }
-      m.lm.base = eng->d_tiled + per_layer * c.layers; m.lm.layer_stride = 0; m.lm.N = c.vocab; m.lm.K = c.hidden; m.lm.mode = TILE_SEQ;
+      m.mat[4].base = eng->d_tiled + per_layer * c.layers; m.mat[4].layer_stride = 0; m.mat[4].N = c.vocab; m.mat[4].K = c.hidden; m.mat[4].mode = TILE_SEQ;
       DTK_CK(launch_retile(W(eng, "dec.lm_head"), c.vocab, c.hidden, TILE_SEQ, eng->d_tiled + per_layer * c.layers, 0));
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
@@ -861,7 +875,7 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     st.slots[i] = slots[i]; st.pos[i] = positions[i]; st.tok[i] = first_ids_host[i];
   }
   set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok);
-  reset_gen_kernel<<<1, 1, 0, s>>>(eng->d_gen, eng->d_counters + (int64_t)c.max_batch * c.heads);
+  reset_gen_kernel<<<1, 1, 0, s>>>(eng->d_gen, eng->d_counters + (int64_t)c.max_batch * c.heads, params->seed);
   eng->launches += 2;
   DTK_CK(cudaGetLastError());
   DTK_CK(cudaStreamSynchronize(s));
@@ -874,7 +888,7 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     SampleArgs& a = eng->gen_sample;
     fill_sample_args(eng, a, eng->d_logits, B, *params);
     for (int i = 0; i < B; ++i) { a.seq[i].suppress = 0; a.seq[i].step = 1; a.seq[i].seq_id = seq_ids ? seq_ids[i] : (uint32_t)i; }
-    a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen;
+    a.gen_tok = eng->d_tok; a.gen_pos = eng->d_pos; a.gen_step = eng->d_gen; a.seed_dev = eng->d_gen + 1; a.seed = 0;
     a.host_ring = eng->dev_ring; a.ring = eng->ring;
     a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
   }
@@ -885,9 +899,8 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
   }
   // graph key: everything baked into kernel arguments
   char key[256];
-  std::snprintf(key, sizeof(key), "B%d|t%.9g|p%.17g|k%d|s%d|b%d|e%d|seed%llu", B, (double)params->temperature,
-                (double)params->top_p, params->top_k, params->do_sample, params->bad_token, params->begin_suppress_token,
-                (unsigned long long)params->seed);
+  std::snprintf(key, sizeof(key), "B%d|t%.9g|p%.17g|k%d|s%d|b%d|e%d", B, (double)params->temperature,
+                (double)params->top_p, params->top_k, params->do_sample, params->bad_token, params->begin_suppress_token);
   std::string skey(key);
   skey += "|g" + std::to_string(eng->decode_gemm_min_batch) + "|i" + std::to_string(get_gemm_impl());
   if (seq_ids) for (int i = 0; i < B; ++i) skey += "," + std::to_string(seq_ids[i]);

@@ -136,6 +136,8 @@ struct SampleArgs {
   float top_p_limit;              // (float)(1.0 - top_p): ascending cumulative mass <= limit is removed
   int top_k, do_sample, bad_token, bs_token;
   uint64_t seed;
+  const unsigned long long* seed_dev;   // generation loop: the seed lives in a device word (written by gen_begin) so that a
+                                        // captured decode graph does not depend on it; null = use `seed`
   float* scratch;             // [B, V] fp32 work buffer (receives the final probability vector)
   int want_probs;             // greedy only: also write softmax(masked logits) to scratch (sampling always writes it)
   int64_t* out_ids;           // device int64[B] or null
@@ -175,7 +177,7 @@ struct MegaArgs {
   const bf16 *embed, *final_norm;
   const bf16 *norm1_0, *norm2_0;                               // row-major arena; layer l = ptr + l * norm_stride
   int64_t norm_stride;
-  MegaMat qkv, o, gu, down, lm;
+  MegaMat mat[5];                                             // qkv, o, gate/up, down (per layer) and lm_head
   const int *tok, *pos, *slots;                               // device state of the sequence being decoded
   bf16* kv;
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(ST) sample_generic_kernel(const SampleArgs p) 
     __syncthreads();
     // 6. inverse-CDF draw in index order
     const uint32_t ctr = sq.step + (uint32_t)gstep;
-    const float u = philox_uniform(p.seed, ctr, sq.seq_id);
+    const float u = philox_uniform(p.seed_dev ? *p.seed_dev : p.seed, ctr, sq.seq_id);
     const int per = (V + ST - 1) / ST;
     const int i0 = tid * per, i1 = min(V, i0 + per);
     float loc = 0.f;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(ST) sample_kernel(const SampleArgs p) {
     __syncthreads();
     // 6. inverse-CDF draw in index order (blocked ranges, read back from the scratch row)
     const uint32_t ctr = sq.step + (uint32_t)gstep;
-    const float u = philox_uniform(p.seed, ctr, sq.seq_id);
+    const float u = philox_uniform(p.seed_dev ? *p.seed_dev : p.seed, ctr, sq.seq_id);
     const int per = (V + ST - 1) / ST;
     const int i0 = tid * per, i1 = min(V, i0 + per);
     float loc = 0.f;

@@ -30,6 +30,8 @@ def to_c_config(cfg: "DetikzifyConfig", max_seqs: int = 4, max_batch: int = 1, m
         heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim,
         vocab=cfg.vocab_size, max_len=max_len or cfg.model_max_length,
         rms_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta, rope_factor=cfg.rope_factor,
+        rope_type={"linear": 0, "llama3": 1}[cfg.rope_type], rope_low_freq=cfg.rope_low_freq_factor,
+        rope_high_freq=cfg.rope_high_freq_factor, rope_orig_max_pos=cfg.rope_original_max_position,
         v_hidden=vc.hidden_size, v_inter=vc.intermediate_size, v_layers=vc.num_hidden_layers,
         v_heads=vc.num_attention_heads, v_image=vc.image_size, v_patch=vc.patch_size, v_act=act,
         v_eps=vc.layer_norm_eps, concat=cfg.concat_patches, image_token_id=cfg.image_token_id,

@@ -57,6 +57,10 @@ class DetikzifyConfig:
     rms_norm_eps: float = 1e-6
     rope_theta: float = 100000.0
     rope_factor: float = 4.0  # linear scaling (DeepSeek-Coder)
+    rope_type: str = "linear"  # "llama3" for the LLaMA-3.x decoders of the v2 checkpoints
+    rope_low_freq_factor: float = 1.0
+    rope_high_freq_factor: float = 4.0
+    rope_original_max_position: int = 8192
     model_max_length: int = 2048  # v1 tokenizer limit, detikzify/model/v1/__init__.py:28
     # special tokens (v1: patch token := tokenizer BOS, v1/__init__.py:49)
     bos_token_id: int = 32013
@@ -120,6 +124,36 @@ def preset(name: str) -> DetikzifyConfig:
                                num_attention_heads=32, num_key_value_heads=32, name_or_path=name,
                                vision_config=VisionConfig(hidden_size=144, intermediate_size=176, num_hidden_layers=2,
                                                           num_attention_heads=2, image_size=56, patch_size=14))
+    if key in ("detikzify-v2-8b", "detikzify-v2.5-8b", "v2-8b", "v2.5-8b"):
+        # v2 / v2.5 (reference detikzify/model/configuration_detikzify.py:31-58,83-120, modeling_detikzify.py:62-86): SigLIP
+        # so400m at 420 px -> 900 patches -> 300 image tokens, bias-free connector, LLaMA-3.1-8B decoder (GQA 32/8,
+        # V 128256, llama3 RoPE scaling; public base config, not in the reference tree), image token 128005
+        return DetikzifyConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                               num_key_value_heads=8, vocab_size=128256, max_position_embeddings=131072, rms_norm_eps=1e-5,
+                               rope_theta=500000.0, rope_factor=8.0, rope_type="llama3", rope_low_freq_factor=1.0,
+                               rope_high_freq_factor=4.0, rope_original_max_position=8192,
+                               bos_token_id=128000, eos_token_id=128001, pad_token_id=128004, patch_token_id=128005,
+                               projector_bias=False, name_or_path=name, vision_config=VisionConfig(image_size=420))
+    if key in ("detikzify-v2-8b-2l", "v2-8b-2l"):   # parity-test shape: every v2-8b matrix shape, two decoder layers, small tower
+        return DetikzifyConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
+                               num_key_value_heads=8, vocab_size=128256, max_position_embeddings=131072, rms_norm_eps=1e-5,
+                               rope_theta=500000.0, rope_factor=8.0, rope_type="llama3", rope_low_freq_factor=1.0,
+                               rope_high_freq_factor=4.0, rope_original_max_position=8192,
+                               bos_token_id=128000, eos_token_id=128001, pad_token_id=128004, patch_token_id=128005,
+                               projector_bias=False, name_or_path=name,
+                               vision_config=VisionConfig(hidden_size=144, intermediate_size=176, num_hidden_layers=2,
+                                                          num_attention_heads=2, image_size=84, patch_size=14))
+    if key == "tiny-v2":   # v2 wiring at a CPU-test size: GQA 4/2, llama3 RoPE (short original context so all three
+        # frequency bands occur), bias-free connector, 6x6 patches -> 12 image tokens
+        return DetikzifyConfig(
+            hidden_size=512, intermediate_size=1376, num_hidden_layers=2, num_attention_heads=4,
+            num_key_value_heads=2, vocab_size=640, model_max_length=128, rms_norm_eps=1e-5,
+            rope_theta=500000.0, rope_factor=8.0, rope_type="llama3", rope_low_freq_factor=1.0, rope_high_freq_factor=4.0,
+            rope_original_max_position=64,
+            bos_token_id=600, eos_token_id=601, pad_token_id=604, patch_token_id=605, projector_bias=False,
+            name_or_path=name,
+            vision_config=VisionConfig(hidden_size=144, intermediate_size=176, num_hidden_layers=2,
+                                       num_attention_heads=2, image_size=84, patch_size=14))
     if key == "tiny":
         return DetikzifyConfig(
             hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,

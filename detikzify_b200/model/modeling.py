@@ -57,8 +57,10 @@ class DetikzifyVisionModel:
         o = self._owner
         with o._lock, o._on_stream():
             tokens, pooled = o.engine.vit_encode(pixel_values)
+            # cast on the engine stream, before the sync: a tensor must not leave the side stream while work on it is pending
+            tokens, pooled = tokens.to(o.dtype), pooled.to(o.dtype)
             o._sync()
-        return VisionOutput(last_hidden_state=tokens.to(o.dtype), pooler_output=pooled.to(o.dtype))
+        return VisionOutput(last_hidden_state=tokens, pooler_output=pooled)
 
     def get_intermediate_layers(self, pixel_values: torch.Tensor, n=None, norm: bool = True, **_):
         """Only the configuration the reference uses: last layer, final norm applied
@@ -248,7 +250,10 @@ class DetikzifyForCausalLM:
                 if ids_host[img_start: img_start + n_patch_tokens] != [patch] * n_patch_tokens:
                     raise ValueError("The image patch tokens should be consecutive.")
                 img = self._image_embeds(pixel_values)
-            elif pixel_values is None and self._img_cache is not None and n_patch_tokens:
+            elif pixel_values is None and n_patch_tokens:
+                # patch tokens without an image: their KV comes from plain embeddings. Forget the image identity too, so a
+                # later call WITH the same image re-validates nothing against these slots
+                self._img_cache = None
                 self._slot_tokens = []
             if T0 == 0:
                 raise ValueError("empty prompt")
@@ -264,6 +269,7 @@ class DetikzifyForCausalLM:
             ids_dev = torch.tensor(ids_host[L:], dtype=torch.int64)
             if self.device.type == "cuda":
                 ids_dev = ids_dev.pin_memory().to(self.device, non_blocking=True)
+            self._slot_tokens = list(ids_host[:L])     # if the prefill raises, the slot only claims what it held before
             last_logits, _ = eng.prefill(self._slot, ids_dev, L, img, img_start)
             self._slot_tokens = list(ids_host)
 
@@ -307,7 +313,9 @@ class DetikzifyForCausalLM:
             # detikzify/infer/generate.py:252); the normal path always terminates the stream
             if streamer is not None:
                 streamer.end()
-            return out_buf[:, : T0 + len(new_tokens)].to(self.device)
+            result = out_buf[:, : T0 + len(new_tokens)].to(self.device)
+            self._sync()
+            return result
 
     # ---- batched generation (extension; the reference's generate() is batch-1) ---------------------
     @torch.no_grad()
@@ -412,7 +420,7 @@ class DetikzifyForCausalLM:
         with self._lock, self._on_stream():
             _, pooled = self.engine.vit_encode(pixel_values, want_tokens=False)
             self._sync()
-        return pooled
+        return pooled   # fp32, produced and synchronised on the engine stream
 
     def close(self):
         self.engine.close()

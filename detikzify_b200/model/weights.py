@@ -142,3 +142,41 @@ def convert_timm_vision(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     out[v + "head.attention.in_proj_bias"] = torch.cat(
         [sd["attn_pool.q.bias"], sd["attn_pool.kv.bias"]], dim=0)
     return out
+
+
+# ---- v2 checkpoint names -> canonical (reference detikzify/model/modeling_detikzify.py:119-131: ``model.text_model`` is
+# an HF LlamaModel, ``model.connector.modality_projection.proj`` the bias-free projector, ``model.vision_model`` an HF
+# SiglipVisionModel; ``lm_head`` sits on the outer module) ---------------------------------------------------------------
+_V2_PREFIXES = (
+    ("model.text_model.", "model."),
+    ("model.connector.modality_projection.proj.", "model.mm_projector."),
+    ("model.vision_model.", "model.vision_model."),
+)
+
+
+def convert_v2_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Reference v2 / v2.5 parameter names -> canonical names (pure renaming, tensors are shared)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        for src, dst in _V2_PREFIXES:
+            if k.startswith(src):
+                out[dst + k[len(src):]] = v
+                break
+        else:
+            out[k] = v
+    return out
+
+
+def to_v2_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Inverse of ``convert_v2_state_dict`` (used to load canonical test weights into the reference's v2 module)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.startswith("model.vision_model."):
+            out[k] = v
+        elif k.startswith("model.mm_projector."):
+            out["model.connector.modality_projection.proj." + k[len("model.mm_projector."):]] = v
+        elif k.startswith("model."):
+            out["model.text_model." + k[len("model."):]] = v
+        else:
+            out[k] = v
+    return out

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DTK_ABI_VERSION 1
+#define DTK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DTK_API __attribute__((visibility("default")))
@@ -48,6 +48,13 @@ typedef struct dtk_config {
   /* decoder */
   int32_t hidden, inter, layers, heads, kv_heads, head_dim, vocab, max_len;
   float rms_eps, rope_theta, rope_factor;
+  /* RoPE frequency scaling: 0 = linear (inv_freq / rope_factor; DeepSeek-Coder decoders of the v1 checkpoints),
+   * 1 = "llama3" (HF modeling_rope_utils._compute_llama3_parameters; LLaMA-3.x decoders of the v2 checkpoints,
+   * detikzify/model/configuration_detikzify.py:83-120): wavelengths above rope_orig_max_pos / rope_low_freq are divided by
+   * rope_factor, those below rope_orig_max_pos / rope_high_freq are kept, the band in between is interpolated */
+  int32_t rope_type;
+  float rope_low_freq, rope_high_freq;
+  int32_t rope_orig_max_pos;
   /* vision tower */
   int32_t v_hidden, v_inter, v_layers, v_heads, v_image, v_patch;
   int32_t v_act;              /* 0 = gelu_pytorch_tanh, 1 = exact (erf) gelu */

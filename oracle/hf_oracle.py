@@ -75,7 +75,11 @@ class Oracle:
             num_key_value_heads=cfg["num_key_value_heads"], head_dim=cfg["head_dim"],
             vocab_size=cfg["vocab_size"], max_position_embeddings=cfg["max_position_embeddings"],
             rms_norm_eps=cfg["rms_norm_eps"], rope_theta=cfg["rope_theta"],
-            rope_scaling={"type": "linear", "factor": cfg["rope_factor"]} if cfg["rope_factor"] != 1.0 else None,
+            rope_scaling=({"rope_type": "llama3", "factor": cfg["rope_factor"], "low_freq_factor": cfg["rope_low_freq_factor"],
+                           "high_freq_factor": cfg["rope_high_freq_factor"],
+                           "original_max_position_embeddings": cfg["rope_original_max_position"]}
+                          if cfg.get("rope_type", "linear") == "llama3" else
+                          {"type": "linear", "factor": cfg["rope_factor"]} if cfg["rope_factor"] != 1.0 else None),
             hidden_act="silu", attention_bias=False, mlp_bias=False, tie_word_embeddings=False,
             bos_token_id=cfg["bos_token_id"], eos_token_id=cfg["eos_token_id"],
             pad_token_id=cfg["pad_token_id"], attn_implementation=attn_implementation,

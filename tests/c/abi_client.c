@@ -11,7 +11,7 @@ int main(void) {
   memset(&c, 0, sizeof c);
   /* detikzify-ds-1.3b + SigLIP so400m/14@384 */
   c.hidden = 2048; c.inter = 5504; c.layers = 24; c.heads = 16; c.kv_heads = 16; c.head_dim = 128; c.vocab = 32256; c.max_len = 2048;
-  c.rms_eps = 1e-6f; c.rope_theta = 100000.f; c.rope_factor = 4.f;
+  c.rms_eps = 1e-6f; c.rope_theta = 100000.f; c.rope_factor = 4.f; c.rope_type = 0;
   c.v_hidden = 1152; c.v_inter = 4304; c.v_layers = 27; c.v_heads = 16; c.v_image = 384; c.v_patch = 14; c.v_act = 0; c.v_eps = 1e-6f;
   c.concat = 3; c.image_token_id = 32013; c.eos_token_id = 32021; c.max_seqs = 2; c.max_batch = 1;
 

@@ -156,3 +156,24 @@ def test_oracle_matches_reference_model_code_at_ds13b_shape():
     dec, _ = oracle.decode_logits(torch.tensor([[gold["next_id"]]]), cache)
     d1 = (dec[0, -1] - gold["decode_logits"]).abs().max().item()
     assert d1 < 2e-4, d1
+
+
+def test_oracle_matches_reference_v2_golden():
+    """v2 wiring (GQA, llama3 RoPE, bias-free connector, masked-scatter merge): the oracle reproduces what the REFERENCE's own
+    v2 module (detikzify/model/modeling_detikzify.py, run by tests/golden/make_reference_golden_v2.py) computed on the tiny-v2
+    fixture — all-position logits, one cached decode step, connector output, greedy ids."""
+    from pathlib import Path
+    gold = torch.load(Path(__file__).parent / "golden" / "reference_v2_tiny.pt", weights_only=False)["tiny-v2"]
+    from conftest import model_bundle
+    from oracle.hf_oracle import synthetic_pixels
+    cfg, sd, oracle = model_bundle("tiny-v2", seed=gold["seed"])
+    assert cfg.num_key_value_heads < cfg.num_attention_heads and cfg.rope_type == "llama3" and not cfg.projector_bias
+    pix = synthetic_pixels(1, cfg.vision_config.image_size, seed=gold["pixel_seed"])
+    ids = gold["input_ids"][None]
+    logits, cache = oracle.forward_logits(ids, pix, use_cache=True)
+    assert (logits[0] - gold["logits"]).abs().max() < 2e-5
+    assert (oracle.image_embeds(pix)[0] - gold["image_embeds"]).abs().max() < 2e-5
+    dec, _ = oracle.decode_logits(torch.tensor([[gold["next_id"]]]), cache)
+    assert (dec[0, -1] - gold["decode_logits"]).abs().max() < 2e-5
+    out = oracle.generate(gold["generate_prompt"][None], pix, max_length=gold["generate_ids"].numel())
+    assert torch.equal(out[0], gold["generate_ids"])
