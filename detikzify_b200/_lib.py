@@ -51,6 +51,7 @@ SYMBOLS = {
     "dtk_seq_alloc": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "dtk_seq_free": (C.c_int, [_P, C.c_int]),
     "dtk_seq_fork": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "dtk_seq_share": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "dtk_prefill": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
     "dtk_decode": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, C.c_int, _P, _P]),
     "dtk_sample": (C.c_int, [_P, _P, C.c_int, C.POINTER(DtkSampling), C.POINTER(C.c_int),

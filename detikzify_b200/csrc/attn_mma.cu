@@ -20,14 +20,17 @@ struct AttnSmem {
   static constexpr int BYTES = 5 * TILE;     // Q + 2 x (K, V)
 };
 
+// rows below split_row come from base2 (shared KV prefix held by another slot), the others from base
 template <int D, int DP>
-DTK_DEV void load_rows(uint32_t sdst, const bf16* base, int64_t row_stride, int row0, int nrows_valid, int tid) {
+DTK_DEV void load_rows(uint32_t sdst, const bf16* base, int64_t row_stride, int row0, int nrows_valid, int tid,
+                       const bf16* base2 = nullptr, int split_row = 0) {
   constexpr int DPS = AttnSmem<D, DP>::DPS;
   constexpr int CH = D / 8;
   for (int c = tid; c < BQ * CH; c += ATHREADS) {
     int r = c / CH, kc = c - r * CH;
     bool ok = (row0 + r) < nrows_valid;
-    const bf16* src = ok ? base + (int64_t)(row0 + r) * row_stride + kc * 8 : base;
+    const bf16* rb = (row0 + r) < split_row ? base2 : base;
+    const bf16* src = ok ? rb + (int64_t)(row0 + r) * row_stride + kc * 8 : base;
     cp_async16(sdst + (uint32_t)(r * DPS + kc * 8) * 2, src, ok ? 16 : 0);
   }
 }
@@ -45,6 +48,8 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   const bf16* qb = p.q + (int64_t)b * p.q_bs + (int64_t)head * p.q_hs;
   const bf16* kb = p.k + (int64_t)b * p.k_bs + (int64_t)kvh * p.k_hs;
   const bf16* vb = p.v + (int64_t)b * p.v_bs + (int64_t)kvh * p.v_hs;
+  const bf16* kb2 = p.split_row > 0 ? p.k2 + (int64_t)b * p.k_bs + (int64_t)kvh * p.k_hs : kb;
+  const bf16* vb2 = p.split_row > 0 ? p.v2 + (int64_t)b * p.v_bs + (int64_t)kvh * p.v_hs : vb;
   const int q0 = qt * BQ;
 
   // zero the padding columns [D, DP) of Q and K tiles once (cp.async never touches them)
@@ -64,8 +69,8 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   const int ntiles = (tk + BKV - 1) / BKV;
 
   load_rows<D, DP>(sQ, qb, p.q_rs, q0, p.Tq, tid);
-  load_rows<D, DP>(sK0, kb, p.k_rs, 0, tk, tid);
-  load_rows<D, DP>(sV0, vb, p.v_rs, 0, tk, tid);
+  load_rows<D, DP>(sK0, kb, p.k_rs, 0, tk, tid, kb2, p.split_row);
+  load_rows<D, DP>(sV0, vb, p.v_rs, 0, tk, tid, vb2, p.split_row);
   cp_async_commit();
 
   float o[D / 8][4];
@@ -81,8 +86,8 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   for (int j = 0; j < ntiles; ++j) {
     const int st = j & 1;
     if (j + 1 < ntiles) {
-      load_rows<D, DP>(sK0 + (st ^ 1) * S::TILE, kb, p.k_rs, (j + 1) * BKV, tk, tid);
-      load_rows<D, DP>(sV0 + (st ^ 1) * S::TILE, vb, p.v_rs, (j + 1) * BKV, tk, tid);
+      load_rows<D, DP>(sK0 + (st ^ 1) * S::TILE, kb, p.k_rs, (j + 1) * BKV, tk, tid, kb2, p.split_row);
+      load_rows<D, DP>(sV0 + (st ^ 1) * S::TILE, vb, p.v_rs, (j + 1) * BKV, tk, tid, vb2, p.split_row);
     }
     cp_async_commit();
     cp_async_wait<1>();

@@ -160,6 +160,10 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   const int j0 = split * chunk, j1 = min(T, j0 + chunk);
   const bf16* kb = p.kv_base + (int64_t)slot * p.kv_slot_stride + (int64_t)kvh * p.max_len * 128;
   const bf16* vb = kb + p.kv_v_offset;
+  // shared prefix: positions below shlen live in another slot (one copy for all rollouts of a figure)
+  const int shlen = p.share_len ? p.share_len[b] : 0;
+  const bf16* kb2 = shlen > 0 ? p.kv_base + (int64_t)p.share_slot[b] * p.kv_slot_stride + (int64_t)kvh * p.max_len * 128 : kb;
+  const bf16* vb2 = kb2 + p.kv_v_offset;
   const float sl2 = p.scale * 1.4426950408889634f;
 
   float q[8];
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
     for (int u = 0; u < DA_UNROLL; ++u) {
       int j = jb + u * 8 + hw;
       if (j < j1) {
-        kr[u] = *reinterpret_cast<const uint4*>(kb + (int64_t)j * 128 + l16 * 8);
-        vr[u] = *reinterpret_cast<const uint4*>(vb + (int64_t)j * 128 + l16 * 8);
+        kr[u] = *reinterpret_cast<const uint4*>((j < shlen ? kb2 : kb) + (int64_t)j * 128 + l16 * 8);
+        vr[u] = *reinterpret_cast<const uint4*>((j < shlen ? vb2 : vb) + (int64_t)j * 128 + l16 * 8);
       } else {
         kr[u] = make_uint4(0, 0, 0, 0);
         vr[u] = make_uint4(0, 0, 0, 0);

@@ -232,8 +232,9 @@ DTK_DEV float consumer_sum(float v, float* red) {
 // Pass 1: coalesced 16-byte loads (one tagged pair per lane) -> fp32 vector in shared memory; pass 2: one thread per
 // k-step converts its 64 bytes in place (the fp32 k-step and its four B entries occupy the same bytes).
 // Deliberately NOT inlined: one copy keeps the whole per-token loop inside the 32 KB instruction cache.
-__device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int nowait, const bf16* src_bf16, int K, int Kp,
+__device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags, const bf16* src_bf16, int K, int Kp,
                                         const bf16* norm_w, float eps, float* xs, float* red) {
+  const bool nowait = (flags & 1) != 0, strong_first = (flags & 2) != 0;
   const int tid = threadIdx.x;
   // norm gains of this thread's first k-step: requested before the vector so that both L2 round trips overlap
   uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
@@ -249,12 +250,30 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int nowait
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pi = p0 + u * CONSUMER_THREADS + tid;
-        if (pi < npair) w[u] = ld_weak2(src + 2 * pi);
+        if (pi < npair) w[u] = strong_first ? ld_strong2(src + 2 * pi) : ld_weak2(src + 2 * pi);
+      }
+      // words whose tag is still old are re-read coherently, ALL of them per round (one L2 round trip per round)
+      Spin sp;
+      for (;;) {
+        bool bad[4], any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pi = p0 + u * CONSUMER_THREADS + tid;
+          bad[u] = pi < npair && !(tag_ok(w[u].x, tag) && tag_ok(w[u].y, tag));
+          any = any || bad[u];
+        }
+        if (!any || nowait) break;
+        sp.tick();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pi = p0 + u * CONSUMER_THREADS + tid;
+          if (bad[u]) w[u] = ld_strong2(src + 2 * pi);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pi = p0 + u * CONSUMER_THREADS + tid;
-        if (pi < npair) xs2[pi] = settle2(w[u], src + 2 * pi, tag, nowait != 0);
+        if (pi < npair) xs2[pi] = make_float2(tag_val(w[u].x), tag_val(w[u].y));
       }
     }
   } else {
@@ -351,6 +370,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
   const bf16* kv_slot = p.kv + (int64_t)slot * p.kv_slot_stride;
+  // shared KV prefix: positions [0, shlen) (a multiple of 16, so a 16-position ring item never straddles) live in another slot
+  const int shlen = p.share_len[0];
+  const bf16* kv_share = p.kv + (int64_t)p.share_slot[0] * p.kv_slot_stride;
   const int nphase = 5 * p.L + 1;
 
   // ---- item ownership. The CTA's local TILE sequence (all phases, in order) is dealt to agents by index:
@@ -399,7 +421,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         if (!attn) phase_span(w, m.groups, g0, cnt, nact);
         const int tpg = attn ? 1 : m.tpg;
         const int ntiles = attn ? as.n_items : cnt * tpg;
-        const bf16* base = attn ? kv_slot + (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128
+        const int64_t kvo = (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
+        const bf16* base = attn ? kv_slot + kvo
                                 : m.base + (int64_t)l * m.layer_stride + (int64_t)g0 * tpg * MEGA_TILE_ELEMS;
         // own tiles j = j0, j0 + NPW, ...
         uint32_t j = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
@@ -412,9 +435,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             if (attn) {
               const int key0 = as.j0 + (int)j * 16;
               const uint32_t bytes = (uint32_t)min(16, p.max_len - key0) * 256u;
+              const bf16* kb = (key0 < shlen ? kv_share + kvo : base) + (int64_t)key0 * 128;
               mbar_expect_tx(fb, 2 * bytes);
-              bulk_g2s(dst, base + (int64_t)key0 * 128, bytes, fb);
-              bulk_g2s(dst + 4096, base + p.kv_v_offset + (int64_t)key0 * 128, bytes, fb);
+              bulk_g2s(dst, kb, bytes, fb);
+              bulk_g2s(dst + 4096, kb + p.kv_v_offset, bytes, fb);
             } else {
               mbar_expect_tx(fb, TILE_BYTES);
               bulk_g2s(dst, base + (int64_t)j * MEGA_TILE_ELEMS, TILE_BYTES, fb);
@@ -671,7 +695,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         const u64* src = ph == PH_QKV ? (l == 0 ? nullptr : t_xb) : ph == PH_O ? t_att : ph == PH_GU ? t_xa : ph == PH_DOWN ? t_h : t_xb;
         const int K = ph == PH_O ? qd : ph == PH_DOWN ? p.I : p.H;
         const bf16* nw = ph == PH_QKV ? p.norm1_0 + no : ph == PH_GU ? p.norm2_0 + no : ph == PH_LM ? p.final_norm : nullptr;
-        rn = stage_vec(src, tag - 1, nowait ? 1 : 0, p.embed + (int64_t)tok * p.H, K, tpg * 256, nw, p.eps, actf, red);
+        rn = stage_vec(src, tag - 1, (nowait ? 1 : 0) | ((p.variant & 1) ? 2 : 0), p.embed + (int64_t)tok * p.H, K, tpg * 256, nw, p.eps, actf, red);
       }
       stamp(1);
       const uint32_t nb0 = w.nb, gb0 = w.gb;

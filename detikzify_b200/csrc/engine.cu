@@ -109,6 +109,9 @@ struct dtk_engine {
   bf16* kv = nullptr;
   int64_t kv_layer_stride = 0, kv_v_offset = 0, kv_slot_stride = 0;
   std::vector<char> slot_used;
+  // one-level shared KV prefix: positions [0, share_len[s]) of slot s are read from slot share_base[s] (a multiple of 16
+  // positions, never written through s); refcnt[b] = sequences borrowing from b, shared_upto[b] = longest prefix lent out
+  std::vector<int> share_base, share_len, refcnt, shared_upto;
   float* rope_cs = nullptr;  // [max_len, 64, 2]
 
   // prefill workspace (max_len rows)
@@ -118,7 +121,7 @@ struct dtk_engine {
   float *d_x = nullptr, *d_q = nullptr, *d_att = nullptr, *d_h = nullptr, *d_logits = nullptr, *d_scratch = nullptr;
   float *d_part_o = nullptr, *d_part_ml = nullptr;
   unsigned int* d_counters = nullptr;  // [max_batch*heads] + 1 (sampler done counter)
-  int *d_slots = nullptr, *d_pos = nullptr, *d_tok = nullptr;
+  int *d_slots = nullptr, *d_pos = nullptr, *d_tok = nullptr, *d_share_slot = nullptr, *d_share_len = nullptr;
   unsigned long long* d_gen = nullptr;  // [0] = step counter
   // ViT workspace (grows with batch)
   int vit_cap = 0;
@@ -153,6 +156,7 @@ struct dtk_engine {
   int mega_trace_layer = -1;
   int mega_debug = 0;
   int mega_flags = 0;
+  int mega_variant = 0;
 };
 
 namespace {
@@ -197,15 +201,17 @@ std::string LN(const char* prefix, int l, const char* s) { return std::string(pr
 
 struct StateArgs {
   int n;
-  int slots[64], pos[64];
+  int slots[64], pos[64], share_slot[64], share_len[64];
   long long tok[64];
   int have_tok;
 };
-__global__ void set_state_kernel(StateArgs a, int* slots, int* pos, int* tok) {
+__global__ void set_state_kernel(StateArgs a, int* slots, int* pos, int* tok, int* share_slot, int* share_len) {
   int i = threadIdx.x;
   if (i < a.n) {
     slots[i] = a.slots[i];
     pos[i] = a.pos[i];
+    share_slot[i] = a.share_slot[i];
+    share_len[i] = a.share_len[i];
     if (a.have_tok) tok[i] = (int)a.tok[i];
   }
 }
@@ -375,6 +381,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.logits = logits;
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
+    m.variant = eng->mega_variant;
     m.dbg2 = (eng->mega_debug && eng->mega_trace_layer >= 0) ? eng->d_dbg2 : nullptr;
     m.dbg_layer = eng->mega_trace_layer;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
@@ -402,7 +409,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
       {
         DecodeAttnArgs a{};
         a.q = eng->d_q; a.q_stride = qd; a.kv_base = kv_layer(eng, 0, l); a.kv_slot_stride = eng->kv_slot_stride;
-        a.kv_v_offset = eng->kv_v_offset; a.slots = eng->d_slots; a.pos = eng->d_pos;
+        a.kv_v_offset = eng->kv_v_offset; a.slots = eng->d_slots; a.pos = eng->d_pos; a.share_slot = eng->d_share_slot; a.share_len = eng->d_share_len;
         a.B = B; a.heads = c.heads; a.kv_group = c.heads / c.kv_heads; a.max_len = c.max_len; a.nsplit = nsplit;
         a.scale = 1.0f / sqrtf(128.f);
         a.part_o = eng->d_part_o; a.part_ml = eng->d_part_ml; a.counters = eng->d_counters;
@@ -433,7 +440,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     {
       DecodeAttnArgs a{};
       a.q = eng->d_q; a.q_stride = qd; a.kv_base = kv_layer(eng, 0, l); a.kv_slot_stride = eng->kv_slot_stride;
-      a.kv_v_offset = eng->kv_v_offset; a.slots = eng->d_slots; a.pos = eng->d_pos;
+      a.kv_v_offset = eng->kv_v_offset; a.slots = eng->d_slots; a.pos = eng->d_pos; a.share_slot = eng->d_share_slot; a.share_len = eng->d_share_len;
       a.B = B; a.heads = c.heads; a.kv_group = c.heads / c.kv_heads; a.max_len = c.max_len; a.nsplit = nsplit;
       a.scale = 1.0f / sqrtf(128.f);
       a.part_o = eng->d_part_o; a.part_ml = eng->d_part_ml; a.counters = eng->d_counters;
@@ -543,6 +550,10 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
   eng->kv_slot_stride = eng->kv_layer_stride * c.layers;
   DTK_ALLOC(eng->kv, eng->kv_slot_stride * c.max_seqs);
   eng->slot_used.assign(c.max_seqs, 0);
+  eng->share_base.assign(c.max_seqs, -1);
+  eng->share_len.assign(c.max_seqs, 0);
+  eng->refcnt.assign(c.max_seqs, 0);
+  eng->shared_upto.assign(c.max_seqs, 0);
 
   // RoPE table (HF modeling_llama.py:83-121: inv_freq = theta^(-2i/d) / factor, fp32; angle = pos * inv_freq)
   {
@@ -589,6 +600,10 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
   DTK_ALLOC(eng->d_slots, MB);
   DTK_ALLOC(eng->d_pos, MB);
   DTK_ALLOC(eng->d_tok, MB);
+  DTK_ALLOC(eng->d_share_slot, MB);
+  DTK_ALLOC(eng->d_share_len, MB);
+  DTK_CK(cudaMemset(eng->d_share_slot, 0, MB * sizeof(int)));
+  DTK_CK(cudaMemset(eng->d_share_len, 0, MB * sizeof(int)));
   DTK_ALLOC(eng->d_gen, 2);
   DTK_CK(cudaMemset(eng->d_gen, 0, 2 * sizeof(unsigned long long)));
   DTK_ALLOC(eng->v_pq, c.v_hidden);
@@ -626,7 +641,7 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
       }
       m.mat[4].base = eng->d_tiled + per_layer * c.layers; m.mat[4].layer_stride = 0; m.mat[4].N = c.vocab; m.mat[4].K = c.hidden; m.mat[4].mode = TILE_SEQ;
       DTK_CK(launch_retile(W(eng, "dec.lm_head"), c.vocab, c.hidden, TILE_SEQ, eng->d_tiled + per_layer * c.layers, 0));
-      m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots;
+      m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots; m.share_slot = eng->d_share_slot; m.share_len = eng->d_share_len;
       m.kv = eng->kv; m.kv_slot_stride = eng->kv_slot_stride; m.kv_layer_stride = eng->kv_layer_stride;
       m.kv_v_offset = eng->kv_v_offset; m.rope_cs = eng->rope_cs;
       m.logits = eng->d_logits;
@@ -665,7 +680,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_gen, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len, eng->d_gen, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
@@ -714,6 +729,26 @@ int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out, void* s
   return DTK_OK;
 }
 
+namespace {
+// copy cached positions [p0, p1) of every (layer, K|V, kv head) segment from slot src to slot dst
+int copy_kv_range(dtk_engine* eng, int src, int dst, int p0, int p1, cudaStream_t s) {
+  if (p1 <= p0) return DTK_OK;
+  const dtk_config& c = eng->cfg;
+  const size_t pitch = (size_t)c.max_len * 128 * sizeof(bf16);
+  DTK_CK(cudaMemcpy2DAsync(kv_layer(eng, dst, 0) + (int64_t)p0 * 128, pitch, kv_layer(eng, src, 0) + (int64_t)p0 * 128, pitch,
+                           (size_t)(p1 - p0) * 128 * sizeof(bf16), (size_t)c.layers * 2 * c.kv_heads, cudaMemcpyDeviceToDevice, s));
+  return DTK_OK;
+}
+void drop_share(dtk_engine* eng, int slot) {
+  const int b = eng->share_base[slot];
+  if (b >= 0) {
+    if (--eng->refcnt[b] == 0) eng->shared_upto[b] = 0;
+    eng->share_base[slot] = -1;
+    eng->share_len[slot] = 0;
+  }
+}
+}  // namespace
+
 int dtk_seq_alloc(dtk_engine* eng, int* slot) {
   if (!eng || !slot) return DTK_ERR_INVALID;
   for (size_t i = 0; i < eng->slot_used.size(); ++i)
@@ -729,6 +764,8 @@ int dtk_seq_alloc(dtk_engine* eng, int* slot) {
 int dtk_seq_free(dtk_engine* eng, int slot) {
   if (!eng) return DTK_ERR_INVALID;
   DTK_REQUIRE(slot >= 0 && slot < (int)eng->slot_used.size() && eng->slot_used[slot], "slot");
+  DTK_REQUIRE(eng->refcnt[slot] == 0, "slot still lends a shared prefix to other sequences (free them first)");
+  drop_share(eng, slot);
   eng->slot_used[slot] = 0;
   return DTK_OK;
 }
@@ -738,13 +775,45 @@ int dtk_seq_fork(dtk_engine* eng, int src, int dst, int len, void* stream) {
   const dtk_config& c = eng->cfg;
   DTK_REQUIRE(src >= 0 && src < c.max_seqs && dst >= 0 && dst < c.max_seqs && src != dst, "slots");
   DTK_REQUIRE(len >= 0 && len <= c.max_len, "len");
-  if (len == 0) return DTK_OK;
+  DTK_REQUIRE(eng->refcnt[dst] == 0, "destination lends a shared prefix to other sequences");
   DTK_CK(cudaSetDevice(eng->device));
-  // rows = layers * 2 * kv_heads segments of [max_len, 128]; copy the first len positions of each
-  const size_t pitch = (size_t)c.max_len * 128 * sizeof(bf16);
-  DTK_CK(cudaMemcpy2DAsync(kv_layer(eng, dst, 0), pitch, kv_layer(eng, src, 0), pitch, (size_t)len * 128 * sizeof(bf16),
-                           (size_t)c.layers * 2 * c.kv_heads, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return DTK_OK;
+  drop_share(eng, dst);          // the copy makes dst self-contained
+  if (len == 0) return DTK_OK;
+  // positions below src's shared length live in its base slot
+  const int sl = eng->share_len[src] < len ? eng->share_len[src] : len;
+  int r = DTK_OK;
+  if (sl > 0) r = copy_kv_range(eng, eng->share_base[src], dst, 0, sl, (cudaStream_t)stream);
+  if (r == DTK_OK) r = copy_kv_range(eng, src, dst, sl, len, (cudaStream_t)stream);
+  return r;
+}
+
+int dtk_seq_share(dtk_engine* eng, int base, int dst, int len, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  const dtk_config& c = eng->cfg;
+  DTK_REQUIRE(base >= 0 && base < c.max_seqs && dst >= 0 && dst < c.max_seqs && base != dst, "slots");
+  DTK_REQUIRE(eng->slot_used[base] && eng->slot_used[dst], "slots must be allocated");
+  DTK_REQUIRE(len >= 0 && len <= c.max_len, "len");
+  DTK_REQUIRE(eng->refcnt[dst] == 0, "destination lends a shared prefix to other sequences");
+  DTK_CK(cudaSetDevice(eng->device));
+  drop_share(eng, dst);
+  if (len == 0) return DTK_OK;
+  // one level only: if `base` itself borrows [0, L0) from a root slot, dst borrows that part from the root too
+  int root = base, rootlen = len;
+  if (eng->share_base[base] >= 0) {
+    root = eng->share_base[base];
+    rootlen = len < eng->share_len[base] ? len : eng->share_len[base];
+  }
+  const int s16 = rootlen & ~15;               // the decode kernel streams the cache in 16-position items
+  if (s16 > 0) {
+    eng->share_base[dst] = root;
+    eng->share_len[dst] = s16;
+    ++eng->refcnt[root];
+    if (eng->shared_upto[root] < s16) eng->shared_upto[root] = s16;
+  }
+  // the remainder [s16, len) becomes dst's own copy: from the root up to rootlen, from base beyond
+  int r = copy_kv_range(eng, root, dst, s16, rootlen, (cudaStream_t)stream);
+  if (r == DTK_OK && root != base) r = copy_kv_range(eng, base, dst, rootlen, len, (cudaStream_t)stream);
+  return r;
 }
 
 int dtk_prefill(dtk_engine* eng, int slot, const int64_t* ids, int T, int start_pos, const float* img_embeds,
@@ -754,6 +823,8 @@ int dtk_prefill(dtk_engine* eng, int slot, const int64_t* ids, int T, int start_
   DTK_REQUIRE(ids && T > 0, "ids/T");
   DTK_REQUIRE(slot >= 0 && slot < c.max_seqs, "slot");
   DTK_REQUIRE(start_pos >= 0 && start_pos + T <= c.max_len, "start_pos + T exceeds max_len");
+  DTK_REQUIRE(start_pos >= eng->share_len[slot], "start_pos lies inside the sequence's shared (read-only) prefix");
+  DTK_REQUIRE(start_pos >= eng->shared_upto[slot], "start_pos lies inside a prefix other sequences share from this slot");
   DTK_CK(cudaSetDevice(eng->device));
   cudaStream_t s = (cudaStream_t)stream;
   uint64_t* lc = &eng->launches;
@@ -780,6 +851,11 @@ int dtk_prefill(dtk_engine* eng, int slot, const int64_t* ids, int T, int start_
       a.o_bs = 0; a.o_hs = 128; a.o_rs = qd;
       a.B = 1; a.heads = c.heads; a.kv_group = c.heads / c.kv_heads; a.Tq = T; a.Tk = start_pos + T; a.q_pos0 = start_pos;
       a.causal = 1; a.head_dim = 128; a.scale = 1.0f / sqrtf(128.f);
+      if (eng->share_len[slot] > 0) {   // keys below the shared length come from the base slot
+        a.k2 = kv_layer(eng, eng->share_base[slot], l);
+        a.v2 = a.k2 + eng->kv_v_offset;
+        a.split_row = eng->share_len[slot];
+      }
       DTK_CK(launch_flash_attn(a, s, lc));
     }
     {
@@ -830,12 +906,16 @@ int dtk_decode(dtk_engine* eng, const int* slots, const int* positions, const in
   for (int i = 0; i < B; ++i) {
     DTK_REQUIRE(slots[i] >= 0 && slots[i] < c.max_seqs, "slot");
     DTK_REQUIRE(positions[i] >= 0 && positions[i] < c.max_len, "position exceeds max_len");
+    DTK_REQUIRE(positions[i] >= eng->share_len[slots[i]], "position lies inside the sequence's shared (read-only) prefix");
+    DTK_REQUIRE(positions[i] >= eng->shared_upto[slots[i]], "position lies inside a prefix other sequences share from this slot");
     st.slots[i] = slots[i];
     st.pos[i] = positions[i];
+    st.share_slot[i] = eng->share_base[slots[i]] >= 0 ? eng->share_base[slots[i]] : slots[i];
+    st.share_len[i] = eng->share_len[slots[i]];
   }
   DTK_CK(cudaSetDevice(eng->device));
   cudaStream_t s = (cudaStream_t)stream;
-  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok);
+  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len);
   ++eng->launches;
   DTK_CK(cudaGetLastError());
   return decode_launches(eng, B, ids, logits, s);
@@ -872,9 +952,12 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
   for (int i = 0; i < B; ++i) {
     DTK_REQUIRE(slots[i] >= 0 && slots[i] < c.max_seqs, "slot");
     DTK_REQUIRE(positions[i] >= 0 && positions[i] < c.max_len, "position exceeds max_len");
+    DTK_REQUIRE(positions[i] >= eng->share_len[slots[i]] && positions[i] >= eng->shared_upto[slots[i]], "position lies inside a shared prefix");
     st.slots[i] = slots[i]; st.pos[i] = positions[i]; st.tok[i] = first_ids_host[i];
+    st.share_slot[i] = eng->share_base[slots[i]] >= 0 ? eng->share_base[slots[i]] : slots[i];
+    st.share_len[i] = eng->share_len[slots[i]];
   }
-  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok);
+  set_state_kernel<<<1, 64, 0, s>>>(st, eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len);
   reset_gen_kernel<<<1, 1, 0, s>>>(eng->d_gen, eng->d_counters + (int64_t)c.max_batch * c.heads, params->seed);
   eng->launches += 2;
   DTK_CK(cudaGetLastError());
@@ -1026,6 +1109,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "mega_debug") == 0) {
     eng->mega_debug = value ? 1 : 0;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "mega_variant") == 0) {  // dev A/B switches of the persistent kernel (results identical)
+    eng->mega_variant = (int)value;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_trace_layer") == 0) {  // dev: per-tile clock trace of this layer (-1 = off); needs mega_debug

@@ -53,6 +53,10 @@ struct AttnArgs {
   int causal;
   int head_dim;               // 72 or 128
   float scale;
+  // shared KV prefix (prefill on a sequence that borrows positions [0, split_row) from another slot): key rows below
+  // split_row are read from k2 / v2 (same strides), the rest from k / v. split_row = 0: everything from k / v.
+  const bf16 *k2, *v2;
+  int split_row;
 };
 cudaError_t launch_flash_attn(const AttnArgs& a, cudaStream_t s, uint64_t* counter);
 
@@ -114,6 +118,8 @@ struct DecodeAttnArgs {
   int64_t kv_slot_stride, kv_v_offset;
   const int* slots;           // device int[B]
   const int* pos;             // device int[B]; keys [0, pos] are attended
+  const int* share_slot;      // device int[B]: slot that holds positions [0, share_len[b]) of sequence b (shared prefix)
+  const int* share_len;       // device int[B]: 0 = nothing shared
   int B, heads, kv_group, max_len, nsplit;
   float scale;
   float* part_o;              // [B, heads, nsplit, 128]
@@ -179,6 +185,7 @@ struct MegaArgs {
   int64_t norm_stride;
   MegaMat mat[5];                                             // qkv, o, gate/up, down (per layer) and lm_head
   const int *tok, *pos, *slots;                               // device state of the sequence being decoded
+  const int *share_slot, *share_len;                          // shared KV prefix: positions [0, share_len[0]) live in share_slot[0] (multiple of 16)
   bf16* kv;
   int64_t kv_slot_stride, kv_layer_stride, kv_v_offset;
   const float* rope_cs;
@@ -190,6 +197,7 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // arrival counter; bar_base[0] = arrivals, [1] = tag epoch of past launches
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
+  int variant;                                                // dev A/B switches (option "mega_variant"): bit 0 = coherent loads first when staging
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
   long long* dbg2;                                            // optional: [grid][MEGA_DBG2_ROWS][4] clock64 per-tile trace of layer dbg_layer

@@ -275,6 +275,10 @@ class Engine:
     def seq_fork(self, src: int, dst: int, length: int):
         self._check(self.lib.dtk_seq_fork(self._h, src, dst, length, self._stream()), "dtk_seq_fork")
 
+    def seq_share(self, base: int, dst: int, length: int):
+        """dst reads cached positions [0, length) from ``base`` (reference counted, no copy of whole 16-position blocks)."""
+        self._check(self.lib.dtk_seq_share(self._h, base, dst, length, self._stream()), "dtk_seq_share")
+
     # ------------------------------------------------------------------ decoder
     def prefill(self, slot: int, ids: torch.Tensor, start_pos: int = 0, img_embeds: Optional[torch.Tensor] = None,
                 img_start: int = 0, want_all_logits: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

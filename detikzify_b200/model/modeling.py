@@ -323,12 +323,23 @@ class DetikzifyForCausalLM:
                        bad_words_ids=None, begin_suppress_tokens=None, temperature: Optional[float] = None,
                        top_p: Optional[float] = None, top_k: Optional[int] = None, max_length: Optional[int] = None,
                        max_new_tokens: Optional[int] = None, do_sample: Optional[bool] = None, seed: Optional[int] = None,
-                       eos_token_id: Optional[int] = None) -> List[torch.Tensor]:
+                       eos_token_id: Optional[int] = None, streamers: Optional[Sequence[Any]] = None,
+                       stopping_criteria: Optional[Sequence[Any]] = None, share_prefix: bool = True,
+                       **ignored) -> List[torch.Tensor]:
         """N independent sequences decoded in lock-step: parallel MCTS rollouts of one figure (``pixel_values`` [1,3,S,S]
         shared) or N figures (``pixel_values`` [N,3,S,S]). One batched decode step per token — the decoder weights are
         streamed once per step for all N sequences instead of once per sequence — with the same logits processors and
         per-sequence RNG streams as N separate ``generate()`` calls (sequence i uses RNG stream i of ``seed``).
-        Every sequence stops at its own EOS / ``max_length``; returns a list of 1-D id tensors (prompt included).
+
+        Per-sequence host contract, as ``generate()`` has it for one sequence (reference util/generation.py:25-66 is batch-1
+        only): ``streamers[i]`` (or None) receives the prompt as ``[1, T0]`` once, every new token as a ``[1]`` tensor and
+        ``end()``; ``stopping_criteria[i]`` (a callable or a list of callables ``(input_ids [1,T], scores) -> bool``; one
+        shared entry is also accepted) is evaluated after every token of sequence i and stops only that sequence. Every
+        sequence also stops at its own EOS / ``max_length``; the loop ends when all have stopped.
+
+        With one shared image the longest common token prefix of the prompts (image span + tree path of an MCTS
+        expansion) is prefilled ONCE and lent to every sequence (``dtk_seq_share``: reference counted, read in place);
+        each sequence prefills only its own suffix. Returns a list of 1-D id tensors (prompt included).
         N is bounded by the engine's ``max_batch`` and free KV slots (``load(..., max_seqs=, max_batch=)``)."""
         cfg, eng = self.config, self.engine
         gc = self.generation_config
@@ -343,11 +354,31 @@ class DetikzifyForCausalLM:
             return []
         if any(len(p) == 0 for p in prompts):
             raise ValueError("empty prompt")
+        streamers = list(streamers) if streamers is not None else [None] * N
+        if len(streamers) != N:
+            raise ValueError("streamers must hold one entry (or None) per sequence")
+        crits: List[StoppingCriteriaList] = []
+        sc = list(stopping_criteria) if stopping_criteria is not None else []
+        per_seq = len(sc) == N and N > 1 or (len(sc) == N and all(isinstance(c, (list, tuple)) for c in sc))
+        for i in range(N):
+            c = sc[i] if per_seq else sc
+            crits.append(StoppingCriteriaList(c if isinstance(c, (list, tuple)) else [c]))
         limits = []
         for p in prompts:
             ml = max_length if max_length is not None else (len(p) + max_new_tokens if max_new_tokens is not None else gc.max_length)
             limits.append(min(int(ml), eng.max_len))
         patch = cfg.image_token_id
+
+        def spans(ids_host):
+            n = ids_host.count(patch)
+            if n == 0:
+                return 0, 0
+            if n != cfg.num_patches:   # splice validation (v1/modeling_detikzify.py:176-184)
+                raise ValueError("The number of image patch tokens should be the same as the number of image patches.")
+            st = ids_host.index(patch)
+            if ids_host[st: st + n] != [patch] * n:
+                raise ValueError("The image patch tokens should be consecutive.")
+            return st, n
 
         with self._lock, self._on_stream():
             imgs = None
@@ -358,25 +389,50 @@ class DetikzifyForCausalLM:
                 if pix.shape[0] not in (1, N):
                     raise ValueError("pixel_values must hold one image (shared) or one image per sequence")
                 imgs = eng.image_embeds(pix)
+            for i, st in enumerate(streamers):
+                if st is not None:
+                    st.put(torch.tensor([prompts[i]], dtype=torch.int64))
             slots: List[int] = []
+            base_slot = None
             try:
                 for _ in range(N):
                     slots.append(eng.seq_alloc())
+                # longest common prefix of the prompts (never splitting an image span, never a whole prompt)
+                lcp = 0
+                one_image = imgs is None or imgs.shape[0] == 1
+                if share_prefix and N > 1 and one_image:
+                    lim = min(len(p) for p in prompts) - 1
+                    while lcp < lim and all(p[lcp] == prompts[0][lcp] for p in prompts[1:]):
+                        lcp += 1
+                    st0, n0 = spans(prompts[0][:]) if imgs is not None else (0, 0)
+                    if n0 and st0 < lcp < st0 + n0:
+                        lcp = st0
+                    if lcp < 16:
+                        lcp = 0
+                if lcp:
+                    try:
+                        base_slot = eng.seq_alloc()
+                    except Exception:       # no spare slot: every sequence prefills its whole prompt
+                        base_slot, lcp = None, 0
+                if lcp:
+                    st0, n0 = spans(prompts[0]) if imgs is not None else (0, 0)
+                    head = torch.tensor(prompts[0][:lcp], dtype=torch.int64)
+                    if self.device.type == "cuda":
+                        head = head.pin_memory().to(self.device, non_blocking=True)
+                    eng.prefill(base_slot, head, 0, imgs[0] if (imgs is not None and n0 and st0 < lcp) else None, st0)
                 last = []
                 for i, ids_host in enumerate(prompts):
                     img, img_start = None, 0
-                    n_patch_tokens = ids_host.count(patch)
-                    if imgs is not None and n_patch_tokens > 0:   # splice validation (v1/modeling_detikzify.py:176-184)
-                        if n_patch_tokens != cfg.num_patches:
-                            raise ValueError("The number of image patch tokens should be the same as the number of image patches.")
-                        img_start = ids_host.index(patch)
-                        if ids_host[img_start: img_start + n_patch_tokens] != [patch] * n_patch_tokens:
-                            raise ValueError("The image patch tokens should be consecutive.")
-                        img = imgs[i if imgs.shape[0] == N else 0]
-                    ids_dev = torch.tensor(ids_host, dtype=torch.int64)
+                    if imgs is not None:
+                        img_start, n_patch = spans(ids_host)
+                        if n_patch and img_start >= lcp:
+                            img = imgs[i if imgs.shape[0] == N else 0]
+                    if lcp:
+                        eng.seq_share(base_slot, slots[i], lcp)
+                    ids_dev = torch.tensor(ids_host[lcp:], dtype=torch.int64)
                     if self.device.type == "cuda":
                         ids_dev = ids_dev.pin_memory().to(self.device, non_blocking=True)
-                    lg, _ = eng.prefill(slots[i], ids_dev, 0, img, img_start)
+                    lg, _ = eng.prefill(slots[i], ids_dev, lcp, img, img_start)
                     last.append(lg)
                 self._call_counter += 1
                 params = eng.sampling(
@@ -388,10 +444,17 @@ class DetikzifyForCausalLM:
                 toks = [int(t) for t in first.tolist()]
                 outs: List[List[int]] = [list(p) for p in prompts]
                 done = [len(p) >= lim for p, lim in zip(prompts, limits)]   # prompt already at max_length: nothing appended
+
+                def accept(i: int, tok: int):
+                    outs[i].append(tok)
+                    if streamers[i] is not None:
+                        streamers[i].put(torch.tensor([tok], dtype=torch.int64))
+                    cur = torch.tensor([outs[i]], dtype=torch.int64) if crits[i] else None
+                    done[i] = tok == eos or len(outs[i]) >= limits[i] or (bool(crits[i]) and crits[i](cur, None))
+
                 for i in range(N):
                     if not done[i]:
-                        outs[i].append(toks[i])
-                        done[i] = toks[i] == eos or len(outs[i]) >= limits[i]
+                        accept(i, toks[i])
                 max_steps = max(lim - len(p) for p, lim in zip(prompts, limits)) - 1
                 if not all(done) and max_steps > 0:
                     eng.gen_begin(slots, [len(p) for p in prompts], toks, params, seq_ids)
@@ -405,14 +468,20 @@ class DetikzifyForCausalLM:
                             waited += 1
                             for i in range(N):
                                 if not done[i]:          # finished sequences keep decoding on the device; the host ignores them
-                                    outs[i].append(int(row[i]))
-                                    done[i] = row[i] == eos or len(outs[i]) >= limits[i]
+                                    accept(i, int(row[i]))
                     finally:
                         eng.gen_end()
-                return [torch.tensor(o, dtype=torch.int64, device=self.device) for o in outs]
+                for st in streamers:
+                    if st is not None:
+                        st.end()
+                result = [torch.tensor(o, dtype=torch.int64, device=self.device) for o in outs]
+                self._sync()
+                return result
             finally:
                 for s in slots:
                     eng.seq_free(s)
+                if base_slot is not None:
+                    eng.seq_free(base_slot)
 
     # ---- SelfSim helper: pooled features straight from the engine --------------------------------
     @torch.no_grad()

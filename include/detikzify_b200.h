@@ -117,8 +117,14 @@ DTK_API int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out,
 /* ---- KV sequence slots (replaces DynamicCache, HF cache_utils). ---------- */
 DTK_API int dtk_seq_alloc(dtk_engine* eng, int* slot);
 DTK_API int dtk_seq_free(dtk_engine* eng, int slot);
-/* copy the first `len` cached positions of src into dst (MCTS prefix sharing) */
+/* copy the first `len` cached positions of src into dst (dst becomes self-contained) */
 DTK_API int dtk_seq_fork(dtk_engine* eng, int src_slot, int dst_slot, int len, void* stream);
+/* make dst READ the first `len` cached positions from base instead of holding a copy (MCTS rollouts of one figure share the
+ * image prefix and the tree path: detikzify/infer/generate.py:246-257,305-313 re-prefills them per rollout). The shared
+ * part is reference counted: base cannot be freed, nor rewritten below the shared length, while a borrower exists; dst
+ * writes only positions >= len. Whole 16-position blocks are shared, the remainder (< 16 positions) is copied into dst.
+ * One level: sharing from a slot that itself borrows resolves to the root slot. */
+DTK_API int dtk_seq_share(dtk_engine* eng, int base_slot, int dst_slot, int len, void* stream);
 
 /* ---- prefill. Replaces DetikzifyModel.forward splice + LlamaModel.forward + lm_head for a
  *      prompt (v1/modeling_detikzify.py:144-200,218-257). Processes ids[0..T) as positions

@@ -43,6 +43,10 @@ class ScriptedEngine:
         self.calls.append(("seq_fork", src, dst, length))
         self._hist[dst] = list(self._hist.get(src, [])[:length])
 
+    def seq_share(self, base, dst, length):
+        self.calls.append(("seq_share", base, dst, length))
+        self._hist[dst] = list(self._hist.get(base, [])[:length])
+
     def image_embeds(self, pix):
         self.calls.append(("image_embeds", tuple(pix.shape)))
         return torch.zeros(pix.shape[0], self.P, self.H)

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.dtk_abi_version() == 1
+    assert lib.dtk_abi_version() == 2
 
 
 @pytest.mark.parametrize("name,arena_gb", [("nllg/detikzify-ds-1.3b", 3.5637), ("nllg/detikzify-ds-7b", 14.3659)])

@@ -287,6 +287,38 @@ def test_generate_batch_equals_separate_generate_calls():
     assert set(eng._slots) == free_before                          # slots released
 
 
+def test_generate_batch_shared_prefix_streamers_and_per_sequence_stop():
+    """Rollouts of one figure: the common prefix (image span + tree path) is prefilled once and lent to every sequence
+    (seq_share), each sequence prefills only its suffix; every sequence feeds its own streamer (prompt once, tokens one by
+    one, end()) and obeys its own stopping criterion. Tokens equal separate generate() calls."""
+    from detikzify_b200.util import TokenStreamer
+    model, proc, eng = _model(eos_at=None)
+    pix = torch.rand(1, 3, 56, 56)
+    enc = proc(images=_figure(), text=None, return_tensors="pt")
+    path = torch.arange(40, 62)                                       # 22 shared path tokens after the 5 image tokens
+    prompts = [torch.cat([enc.input_ids[0], path, torch.arange(70 + 10 * i, 70 + 10 * i + 2 + i)]) for i in range(3)]
+    kw = dict(max_length=70, do_sample=False, bad_words_ids=[[model.config.image_token_id]],
+              begin_suppress_tokens=[model.config.eos_token_id])
+    singles = [model.generate(input_ids=p[None], pixel_values=pix, **kw)[0] for p in prompts]
+    eng.calls.clear()
+    free_before = set(eng._slots)
+    streamers = [TokenStreamer(skip_prompt=True), None, TokenStreamer(skip_prompt=False)]
+    stop_after = 4                                                    # sequence 1 stops after 4 new tokens
+    crit = [[], [lambda ids, scores: ids.shape[1] >= len(prompts[1]) + stop_after], []]
+    outs = model.generate_batch(prompts, pixel_values=pix, streamers=streamers, stopping_criteria=crit, **kw)
+    assert outs[0].tolist() == singles[0].tolist() and outs[2].tolist() == singles[2].tolist()
+    assert outs[1].tolist() == singles[1].tolist()[: len(prompts[1]) + stop_after]
+    assert list(streamers[0]) == outs[0].tolist()[len(prompts[0]):]
+    assert list(streamers[2]) == outs[2].tolist()                    # skip_prompt=False: prompt tokens first
+    shares = [c for c in eng.calls if c[0] == "seq_share"]
+    lcp = 5 + 22
+    assert len(shares) == 3 and all(c[3] == lcp for c in shares) and len({c[1] for c in shares}) == 1
+    pre = [c for c in eng.calls if c[0] == "prefill"]
+    assert pre[0][2:4] == (0, lcp) and pre[0][4]                      # the shared head, with the image, once
+    assert [c[2] for c in pre[1:]] == [lcp] * 3 and [c[3] for c in pre[1:]] == [2, 3, 4] and not any(c[4] for c in pre[1:])
+    assert set(eng._slots) == free_before
+
+
 def test_generate_batch_limits_and_validation():
     model, proc, eng = _model()
     enc = proc(images=_figure(), text=None, return_tensors="pt")

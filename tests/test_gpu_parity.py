@@ -122,3 +122,64 @@ def test_imagesim_on_cuda_tower_matches_oracle(mode):
         p0 = proc.image_processor(images=expand(load(ims[0]), max(ims[0].size), do_trim=True), return_tensors="pt")["pixel_values"]
         p1 = proc.image_processor(images=expand(load(ims[1]), max(ims[1].size), do_trim=True), return_tensors="pt")["pixel_values"]
         assert abs(oracle.selfsim_cos(p0, p1) - ref) < 1e-9
+
+
+def test_shared_prefix_rollouts_against_oracle():
+    """dtk_seq_share: four rollouts READ the first 41 positions (image span + path prefix) from one base slot — whole
+    16-position blocks shared, the 9-position remainder copied — then prefill their own suffixes and decode. Every logits
+    row (suffix prefill, batch-1 decode on both implementations, batched-GEMM decode of all four) is checked against the
+    oracle's full forward of the same token sequence; reference counting protects the base slot."""
+    from detikzify_b200.engine import EngineError
+    name = "tiny2"
+    cfg, sd, oracle = model_bundle(name)
+    eng = engine_for(name, max_seqs=8, max_batch=8)
+    pix = _pixels(cfg, 1)
+    img = eng.image_embeds(pix.cuda())[0]
+    P = cfg.num_patches
+    g = torch.Generator().manual_seed(4100)
+    hi = min(cfg.vocab_size, cfg.patch_token_id)
+    prefix = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, hi, (14,), generator=g)]).long()
+    cut = prefix.numel()
+    assert cut % 16 != 0
+    R = 4
+    suffixes = [torch.randint(0, hi, (5 + 3 * i,), generator=g) for i in range(R)]
+    toks = torch.randint(0, hi, (R,), generator=g)
+    base = eng.seq_alloc()
+    subs = [eng.seq_alloc() for _ in range(R)]
+    try:
+        eng.prefill(base, prefix.cuda(), 0, img, 0)
+        refs, lens = [], []
+        for s, suf in zip(subs, suffixes):
+            eng.seq_share(base, s, cut)
+            last, _ = eng.prefill(s, suf.cuda(), cut, None, 0)
+            full = torch.cat([prefix, suf])
+            ref, _ = oracle.forward_logits(torch.cat([full, toks[len(refs):len(refs) + 1]])[None], pix)
+            assert (last.cpu() - ref[0, -2]).abs().max().item() < TOL
+            refs.append(ref[0, -1]); lens.append(full.numel())
+        # the base is protected while borrowers exist
+        with pytest.raises(EngineError):
+            eng.seq_free(base)
+        with pytest.raises(EngineError):
+            eng.prefill(base, prefix[:8].cuda(), 4, None, 0)
+        for impl in (1, 0):
+            eng.set_option("decode_impl", impl)
+            for i in (0, R - 1):
+                lg = eng.decode([subs[i]], [lens[i]], toks[i:i + 1].cuda())[0].cpu()
+                assert (lg - refs[i]).abs().max().item() < TOL, (impl, i)
+        eng.set_option("decode_impl", 1)
+        batched = eng.decode(subs, lens, toks.cuda())
+        for i in range(R):
+            assert (batched[i].cpu() - refs[i]).abs().max().item() < TOL, i
+        # a fork of a borrower is self-contained
+        extra = eng.seq_alloc()
+        try:
+            eng.seq_fork(subs[1], extra, lens[1])
+            lg = eng.decode([extra], [lens[1]], toks[1:2].cuda())[0].cpu()
+            assert (lg - refs[1]).abs().max().item() < TOL
+        finally:
+            eng.seq_free(extra)
+    finally:
+        eng.set_option("decode_impl", 1)
+        for s in subs:
+            eng.seq_free(s)
+        eng.seq_free(base)

@@ -25,9 +25,12 @@ def timeit(label):
 import subprocess
 print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 timeit("default")
-for flags in (1, 2, 4, 0):
+for variant in (1, 0, 1, 0):
+    eng.set_option("mega_variant", variant)
+    timeit(f"variant={variant} (bit 0: coherent loads first when staging)")
+for flags in (1, 2, 0):
     eng.set_option("mega_flags", flags)
-    timeit(f"flags={flags} (1=no mma, 2=no grid barrier, 4=relaxed arrive)")
+    timeit(f"flags={flags} (1=no mma, 2=no waiting at all)")
 print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 eng.set_option("mega_debug", 1)
 eng.decode([slot], [ctx], tok)
