@@ -53,6 +53,22 @@ class ImageSim:
         f1, f2 = self.get_vision_features(img1), self.get_vision_features(img2)
         return F.cosine_similarity(f1.double(), f2.double(), dim=0).item()
 
+    def get_similarities(self, candidates: List[Union[Image.Image, str]], reference: Union[Image.Image, str]) -> List[float]:
+        """SelfSim of several candidate renders against one reference figure: all images go through ONE batched ViT pass
+        (the renders of a batch of parallel MCTS rollouts), the fp64 cosines are taken on the device and read back with a
+        single transfer. Same values as ``get_similarity`` per pair (reference evaluate/imagesim.py:91-125)."""
+        pix = []
+        for image in [reference, *candidates]:
+            image = load(image)
+            if self.preprocess:
+                image = expand(image, max(image.size), do_trim=True)
+            pix.append(self.processor(images=image, return_tensors="pt")["pixel_values"])
+        with torch.inference_mode():
+            out = self.model(pixel_values=torch.cat(pix))
+            feats = out.pooler_output if self.mode == "cos" else out.last_hidden_state.mean(dim=1)
+            feats = feats.double()
+            return F.cosine_similarity(feats[1:], feats[:1].expand_as(feats[1:]), dim=1).tolist()
+
     def update(self, img1=None, img2=None, text1=None, text2=None):
         imgs1 = img1 if isinstance(img1, list) else [img1]
         imgs2 = img2 if isinstance(img2, list) else [img2]

@@ -24,7 +24,6 @@ from collections import deque
 from dataclasses import dataclass
 from functools import cached_property
 from math import sqrt
-from multiprocessing.pool import ThreadPool
 from time import time
 from types import SimpleNamespace
 from typing import Any, Dict, Generator, List, Optional, Set, Tuple, Union
@@ -146,20 +145,77 @@ class DynMinMaxNorm:
         __radd__, __rmul__ = __add__, __mul__
 
 
+class LineTracker:
+    """Per-sequence observer of one rollout, run by ``model.generate_batch`` as that sequence's stopping criterion (called
+    with the ids so far after every new token). It cuts the token stream into source lines — one candidate tree node per
+    completed line, as the reference's ``rollout`` generator yields them (detikzify/infer/generate.py:246-282) — and stops
+    its sequence as soon as the prefix is one that is already known to fail (``failed_rollouts`` memo, :318-323) or the
+    shared abort flag is raised. Unlike the reference's streamer + worker-thread construction this needs no thread per
+    rollout, which is what lets K rollouts advance in one lock-step batch."""
+
+    def __init__(self, start: NodeState, newlineinfo: Dict[int, Any], failed: Dict[NodeState, List["WideNode"]],
+                 control: ExplicitAbort, exploration: float):
+        self.prefix: List[int] = start.token_ids.tolist()
+        self.device = start.token_ids.device
+        self.num_lines, self.continuation = start.num_lines, False
+        self.newlineinfo, self.failed, self.control, self.exploration = newlineinfo, failed, control, exploration
+        self.line: List[int] = []
+        self.nodes: List[WideNode] = []
+        self.memo_hit = False
+
+    def _node(self, num_lines: int) -> "WideNode":
+        self.prefix.extend(self.line)
+        self.line.clear()
+        return WideNode(torch.tensor(self.prefix, device=self.device), num_lines, exploration=self.exploration)
+
+    def __call__(self, input_ids, scores=None, **_) -> bool:
+        token = int(input_ids[0, -1])
+        self.line.append(token)
+        info = self.newlineinfo.get(token)
+        if info:
+            self.num_lines += info.num_lines - self.continuation
+            self.continuation = not info.trailing
+            cand = self._node(self.num_lines)
+            known = self.failed.get(cand.state)
+            if known is not None:          # this prefix ran into a compile error before: reuse its continuation
+                self.nodes.extend(known)
+                self.memo_hit = True
+                return True
+            self.nodes.append(cand)
+        return self.control.should_stop
+
+    def finish(self) -> List["WideNode"]:
+        if self.line and not self.memo_hit:   # trailing text without a newline
+            self.nodes.append(self._node(self.num_lines - self.continuation))
+        return self.nodes
+
+
 class DetikzifyGenerator:
+    """MCTS over TikZ source lines with the reference's search semantics (detikzify/infer/generate.py:145-353) — one
+    expansion = one rollout from the chosen node's token prefix, a tree node per generated line, sqrt(n) node thinning,
+    failed-rollout memo keyed by token prefix, error-line pruning, min-max normalised SelfSim reward, widen nodes — but
+    organised around BATCHED expansions: ``rollouts`` leaves are selected per step (virtual visits keep the selections
+    apart), rolled out together by ``model.generate_batch`` (one weight stream per decode step for all of them, the image
+    span + common tree path prefilled once and shared), compiled, scored in one ViT batch and back-propagated.
+    ``rollouts=1`` reproduces the reference's one-rollout-per-expansion schedule."""
+
     def __init__(self, model, processor, image: Optional[Image.Image], text: Optional[str] = None, metric=None,
                  compile_timeout: Optional[int] = 60, mcts_timeout: Optional[int] = None, streamer=None,
-                 control: Optional[ExplicitAbort] = None, exploration: float = 0.6, strict: bool = False, **gen_kwargs):
+                 control: Optional[ExplicitAbort] = None, exploration: float = 0.6, strict: bool = False,
+                 rollouts: int = 1, **gen_kwargs):
         self.model, self.processor = model, processor
         self.metric, self.image, self.text = metric, image, text
         self.compile_timeout, self.mcts_timeout = compile_timeout, mcts_timeout
         self.streamer, self.exploration, self.strict = streamer, exploration, strict
+        self.rollouts = max(1, int(rollouts))
         self.gen_kwargs = gen_kwargs
-        self.solution: deque = deque(maxlen=1)
+        self.solution: deque = deque()
         self.failed_rollouts: Dict[NodeState, List[WideNode]] = dict()
         self.norm = DynMinMaxNorm()
         self.control = control or ExplicitAbort()
-        root_ids = processor(images=self.image, text=self.text, return_tensors="pt").input_ids.to(model.device).squeeze()
+        enc = processor(images=self.image, text=self.text, text_kwargs={"truncation": True}, return_tensors="pt")
+        self.pixel_values = enc.get("pixel_values")       # preprocessed once per figure (the reference re-runs it per rollout)
+        root_ids = enc.input_ids.to(model.device).squeeze()
         self.montecarlo = MonteCarlo(root_node=WideNode(root_ids, exploration=self.exploration))
         self.montecarlo.child_finder = self.child_finder
         self.decode = cache_cast(lambda token_ids: tuple(token_ids.tolist()))(self.decode)
@@ -168,34 +224,47 @@ class DetikzifyGenerator:
     def __call__(self, *args, **kwargs):
         return self.simulate(*args, **kwargs)
 
+    # ---- public driver --------------------------------------------------------------------------------------------
     def simulate(self, expansions: Optional[Numeric] = 1) -> Generator[Tuple[Numeric, TikzDocument], None, None]:
-        """Yield every rollout (successful or not) as (score, document); reference :197-207."""
+        """Yield every rollout (successful or not) as (score, document); reference :197-207. ``expansions`` counts
+        rollouts; with ``rollouts = K`` they are produced K at a time."""
         start = time()
-        while expansions is None or (expansions := expansions - 1) >= 0:
-            self.montecarlo.simulate()
-            yield self.solution.pop()
+        remaining = expansions
+        while remaining is None or remaining > 0:
+            k = self.rollouts if remaining is None else int(min(self.rollouts, remaining))
+            self.expand_batch(k)
+            while self.solution:
+                yield self.solution.popleft()
+            if remaining is not None:
+                remaining -= k
             if self.mcts_timeout is not None and time() - start > self.mcts_timeout:
                 return
 
+    def sample(self):
+        return self.decode(self.generate(input_ids=self.montecarlo.root_node.token_ids))
+
     def generate(self, input_ids: torch.Tensor, streamer=None, **gen_kwargs) -> torch.Tensor:
-        """One ``model.generate`` call continuing ``input_ids`` (reference :209-227)."""
+        """One batch-1 ``model.generate`` call continuing ``input_ids`` (reference :209-227)."""
         streamers = StreamerList(filter(bool, [streamer, self.streamer]))
         numel = input_ids.numel()
-        max_length = {**self.model.generation_config.to_dict(), **self.gen_kwargs, **gen_kwargs}["max_length"]
-        if (numel and input_ids[-1] == unwrap(self.processor).tokenizer.eos_token_id) or numel >= max_length:
+        if self._exhausted(input_ids, gen_kwargs):
             streamers.end()
             return input_ids  # never continue past EOS / the length budget
         with torch.inference_mode():
-            enc = self.processor(images=self.image, text=self.text, text_kwargs={"truncation": True}, return_tensors="pt")
             return self.model.generate(
                 input_ids=input_ids.unsqueeze(0),
                 bad_words_ids=[[self.model.config.image_token_id]],
                 begin_suppress_tokens=[self.model.config.text_config.eos_token_id],
-                pixel_values=enc.get("pixel_values"),
+                pixel_values=self.pixel_values,
                 streamer=streamers,
                 **self.gen_kwargs,
                 **gen_kwargs,
             ).squeeze()
+
+    def _exhausted(self, input_ids: torch.Tensor, gen_kwargs=None) -> bool:
+        max_length = {**self.model.generation_config.to_dict(), **self.gen_kwargs, **(gen_kwargs or {})}["max_length"]
+        numel = input_ids.numel()
+        return bool((numel and input_ids[-1] == unwrap(self.processor).tokenizer.eos_token_id) or numel >= max_length)
 
     @cached_property
     def newlineinfo(self):
@@ -207,35 +276,6 @@ class DetikzifyGenerator:
                 info[token_id] = SimpleNamespace(num_lines=n, trailing=token.endswith("\n"))
         assert info
         return info
-
-    def rollout(self, state: NodeState) -> Generator[Tuple[torch.Tensor, int], None, None]:
-        """Generate from ``state`` on a worker thread; yield (prefix ids, #lines) at every newline token."""
-        input_ids, num_lines, continuation = state.token_ids, state.num_lines, False
-        with ThreadPool(processes=1) as thread:
-            streamer = TokenStreamer()
-            result = thread.apply_async(
-                func=self.generate, error_callback=streamer.propagate_error, args=[input_ids],
-                kwds=dict(stopping_criteria=StoppingCriteriaList([self.control.reset()]), streamer=streamer))
-            try:
-                prev_ids, line = input_ids, list()
-                for token in streamer:
-                    line.append(token)
-                    if info := self.newlineinfo.get(token):
-                        num_lines += info.num_lines - continuation
-                        continuation = not info.trailing
-                        prev_ids = torch.cat((prev_ids, torch.tensor(line, device=prev_ids.device)))
-                        line.clear()
-                        yield prev_ids, num_lines
-                if line:
-                    yield torch.cat((prev_ids, torch.tensor(line, device=prev_ids.device))), num_lines - continuation
-            except (GeneratorExit, KeyboardInterrupt):
-                self.control.abort()
-                raise
-            else:
-                if self.control.should_stop:
-                    raise InterruptedError
-            finally:
-                result.wait()
 
     def decode(self, token_ids: torch.Tensor) -> TikzDocument:
         return TikzDocument(
@@ -249,24 +289,53 @@ class DetikzifyGenerator:
         self.metric.reset()
         return value
 
-    def sample(self):
-        return self.decode(self.generate(input_ids=self.montecarlo.root_node.token_ids))
+    # ---- one batch of expansions ------------------------------------------------------------------------------------
+    def _select(self, k: int) -> List[WideNode]:
+        """k leaves by repeated tree descent; every pick leaves a virtual visit on its path so that the next descent
+        sees a lower exploration bonus there (undone before the real update)."""
+        picks: List[WideNode] = []
+        for _ in range(k):
+            node = self.montecarlo.root_node
+            while node.expanded:
+                node = node.get_preferred_child(self.montecarlo.root_node)
+            picks.append(node)
+            cur: Optional[WideNode] = node
+            while cur is not None:
+                cur.visits += 1
+                cur = cur.parent
+        for node in picks:
+            cur = node
+            while cur is not None:
+                cur.visits -= 1
+                cur = cur.parent
+        return picks
 
-    # ---- one MCTS expansion (reference :305-343), split into its three concerns ---------------------
-    def _rollout_nodes(self, start: WideNode) -> List[WideNode]:
-        """Roll out from ``start`` and turn every completed source line into a candidate node; a prefix
-        already known to fail short-circuits the rollout with its memoised continuation."""
-        nodes: List[WideNode] = []
-        stream = self.rollout(start.state)
-        for ids, n_lines in stream:
-            cand = WideNode(ids, n_lines, exploration=self.exploration)
-            known = self.failed_rollouts.get(cand.state)
-            if known is not None:
-                nodes.extend(known)
-                stream.close()
-                break
-            nodes.append(cand)
-        return nodes
+    def _rollout_batch(self, starts: List[WideNode]) -> List[List[WideNode]]:
+        """Roll out from every start node; returns the candidate nodes (one per completed line) of each rollout."""
+        trackers = [LineTracker(n.state, self.newlineinfo, self.failed_rollouts, self.control.reset() if i == 0 else self.control,
+                                self.exploration) for i, n in enumerate(starts)]
+        live = [i for i, n in enumerate(starts) if not self._exhausted(n.token_ids)]
+        if live:
+            streamers = [self.streamer if (i == live[0]) else None for i in live]   # an external streamer follows the first rollout
+            with torch.inference_mode():
+                if len(live) == 1 or not hasattr(self.model, "generate_batch"):
+                    for i, st in zip(live, streamers):
+                        self.model.generate(
+                            input_ids=starts[i].token_ids.unsqueeze(0), pixel_values=self.pixel_values,
+                            bad_words_ids=[[self.model.config.image_token_id]],
+                            begin_suppress_tokens=[self.model.config.text_config.eos_token_id],
+                            streamer=st, stopping_criteria=StoppingCriteriaList([trackers[i]]), **self.gen_kwargs)
+                else:
+                    self.model.generate_batch(
+                        [starts[i].token_ids for i in live], pixel_values=self.pixel_values,
+                        bad_words_ids=[[self.model.config.image_token_id]],
+                        begin_suppress_tokens=[self.model.config.text_config.eos_token_id],
+                        streamers=streamers, stopping_criteria=[[trackers[i]] for i in live], **self.gen_kwargs)
+        elif self.streamer is not None:
+            self.streamer.end()
+        if self.control.should_stop:
+            raise InterruptedError
+        return [t.finish() for t in trackers]
 
     def _graft(self, anchor: WideNode, nodes: List[WideNode], tikz: TikzDocument, scorable: bool) -> WideNode:
         """Attach (a thinned subset of) the rollout's nodes below ``anchor``; returns the deepest attached node."""
@@ -289,20 +358,55 @@ class DetikzifyGenerator:
                     break
         return anchor
 
+    def _rewards(self, docs: List[TikzDocument], scorable: List[bool]) -> List[Numeric]:
+        """SelfSim rewards of the scorable documents in ONE batched ViT pass when the metric can do that
+        (``ImageSim.get_similarities``); compiler-diagnostic reward without a metric (reference :334-339)."""
+        if not self.metric:
+            return [ok - d.compiled_with_errors for d, ok in zip(docs, scorable)]
+        rewards: List[Numeric] = [-1] * len(docs)
+        idx = [i for i, ok in enumerate(scorable) if ok]
+        if len(idx) > 1 and hasattr(self.metric, "get_similarities"):
+            values = self.metric.get_similarities([docs[i].rasterize() for i in idx], self.image)
+            for i, v in zip(idx, values):
+                rewards[i] = v
+        else:
+            for i in idx:
+                rewards[i] = self.score(docs[i].rasterize())
+        return rewards
+
+    def expand_batch(self, k: int = 1, starts: Optional[List[WideNode]] = None) -> None:
+        starts = starts if starts is not None else self._select(k)
+        rollouts = self._rollout_batch(starts)
+        anchors, tails, docs = [], [], []
+        for node, nodes in zip(starts, rollouts):
+            if node.is_widen_node:           # the twin stands for "sample another continuation of my parent"
+                node.visits += 1
+                node, nodes = self.merge(node.parent, nodes)
+            anchors.append(node)
+            tails.append(nodes)
+            docs.append(self.decode((nodes or [node])[-1].token_ids))
+        scorable = [bool(d.is_rasterizable and not (self.strict and d.compiled_with_errors)) for d in docs]
+        rewards = self._rewards(docs, scorable)
+        for node, nodes, tikz, ok, reward in zip(anchors, tails, docs, scorable, rewards):
+            if nodes and nodes[0].parent is None and any(ch.state == nodes[0].state for ch in node.children):
+                node, nodes = self.merge(node, nodes)     # two rollouts of this batch started with the same line(s)
+            node = self._graft(node, nodes, tikz, ok)
+            node.update_win_value(self.norm(reward) if ok and self.metric else reward)
+            self.solution.append((reward, tikz))
+        for node in starts:   # MonteCarlo.expand's bookkeeping (mcts/montecarlo.py): a node with children is inner from now on
+            self.montecarlo.stats_expansion_count += 1   # (every real node carries its widen twin, widen nodes stay leaves)
+            if node.children:
+                node.expanded = True
+            else:
+                self.montecarlo.stats_failed_expansion_count += 1
+
     def child_finder(self, node: WideNode, montecarlo: MonteCarlo):
-        nodes = self._rollout_nodes(node)
-        if node.is_widen_node:           # the twin stands for "sample another continuation of my parent"
-            node.visits += 1
-            node, nodes = self.merge(node.parent, nodes)
-        tikz = self.decode((nodes or [node])[-1].token_ids)
-        scorable = bool(tikz.is_rasterizable and not (self.strict and tikz.compiled_with_errors))
-        node = self._graft(node, nodes, tikz, scorable)
-        if self.metric:
-            reward = self.score(tikz.rasterize()) if scorable else -1
-        else:                            # no metric: reward from compiler diagnostics
-            reward = scorable - tikz.compiled_with_errors
-        node.update_win_value(self.norm(reward) if scorable and self.metric else reward)
-        self.solution.append((reward, tikz))
+        """``MonteCarlo.expand`` hook (reference :305-343): one sequential expansion of ``node`` (the caller does the
+        expansion bookkeeping itself)."""
+        count, failed = montecarlo.stats_expansion_count, montecarlo.stats_failed_expansion_count
+        was = node.expanded
+        self.expand_batch(1, starts=[node])
+        montecarlo.stats_expansion_count, montecarlo.stats_failed_expansion_count, node.expanded = count, failed, was
 
     def merge(self, node: WideNode, nodes_to_merge: List[WideNode]) -> Tuple[WideNode, List[WideNode]]:
         """Walk down existing children that coincide with the head of the new rollout."""
@@ -353,6 +457,7 @@ class DetikzifyPipeline:
             image=self.load(image, preprocess=preprocess) if image is not None else None, text=text,
             **self.gen_kwargs, **gen_kwargs)
         yield from generator.simulate(expansions or None)
+
 
     def sample_batch(self, images, preprocess: bool = True, samples_per_image: int = 1, **gen_kwargs) -> List[TikzDocument]:
         """Extension (the reference samples one figure at a time): DeTikZify several figures — and/or draw several samples

@@ -190,6 +190,30 @@ def test_pipeline_sample_and_mcts_simulate(monkeypatch):
         pipe.sample(image=_figure(), text="caption")          # no adapter loaded
 
 
+def test_mcts_batched_expansions(monkeypatch):
+    """rollouts=K: K leaves are expanded per step through ONE generate_batch call (one gen loop over K slots, the common
+    prefix shared), rewards come from one batched SelfSim pass, and the tree grows as with sequential expansions."""
+    from detikzify_b200.infer import DetikzifyPipeline, TikzDocument
+    from detikzify_b200.infer.pipeline import DetikzifyGenerator
+    model, proc, eng = _model(eos_at=40)
+    monkeypatch.setattr(TikzDocument, "backend", staticmethod(_fake_renderer()))
+    pipe = DetikzifyPipeline(model, proc, metric="model")
+    gen = DetikzifyGenerator(model=model, processor=proc, image=pipe.load(_figure()), metric=pipe.metric, rollouts=3,
+                             **{k: v for k, v in pipe.gen_kwargs.items() if k != "compile_timeout"}, compile_timeout=5)
+    eng.calls.clear()
+    results = list(gen.simulate(expansions=6))
+    assert len(results) == 6 and all(-1.0 <= sc <= 1.0 + 1e-9 and doc.is_rasterizable for sc, doc in results)
+    begins = [c for c in eng.calls if c[0] == "gen_begin"]
+    assert len(begins) == 2 and all(len(b[1]) == 3 for b in begins)      # two steps of three lock-step rollouts
+    vits = [c for c in eng.calls if c[0] == "vit_encode"]
+    assert any(c[1][0] == 4 for c in vits)                               # reference + 3 candidate renders in one ViT batch
+    root = gen.montecarlo.root_node
+    assert root.visits == 6 and root.expanded
+    assert gen.montecarlo.stats_expansion_count == 6
+    real = [ch for ch in root.children if not ch.is_widen_node]
+    assert real and all(ch.parent is root for ch in real)
+
+
 def test_mcts_tree_growth_and_failed_rollout_memo(monkeypatch):
     from detikzify_b200.infer import DetikzifyGenerator, TikzDocument
     model, proc, eng = _model(eos_at=36)

@@ -118,6 +118,9 @@ def test_imagesim_on_cuda_tower_matches_oracle(mode):
     ref = F.cosine_similarity(feats[0].double(), feats[1].double(), dim=0).item()
     assert abs(got - ref) < 5e-3, (got, ref)
     assert abs(sim.get_similarity(ims[0], ims[0]) - 1.0) < 1e-6
+    # batched form (candidate renders of parallel rollouts through one ViT pass): same values as pair by pair
+    both = sim.get_similarities([ims[1], ims[0]], ims[0])
+    assert abs(both[0] - got) < 2e-3 and abs(both[1] - 1.0) < 1e-6
     if mode == "cos":
         p0 = proc.image_processor(images=expand(load(ims[0]), max(ims[0].size), do_trim=True), return_tensors="pt")["pixel_values"]
         p1 = proc.image_processor(images=expand(load(ims[1]), max(ims[1].size), do_trim=True), return_tensors="pt")["pixel_values"]
