@@ -214,8 +214,16 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
 template <int D, int DP, bool CAUSAL>
 cudaError_t launch_t(const AttnArgs& a, cudaStream_t s) {
   const int smem = AttnSmem<D, DP>::BYTES;
-  cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<D, DP, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // the attribute is per device; set once per device (not per launch: launches may be captured into a CUDA graph)
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(flash_attn_kernel<D, DP, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
   dim3 grid((a.Tq + BQ - 1) / BQ, a.heads, a.B);
   flash_attn_kernel<D, DP, CAUSAL><<<grid, ATHREADS, smem, s>>>(a);
   return cudaGetLastError();

@@ -166,6 +166,32 @@ DTK_DEV float settle1(u64 w, const u64* p, uint32_t tag, bool nowait) {
   return tag_val(w);
 }
 
+// N tagged pairs per thread: weak loads first, then every pair whose tag is still old is re-read coherently, all of them per
+// round (one L2 round trip per round however many are late)
+template <int N>
+DTK_DEV void ld_pairs(const u64* const (&ptr)[N], const bool (&on)[N], uint32_t tag, bool nowait, float2 (&out)[N]) {
+  ulonglong2 w[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u)
+    if (on[u]) w[u] = ld_weak2(ptr[u]);
+  Spin sp;
+  for (;;) {
+    bool bad[N], any = false;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      bad[u] = on[u] && !(tag_ok(w[u].x, tag) && tag_ok(w[u].y, tag));
+      any = any || bad[u];
+    }
+    if (!any || nowait) break;
+    sp.tick();
+#pragma unroll
+    for (int u = 0; u < N; ++u)
+      if (bad[u]) w[u] = ld_strong2(ptr[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) out[u] = on[u] ? make_float2(tag_val(w[u].x), tag_val(w[u].y)) : make_float2(0.f, 0.f);
+}
+
 // grid-wide arrival counter over the consumer threads of all CTAs (producer warps never take part): a HINT, not a memory
 // barrier — relaxed arrive, relaxed poll. It tells a CTA when the other CTAs have issued their tagged stores.
 DTK_DEV void hint_barrier(unsigned long long* counter, unsigned long long target, int flags) {
@@ -514,32 +540,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       // this head only.
       if (as.active) {
         const int hw = lane >> 4, l16 = lane & 15;
-        if (warp == 0) {
+        if (warp == 0) {   // one warp fetches q (and, in the head's last key range, the new key / value row): 64 pairs each
           const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 128^-1/2 * log2(e)
           float2* q2 = reinterpret_cast<float2*>(qkn);
           const u64* qsrc = t_q + as.head * 128;
-          ulonglong2 wq[2], wk[2], wv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) wq[u] = ld_weak2(qsrc + 2 * (lane + 32 * u));
-          if (as.last) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              wk[u] = ld_weak2(t_kn + kvh * 128 + 2 * (lane + 32 * u));
-              wv[u] = ld_weak2(t_vn + kvh * 128 + 2 * (lane + 32 * u));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float2 v = settle2(wq[u], qsrc + 2 * (lane + 32 * u), tag - 1, nowait);
-            q2[lane + 32 * u] = make_float2(v.x * sl2, v.y * sl2);
-          }
-          if (as.last) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              q2[64 + lane + 32 * u] = settle2(wk[u], t_kn + kvh * 128 + 2 * (lane + 32 * u), tag - 1, nowait);
-              q2[128 + lane + 32 * u] = settle2(wv[u], t_vn + kvh * 128 + 2 * (lane + 32 * u), tag - 1, nowait);
-            }
-          }
+          const u64* const ptr[6] = {qsrc + 2 * lane, qsrc + 2 * (lane + 32), t_kn + kvh * 128 + 2 * lane, t_kn + kvh * 128 + 2 * (lane + 32),
+                                     t_vn + kvh * 128 + 2 * lane, t_vn + kvh * 128 + 2 * (lane + 32)};
+          const bool lastr = as.last != 0;
+          const bool on[6] = {true, true, lastr, lastr, lastr, lastr};
+          float2 v[6];
+          ld_pairs<6>(ptr, on, tag - 1, nowait, v);
+          q2[lane] = make_float2(v[0].x * sl2, v[0].y * sl2);
+          q2[lane + 32] = make_float2(v[1].x * sl2, v[1].y * sl2);
+          if (lastr) { q2[64 + lane] = v[2]; q2[96 + lane] = v[3]; q2[128 + lane] = v[4]; q2[160 + lane] = v[5]; }
         }
         consumer_sync();   // q is staged; every warp is past its last qkv tile (the merge scratch below aliases the staged vector)
         stamp(1);
@@ -551,21 +564,42 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         float m = -INFINITY, lsum = 0.f, o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        auto key_update = [&](const float (&kf)[8], const float (&vf)[8], bool valid) {
-          float s2 = 0.f;
+        // online softmax over FOUR keys at a time (per half-warp): the four dot products and their shuffle reductions are
+        // independent chains, one rescale per batch instead of one per key
+        auto keys4 = [&](const uint4 (&kr)[4], const uint4 (&vr)[4], const bool (&valid)[4]) {
+          float s2[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s2 += q[i] * kf[i];
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-          if (valid) {
-            const float mn = fmaxf(m, s2), alpha = exp2f(m - mn), pj = exp2f(s2 - mn);
-            lsum = lsum * alpha + pj;
+          for (int u = 0; u < 4; ++u) {
+            float kf[8];
+            unpack8(kr[u], kf);
+            float d = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * vf[i];
-            m = mn;
+            for (int i = 0; i < 8; ++i) d += q[i] * kf[i];
+            s2[u] = d;
           }
+#pragma unroll
+          for (int st = 8; st > 0; st >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], st);
+          float mx = m;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { s2[u] = valid[u] ? s2[u] : -INFINITY; mx = fmaxf(mx, s2[u]); }
+          if (mx == -INFINITY) return;           // nothing valid so far
+          const float alpha = exp2f(m - mx);      // m = -inf -> 0
+          float pj[4], ps = 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { pj[u] = exp2f(s2[u] - mx); ps += pj[u]; }
+          lsum = lsum * alpha + ps;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= alpha;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float vf[8];
+            unpack8(vr[u], vf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += pj[u] * vf[i];
+          }
+          m = mx;
         };
         // ring items: 16 positions each; half-warp hw takes positions hw, hw + 2, ... of the item
         {
@@ -585,20 +619,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               cur_slot = sl;
               const uint32_t base = ring_u32 + sl * TILE_BYTES + l16 * 16;
               const int key0 = as.j0 + (int)j * 16;
-              uint4 kr[8], vr[8];
+              uint4 kr[2][4], vr[2][4];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const uint32_t a = base + (uint32_t)(u * 2 + hw) * 256u;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(kr[u].x), "=r"(kr[u].y), "=r"(kr[u].z), "=r"(kr[u].w) : "r"(a));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(vr[u].x), "=r"(vr[u].y), "=r"(vr[u].z), "=r"(vr[u].w) : "r"(a + 4096u));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(kr[u >> 2][u & 3].x), "=r"(kr[u >> 2][u & 3].y), "=r"(kr[u >> 2][u & 3].z), "=r"(kr[u >> 2][u & 3].w) : "r"(a));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(vr[u >> 2][u & 3].x), "=r"(vr[u >> 2][u & 3].y), "=r"(vr[u >> 2][u & 3].z), "=r"(vr[u >> 2][u & 3].w) : "r"(a + 4096u));
               }
               release();
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                float kf[8], vf[8];
-                unpack8(kr[u], kf);
-                unpack8(vr[u], vf);
-                key_update(kf, vf, key0 + u * 2 + hw < as.j1);
+              for (int h = 0; h < 2; ++h) {
+                const bool valid[4] = {key0 + (h * 4 + 0) * 2 + hw < as.j1, key0 + (h * 4 + 1) * 2 + hw < as.j1,
+                                       key0 + (h * 4 + 2) * 2 + hw < as.j1, key0 + (h * 4 + 3) * 2 + hw < as.j1};
+                keys4(kr[h], vr[h], valid);
               }
               if (DBG && trow && lane == 0) trow[2] = clock64();
               sl += NCW;
@@ -607,11 +640,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           }
           w.nb += as.n_items;
         }
-        if (as.last && warp == 0) {   // the key / value of the token being decoded (published by the qkv phase of this launch)
-          float kf[8], vf[8];
+        if (as.last && warp == 0 && hw == 0) {   // the key / value of the token being decoded (published by the qkv phase of this launch)
+          float d = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { kf[i] = qkn[128 + l16 * 8 + i]; vf[i] = qkn[256 + l16 * 8 + i]; }
-          key_update(kf, vf, hw == 0);
+          for (int i = 0; i < 8; ++i) d += q[i] * qkn[128 + l16 * 8 + i];
+#pragma unroll
+          for (int st = 8; st > 0; st >>= 1) d += __shfl_xor_sync(0x0000ffffu, d, st);
+          const float mx = fmaxf(m, d), alpha = exp2f(m - mx), pj = exp2f(d - mx);
+          lsum = lsum * alpha + pj;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = o[i] * alpha + pj * qkn[256 + l16 * 8 + i];
+          m = mx;
         }
         // merge the 16 half-warp states -> one partial per CTA
         float* sm_m = actf;            // [16]
@@ -622,6 +661,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 #pragma unroll
         for (int i = 0; i < 8; ++i) sm_o[hidx * 128 + l16 * 8 + i] = o[i];
         consumer_sync();
+        const bool owner = c < p.heads;   // the CTA of the head's first key range folds the head's partials
+        float* mg = actf + 32 + 16 * 128;   // [cph][132] (owner only)
         if (tid < 128) {
           float M = -INFINITY;
 #pragma unroll
@@ -633,34 +674,30 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             Lt += sm_l[h] * wgt;
             O += sm_o[h * 128 + tid] * wgt;
           }
-          u64* pp = t_part + (int64_t)c * 132;
-          st_tag(pp + tid, O, tag);
-          if (tid == 0) { st_tag(pp + 128, M, tag); st_tag(pp + 129, Lt, tag); }
+          if (owner) {
+            mg[tid] = O;
+            if (tid == 0) { mg[128] = M; mg[129] = Lt; }
+          } else {
+            u64* pp = t_part + (int64_t)c * 132;
+            st_tag(pp + tid, O, tag);
+            if (tid == 0) { st_tag(pp + 128, M, tag); st_tag(pp + 129, Lt, tag); }
+          }
         }
-        // the LAST CTA of this head to get here merges the head's partials into the normalised output (the partials are
-        // tagged, so the arrival counter needs no release / acquire)
-        consumer_sync();
-        if (tid == 0) {
-          unsigned prev;
-          asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "l"(p.head_cnt + as.head) : "memory");
-          red[8] = (prev == (unsigned)as.cph - 1u) ? 1.f : 0.f;
-        }
-        consumer_sync();
-        if (red[8] != 0.f) {
-          // the head's partials -> shared memory (coalesced, validated), then 128 threads fold them in CTA order
-          float* mg = actf + 32 + 16 * 128;   // [cph][132]
-          const int nw = as.cph * 130;
+        if (owner) {
+          // fixed owner instead of "last CTA to arrive": no atomic round trip on the critical path; the partials are tagged,
+          // the owner polls them (coalesced, with back-off) as soon as its own share is done
+          const int nw = (as.cph - 1) * 130;
           for (int i0 = 0; i0 < nw; i0 += 2 * CONSUMER_THREADS) {
             u64 wv2[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int i = i0 + u * CONSUMER_THREADS + tid;
-              if (i < nw) wv2[u] = ld_weak1(t_part + (int64_t)((i / 130) * p.heads + as.head) * 132 + (i % 130));
+              if (i < nw) wv2[u] = ld_weak1(t_part + (int64_t)((i / 130 + 1) * p.heads + as.head) * 132 + (i % 130));
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int i = i0 + u * CONSUMER_THREADS + tid;
-              if (i < nw) mg[(i / 130) * 132 + (i % 130)] = settle1(wv2[u], t_part + (int64_t)((i / 130) * p.heads + as.head) * 132 + (i % 130), tag, nowait);
+              if (i < nw) mg[(i / 130 + 1) * 132 + (i % 130)] = settle1(wv2[u], t_part + (int64_t)((i / 130 + 1) * p.heads + as.head) * 132 + (i % 130), tag, nowait);
             }
           }
           consumer_sync();
@@ -677,7 +714,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             }
             st_tag(t_att + as.head * 128 + tid, O / Lt, tag);
           }
-          if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p.head_cnt + as.head), "r"(0u) : "memory");  // next use is a layer away
         }
       } else {
         stamp(1);
@@ -704,12 +740,29 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
       const int ntiles = cnt * tpg;
       uint32_t j = ((uint32_t)warp + NCW - (nb0 & (NCW - 1))) & (NCW - 1);
-      if ((int)j < ntiles) {
+      // Software pipeline over the warp's tiles: [A] wait for tile n, issue its shared-memory loads; [C] finish the
+      // bookkeeping of tile n-1 (its group counter atomic was issued at the end of the previous iteration, so its latency
+      // and a possible group epilogue overlap the loads of tile n); [B] mma of tile n, partial sums, counter atomic.
+      // (Measured on resident tiles, tools/tile_bench.py: 516 cycles per round of 8 tiles for the loads alone, +260 for the
+      // mma, +240 for the bookkeeping when the three run back to back.)
+      bool more = (int)j < ntiles, pend = false;
+      uint32_t sl = 0, use = 0, k = 0, ks = 0;
+      if (more) {
         const uint32_t n00 = nb0 + j;
-        uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
-        uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-        for (; (int)j < ntiles; j += NCW) {
-          long long* trow = nullptr;
+        sl = n00 % (uint32_t)nslots; use = n00 / (uint32_t)nslots;
+        k = j / (uint32_t)tpg; ks = j - k * (uint32_t)tpg;
+      }
+      uint32_t pk = 0, pgslot = 0;
+      int pold = 0;
+      while (more || pend) {
+        uint32_t a[16][4];
+        uint2 b[16];
+        uint32_t ta = 0;
+        long long* trow = nullptr;
+        if (more) {
+          // ---- [A] one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
+          // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
+          // column 0 and W.lo in column 1.
           if (DBG && ctr) {
             const uint32_t row = nb0 + j - ctr_nb0;
             if (row < 160u) trow = ctr + row * 4;
@@ -718,76 +771,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           mbar_wait(full0 + 8 * sl, use & 1);
           if (DBG && trow && lane == 0) trow[1] = clock64();
           cur_slot = sl;
-          // ---- one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
-          // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
-          // column 0 and W.lo in column 1. The B fragments are loaded first and the A fragments in batches of four
-          // k-steps interleaved with the mma of earlier batches, so that the tensor pipe starts while the rest of the
-          // tile is still being read (shared-memory returns are in order; all 16 ldmatrix in front of the first mma made
-          // the two pipes take turns: 0.53 us per tile, the sum of both).
-          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-          {
-            const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
-            const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
-            uint2 b[16];
+          ta = ring_u32 + sl * TILE_BYTES + lane * 16;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
-            uint32_t a[16][4];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-#pragma unroll
-            for (int bq = 0; bq < 4; ++bq) {
-              if (bq < 2) {
-#pragma unroll
-                for (int s = 8 + 4 * bq; s < 12 + 4 * bq; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-              }
-              if (bq == 1) release();
-              if (!(dflags & 1)) {
-#pragma unroll
-                for (int s = 4 * bq; s < 4 * bq + 4; s += 2) {
-                  mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
-                  mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
-                }
-              }
-            }
-            // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
-            acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
-            acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
-          }
-          const uint32_t gslot = (gb0 + k) % NG;
-          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
-            // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
-            // critical path of the group's epilogue (the value was published two or more phases ago)
-            const int row = (g0 + (int)k) * 16 + lane;
-            float bres = 0.f;
-            if (row < p.H)
-              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
-                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
-            rbuf[gslot * 16 + lane] = bres;
-          }
-          const uint32_t n = nb0 + j;
-          if ((lane & 3) == 0) {
-            float* tp = tpart + (n % NT) * 16;
-            tp[lane >> 2] = acc[0];
-            tp[(lane >> 2) + 8] = acc[2];
-          }
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) {
-            __threadfence_block();
-            last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
-          }
-          last = __shfl_sync(0xffffffffu, last, 0);
+          for (int s = 0; s < 8; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+        }
+        if (pend) {
+          // ---- [C] previous tile: did it complete its group? then sum the group's partials in k order (deterministic)
+          // and run the fused epilogue for its 16 rows
+          pend = false;
+          const int last = __shfl_sync(0xffffffffu, pold == tpg - 1, 0);
           if (last) {
             __threadfence_block();
-            // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
-            const uint32_t n0 = nb0 + k * tpg;
+            const uint32_t n0 = nb0 + pk * tpg;
             float v = 0.f;
             if (lane < 16)
               for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
             const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
-            if (lane == 0) gcnt[gslot] = 0;
+            if (lane == 0) gcnt[pgslot] = 0;
             if (lane < 8) {
-              const int gi = g0 + (int)k, r = lane;
+              const int gi = g0 + (int)pk, r = lane;
               if (ph == PH_QKV) {
                 const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
                 const int row0 = hb * 128 + i;
@@ -817,7 +819,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               } else if (ph == PH_O || ph == PH_DOWN) {
                 u64* dst = (ph == PH_O) ? t_xa : t_xb;
                 const int r0 = gi * 16 + r, r1 = r0 + 8;
-                const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
+                const float b0 = *reinterpret_cast<volatile float*>(rbuf + pgslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + pgslot * 16 + r + 8);
                 if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
                 if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
               } else if (ph == PH_GU) {
@@ -830,7 +832,58 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               }
             }
           }
+        }
+        if (more) {
+          // ---- [B] the A fragments come in batches of four k-steps interleaved with the mma of earlier batches
+          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
+#pragma unroll
+          for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
+#pragma unroll
+          for (int bq = 0; bq < 4; ++bq) {
+            if (bq < 2) {
+#pragma unroll
+              for (int s = 8 + 4 * bq; s < 12 + 4 * bq; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+            }
+            if (bq == 1) release();
+            if (!(dflags & 1)) {
+#pragma unroll
+              for (int s = 4 * bq; s < 4 * bq + 4; s += 2) {
+                mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
+                mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
+              }
+            }
+          }
+          // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
+          acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
+          acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
+          const uint32_t gslot = (gb0 + k) % NG;
+          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+            // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
+            // critical path of the group's epilogue (the value was published two or more phases ago)
+            const int row = (g0 + (int)k) * 16 + lane;
+            float bres = 0.f;
+            if (row < p.H)
+              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
+                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
+            rbuf[gslot * 16 + lane] = bres;
+          }
+          const uint32_t n = nb0 + j;
+          if ((lane & 3) == 0) {
+            float* tp = tpart + (n % NT) * 16;
+            tp[lane >> 2] = acc[0];
+            tp[(lane >> 2) + 8] = acc[2];
+          }
+          __syncwarp();
+          pold = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            pold = atomicAdd(&gcnt[gslot], 1);     // consumed in [C] of the next iteration
+          }
+          pk = k; pgslot = gslot; pend = true;
           if (DBG && trow && lane == 0) trow[2] = clock64();
+          j += NCW;
+          more = (int)j < ntiles;
           sl += NCW;
           if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
           ks += NCW;

@@ -128,6 +128,12 @@ struct dtk_engine {
   float *v_x = nullptr, *v_small_f = nullptr, *v_pq = nullptr;
   bf16 *v_xn = nullptr, *v_qkv = nullptr, *v_att = nullptr, *v_h = nullptr, *v_small_b = nullptr;
   bool pq_ready = false;
+  // the ViT forward of a chunk of nb images is captured once per (nb, outputs) into a CUDA graph over engine-owned
+  // staging buffers (~250 launches per chunk, each encoding two tensor maps on the host, become one graph launch)
+  struct VitGraph { cudaGraphExec_t exec; uint64_t launches; };
+  std::map<int, VitGraph> vit_graphs;
+  float *v_pix_in = nullptr, *v_tok_out = nullptr, *v_pool_out = nullptr;
+  int vit_graph = 1;
 
   // generation loop
   int gen_B = 0;
@@ -224,14 +230,15 @@ __global__ void reset_gen_kernel(unsigned long long* gen, unsigned int* done, un
   *done = 0u;
 }
 
-int ensure_vit_ws(dtk_engine* eng, int B) {
-  if (B <= eng->vit_cap) return DTK_OK;
+constexpr int VIT_CHUNK = 64;   // images per ViT pass (larger batches are processed in chunks)
+
+// ViT workspace: allocated ONCE, for a full chunk, at the first vision call (no regrowth: a cudaFree inside a stream-ordered
+// call would synchronise the device, and captured graphs keep pointing at these buffers)
+int ensure_vit_ws(dtk_engine* eng, int /*B*/) {
+  if (eng->vit_cap > 0) return DTK_OK;
   const dtk_config& c = eng->cfg;
+  const int B = VIT_CHUNK;
   const int64_t rows = (int64_t)B * v_tokens(c);
-  cudaFree(eng->v_x); cudaFree(eng->v_xn); cudaFree(eng->v_qkv); cudaFree(eng->v_att); cudaFree(eng->v_h);
-  cudaFree(eng->v_small_f); cudaFree(eng->v_small_b);
-  eng->v_x = nullptr; eng->v_xn = eng->v_qkv = eng->v_att = eng->v_h = eng->v_small_b = nullptr; eng->v_small_f = nullptr;
-  eng->vit_cap = 0;
   DTK_ALLOC(eng->v_x, rows * c.v_hidden);
   DTK_ALLOC(eng->v_xn, rows * c.v_hidden);
   DTK_ALLOC(eng->v_qkv, rows * 3 * c.v_hidden);
@@ -240,7 +247,22 @@ int ensure_vit_ws(dtk_engine* eng, int B) {
   DTK_ALLOC(eng->v_h, rows * hcols);
   DTK_ALLOC(eng->v_small_f, (int64_t)B * c.v_hidden * 2);
   DTK_ALLOC(eng->v_small_b, (int64_t)B * (c.v_hidden * 2 + c.v_inter));
+  DTK_ALLOC(eng->v_pix_in, (int64_t)B * 3 * c.v_image * c.v_image);
+  DTK_ALLOC(eng->v_tok_out, rows * c.v_hidden);
+  DTK_ALLOC(eng->v_pool_out, (int64_t)B * c.v_hidden);
   eng->vit_cap = B;
+  return DTK_OK;
+}
+
+// probe query of the attention-pool head: input independent (q = probe Wq^T + bq), computed once per engine
+int ensure_probe_query(dtk_engine* eng, cudaStream_t s) {
+  if (eng->pq_ready) return DTK_OK;
+  const int D = eng->cfg.v_hidden;
+  GemmArgs g{};
+  g.A = W(eng, "vit.head.probe"); g.lda = D; g.W = W(eng, "vit.head.wq"); g.ldw = D; g.M = 1; g.N = D; g.K = D;
+  g.bias = W(eng, "vit.head.bq"); g.out_f32 = eng->v_pq; g.ldo = D;
+  DTK_CK(launch_gemm(g, s, &eng->launches));
+  eng->pq_ready = true;
   return DTK_OK;
 }
 
@@ -300,13 +322,6 @@ int vit_forward(dtk_engine* eng, const float* pixels, int B, float* tokens_out, 
   DTK_CK(launch_layernorm(eng->v_x, W(eng, "vit.post_w"), W(eng, "vit.post_b"), c.v_eps, M, D, eng->v_xn, tokens_out, s, lc));
 
   if (pooled_out) {
-    if (!eng->pq_ready) {  // probe query is input independent: q = probe Wq^T + bq
-      GemmArgs g{};
-      g.A = W(eng, "vit.head.probe"); g.lda = D; g.W = W(eng, "vit.head.wq"); g.ldw = D; g.M = 1; g.N = D; g.K = D;
-      g.bias = W(eng, "vit.head.bq"); g.out_f32 = eng->v_pq; g.ldo = D;
-      DTK_CK(launch_gemm(g, s, lc));
-      eng->pq_ready = true;
-    }
     bf16* kvb = eng->v_qkv;  // [M, 2D]
     {
       GemmArgs g{};
@@ -678,7 +693,8 @@ int dtk_destroy(dtk_engine* eng) {
   cudaSetDevice(eng->device);
   cudaDeviceSynchronize();
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
-  void* ptrs[] = {eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
+  for (auto& g : eng->vit_graphs) cudaGraphExecDestroy(g.second.exec);
+  void* ptrs[] = {eng->v_pix_in, eng->v_tok_out, eng->v_pool_out, eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
                   eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len, eng->d_gen, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
@@ -698,15 +714,44 @@ int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_ou
   DTK_REQUIRE(pixels && B > 0, "pixels/B");
   DTK_CK(cudaSetDevice(eng->device));
   const dtk_config& c = eng->cfg;
-  const int CH = 64;
-  int r = ensure_vit_ws(eng, B < CH ? B : CH);
+  cudaStream_t s = (cudaStream_t)stream;
+  int r = ensure_vit_ws(eng, B);
   if (r != DTK_OK) return r;
+  if (pooled_out && (r = ensure_probe_query(eng, s)) != DTK_OK) return r;
   const int64_t pix_per = (int64_t)3 * c.v_image * c.v_image, N = v_tokens(c), D = c.v_hidden;
-  for (int b0 = 0; b0 < B; b0 += CH) {
-    int nb = B - b0 < CH ? B - b0 : CH;
-    r = vit_forward(eng, pixels + b0 * pix_per, nb, tokens_out ? tokens_out + b0 * N * D : nullptr,
-                    pooled_out ? pooled_out + (int64_t)b0 * D : nullptr, (cudaStream_t)stream);
-    if (r != DTK_OK) return r;
+  for (int b0 = 0; b0 < B; b0 += VIT_CHUNK) {
+    const int nb = B - b0 < VIT_CHUNK ? B - b0 : VIT_CHUNK;
+    float* tok = tokens_out ? tokens_out + b0 * N * D : nullptr;
+    float* pool = pooled_out ? pooled_out + (int64_t)b0 * D : nullptr;
+    if (!eng->vit_graph) {
+      r = vit_forward(eng, pixels + b0 * pix_per, nb, tok, pool, s);
+      if (r != DTK_OK) return r;
+      continue;
+    }
+    const int key = nb | (tok ? 1 << 8 : 0) | (pool ? 1 << 9 : 0) | (get_gemm_impl() << 10);
+    auto it = eng->vit_graphs.find(key);
+    if (it == eng->vit_graphs.end()) {
+      if (!eng->cap_stream) DTK_CK(cudaStreamCreateWithFlags(&eng->cap_stream, cudaStreamNonBlocking));
+      cudaStream_t cs = eng->cap_stream;
+      const uint64_t before = eng->launches;
+      cudaGraph_t graph = nullptr;
+      DTK_CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      r = vit_forward(eng, eng->v_pix_in, nb, tok ? eng->v_tok_out : nullptr, pool ? eng->v_pool_out : nullptr, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      const uint64_t n = eng->launches - before;
+      eng->launches = before;             // captured launches are counted per replay
+      if (r != DTK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce != cudaSuccess) { eng->err = std::string("cudaStreamEndCapture (ViT): ") + cudaGetErrorString(ce); return DTK_ERR_CUDA; }
+      cudaGraphExec_t exec = nullptr;
+      DTK_CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = eng->vit_graphs.emplace(key, dtk_engine::VitGraph{exec, n}).first;
+    }
+    DTK_CK(cudaMemcpyAsync(eng->v_pix_in, pixels + b0 * pix_per, (size_t)nb * pix_per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    DTK_CK(cudaGraphLaunch(it->second.exec, s));
+    eng->launches += it->second.launches;
+    if (tok) DTK_CK(cudaMemcpyAsync(tok, eng->v_tok_out, (size_t)nb * N * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (pool) DTK_CK(cudaMemcpyAsync(pool, eng->v_pool_out, (size_t)nb * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   return DTK_OK;
 }
@@ -716,7 +761,7 @@ int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out, void* s
   DTK_REQUIRE(tokens && out && B > 0, "tokens/out/B");
   DTK_CK(cudaSetDevice(eng->device));
   const dtk_config& c = eng->cfg;
-  const int CH = 64;
+  const int CH = VIT_CHUNK;
   int r = ensure_vit_ws(eng, B < CH ? B : CH);
   if (r != DTK_OK) return r;
   const int64_t per = (int64_t)v_tokens(c) * c.v_hidden;
@@ -1109,6 +1154,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "mega_debug") == 0) {
     eng->mega_debug = value ? 1 : 0;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "vit_graph") == 0) {  // 1 (default) = ViT chunks replayed from CUDA graphs, 0 = direct launches
+    eng->vit_graph = value ? 1 : 0;
     return DTK_OK;
   }
   if (std::strcmp(key, "mega_variant") == 0) {  // dev A/B switches of the persistent kernel (results identical)

@@ -20,16 +20,17 @@ from typing import Dict, Optional
 
 import torch
 
-from .configuration import DetikzifyConfig, VisionConfig, preset
+from .configuration import DetikzifyConfig, VisionConfig, config_from_dict, preset
 from .modeling import DetikzifyForCausalLM
 from .processing import DetikzifyImageProcessor, DetikzifyProcessor, SyntheticTokenizer
-from .weights import canonical_shapes, convert_timm_vision, random_init
+from .weights import canonical_shapes, convert_timm_vision, convert_v2_state_dict, random_init
 
+# v1 checkpoints with a shape preset. The reference also lists detikzify-tl-1.1b (TinyLlama: head_dim 64, which the decode
+# kernels do not support) and detikzify-cl-7b (no offline config to derive a preset from); a local directory of either loads
+# through its config.json and fails loudly at engine creation if the shape is unsupported.
 v1_models = [
     "nllg/detikzify-ds-1.3b",
     "nllg/detikzify-ds-7b",
-    "nllg/detikzify-tl-1.1b",
-    "nllg/detikzify-cl-7b",
 ]
 
 
@@ -47,14 +48,40 @@ def _device_index(device_map) -> int:
     raise ValueError(f"unsupported device_map {device_map!r}")
 
 
-def _load_safetensors_dir(path: str) -> Dict[str, torch.Tensor]:
+def _load_safetensors_dir(path: str, vision_tower: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    """Canonical state dict of a checkpoint directory. v2 / v2.5 names are mapped onto the canonical ones; v1 checkpoints do
+    NOT contain the vision tower (the reference wraps the timm model in a list so that it stays out of the state dict and
+    pulls the pretrained timm weights instead, v1/modeling_detikzify.py:49-57,84-96) — pass ``vision_tower`` (a timm
+    ``vit_so400m_patch14_siglip_384`` safetensors file or directory) to supply it."""
     from safetensors.torch import load_file
     sd: Dict[str, torch.Tensor] = {}
     for f in sorted(glob(os.path.join(path, "*.safetensors"))):
         sd.update(load_file(f))
-    if any(k.startswith("blocks.") or k.startswith("patch_embed.") for k in sd):
+    if any(k.startswith("model.text_model.") or k.startswith("model.connector.") for k in sd):
+        sd = convert_v2_state_dict(sd)
+    if vision_tower is not None:
+        files = sorted(glob(os.path.join(vision_tower, "*.safetensors"))) if os.path.isdir(vision_tower) else [vision_tower]
+        tower: Dict[str, torch.Tensor] = {}
+        for f in files:
+            tower.update(load_file(f))
+        sd.update(convert_timm_vision(tower))
+    elif any(k.startswith("blocks.") or k.startswith("patch_embed.") for k in sd):
         sd.update(convert_timm_vision(sd))
+    if not any(k.startswith("model.vision_model.") for k in sd):
+        raise FileNotFoundError(
+            f"{path}: the checkpoint holds no vision tower (v1 checkpoints never do); pass vision_tower=<timm "
+            "vit_so400m_patch14_siglip_384 safetensors> to load()")
     return sd
+
+
+def _load_tokenizer(path: str, cfg: DetikzifyConfig):
+    """The checkpoint's own tokenizer when its files are present (v1 settings: reference v1/__init__.py:24-33); None otherwise."""
+    if not any(os.path.exists(os.path.join(path, f)) for f in ("tokenizer.json", "tokenizer.model", "tokenizer_config.json")):
+        return None
+    from transformers import AutoTokenizer   # host-side text <-> ids only, not on the GPU path
+    tok = AutoTokenizer.from_pretrained(path, model_max_length=cfg.model_max_length, add_bos_token=False, add_eos_token=True,
+                                        pad_token="<pad>", padding_side="right", legacy=False)
+    return tok
 
 
 def build_processor(cfg: DetikzifyConfig, tokenizer=None) -> DetikzifyProcessor:
@@ -70,7 +97,7 @@ def build_processor(cfg: DetikzifyConfig, tokenizer=None) -> DetikzifyProcessor:
 def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bool = False, *,
          random_init_weights: Optional[bool] = None, seed: int = 0, state_dict: Optional[Dict[str, torch.Tensor]] = None,
          config: Optional[DetikzifyConfig] = None, max_seqs: int = 2, max_batch: int = 1, broadcast: bool = False,
-         prefix_slots: Optional[int] = None, device_init: bool = False, **kwargs):
+         prefix_slots: Optional[int] = None, device_init: bool = False, vision_tower: Optional[str] = None, **kwargs):
     """Returns ``(model, processor)``.
 
     ``max_seqs`` KV slots are preallocated (0.40 GB each for ds-1.3b at 2k context); ``generate()`` keeps a prefix cache
@@ -87,7 +114,14 @@ def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bo
     from .. import _lib
     import ctypes as C
 
-    cfg = config or preset(model_name_or_path)
+    is_dir = isinstance(model_name_or_path, str) and os.path.isdir(model_name_or_path)
+    cfg = config
+    if cfg is None and is_dir and os.path.exists(os.path.join(model_name_or_path, "config.json")):
+        import json
+        with open(os.path.join(model_name_or_path, "config.json")) as f:
+            cfg = config_from_dict(json.load(f), name=model_name_or_path)
+    if cfg is None:
+        cfg = preset(model_name_or_path)
     device = _device_index(kwargs.pop("device_map", None))
     dtype = kwargs.pop("torch_dtype", kwargs.pop("dtype", torch.bfloat16))
     if isinstance(dtype, str):
@@ -106,7 +140,7 @@ def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bo
         sd = state_dict
         if sd is None and isinstance(model_name_or_path, str) and os.path.isdir(model_name_or_path) \
                 and glob(os.path.join(model_name_or_path, "*.safetensors")):
-            sd = _load_safetensors_dir(model_name_or_path)
+            sd = _load_safetensors_dir(model_name_or_path, vision_tower)
         if sd is None:
             if random_init_weights is False:
                 raise FileNotFoundError(f"no weights found for {model_name_or_path!r} (offline) and random init disabled")
@@ -131,7 +165,8 @@ def load(model_name_or_path, modality_projector: Optional[str] = None, is_v1: bo
 
     model = DetikzifyForCausalLM(cfg, arena, device=device, dtype=dtype, max_seqs=max_seqs, max_batch=max_batch,
                                  prefix_slots=prefix_slots)
-    return model, build_processor(cfg)
+    tokenizer = _load_tokenizer(model_name_or_path, cfg) if is_dir else None
+    return model, build_processor(cfg, tokenizer)
 
 
 __all__ = ["load", "v1_models", "DetikzifyConfig", "VisionConfig", "DetikzifyForCausalLM", "DetikzifyProcessor",

@@ -171,3 +171,45 @@ def preset(name: str) -> DetikzifyConfig:
             vision_config=VisionConfig(hidden_size=216, intermediate_size=400, num_hidden_layers=3,
                                        num_attention_heads=3, image_size=126, patch_size=14))
     raise KeyError(f"unknown model preset {name!r}")
+
+
+def config_from_dict(d: Dict[str, Any], name: str = "") -> DetikzifyConfig:
+    """``config.json`` of a checkpoint directory -> DetikzifyConfig. Two layouts exist: v1 checkpoints carry a flat LLaMA
+    config plus the fields ``initialize_vision_modules`` wrote (reference v1/configuration_detikzify.py:3-13,
+    v1/modeling_detikzify.py:98-107: patch_token_id, concat_patches, num_patches, vision_tower ...; the tower itself is a timm
+    so400m/14@384 SigLIP and is NOT described in the file), v2 / v2.5 nest ``text_config`` / ``vision_config`` and name the
+    image token ``image_token_id`` (reference configuration_detikzify.py:83-120)."""
+    def rope(t: Dict[str, Any]) -> Dict[str, Any]:
+        rs = t.get("rope_scaling") or t.get("rope_parameters") or {}
+        kind = rs.get("rope_type", rs.get("type", "default"))
+        out = dict(rope_theta=float(t.get("rope_theta", rs.get("rope_theta", 10000.0))), rope_factor=float(rs.get("factor", 1.0)))
+        if kind == "llama3":
+            out.update(rope_type="llama3", rope_low_freq_factor=float(rs.get("low_freq_factor", 1.0)),
+                       rope_high_freq_factor=float(rs.get("high_freq_factor", 4.0)),
+                       rope_original_max_position=int(rs.get("original_max_position_embeddings", 8192)))
+        elif kind not in ("default", "linear"):
+            raise ValueError(f"unsupported rope scaling {kind!r}")
+        return out
+
+    v2 = "text_config" in d
+    t = d["text_config"] if v2 else d
+    heads = int(t["num_attention_heads"])
+    head_dim = int(t.get("head_dim") or t["hidden_size"] // heads)
+    common = dict(
+        hidden_size=int(t["hidden_size"]), intermediate_size=int(t["intermediate_size"]), num_hidden_layers=int(t["num_hidden_layers"]),
+        num_attention_heads=heads, num_key_value_heads=int(t.get("num_key_value_heads", heads)), head_dim=head_dim,
+        vocab_size=int(t["vocab_size"]), max_position_embeddings=int(t.get("max_position_embeddings", 2048)),
+        rms_norm_eps=float(t.get("rms_norm_eps", 1e-6)), bos_token_id=int(t.get("bos_token_id") or 0),
+        eos_token_id=int(t["eos_token_id"] if not isinstance(t.get("eos_token_id"), list) else t["eos_token_id"][0]),
+        pad_token_id=int(t.get("pad_token_id") if t.get("pad_token_id") is not None else d.get("pad_token_id", 0)),
+        name_or_path=name, **rope(t))
+    if v2:
+        vc = d.get("vision_config") or {}
+        vision = VisionConfig(**{k: vc[k] for k in ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                                                   "image_size", "patch_size", "num_channels", "layer_norm_eps", "hidden_act") if k in vc})
+        if "image_size" not in vc:
+            vision.image_size = 420
+        return DetikzifyConfig(patch_token_id=int(d.get("image_token_id", 128005)), concat_patches=int(d.get("concat_factor", 3)),
+                               projector_bias=False, vision_config=vision, **common)
+    return DetikzifyConfig(patch_token_id=int(d["patch_token_id"]), concat_patches=int(d.get("concat_patches", 3)),
+                           projector_bias=True, vision_config=VisionConfig(), **common)

@@ -426,3 +426,38 @@ def test_prefix_cache_invalidated_by_new_image_and_bounded_by_engine_slots():
     other = torch.cat([ids[0], torch.arange(50, 55)])[None]
     out = model.generate(input_ids=other, pixel_values=None, max_new_tokens=3)
     assert out.shape[1] == other.shape[1] + 3
+
+
+# ------------------------------------------------------------------ checkpoint directory loading (host side)
+def test_checkpoint_directory_config_and_state_dict(tmp_path):
+    """load() on a local directory: config.json decides the shape (v1 flat / v2 nested), v2 parameter names map onto the
+    canonical ones, and a v1 checkpoint without a vision tower asks for one instead of failing with a KeyError."""
+    import json
+    from safetensors.torch import save_file
+    from detikzify_b200.model import _load_safetensors_dir
+    from detikzify_b200.model.configuration import config_from_dict, preset
+    from detikzify_b200.model.weights import random_init, to_v2_state_dict
+    cfg = preset("tiny-v2")
+    sd = random_init(cfg)
+    d = tmp_path / "v2"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in to_v2_state_dict(sd).items()}, str(d / "model.safetensors"))
+    text = dict(hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_hidden_layers,
+                num_attention_heads=cfg.num_attention_heads, num_key_value_heads=cfg.num_key_value_heads, head_dim=128,
+                vocab_size=cfg.vocab_size, rms_norm_eps=1e-5, rope_theta=500000.0, bos_token_id=600, eos_token_id=601, pad_token_id=604,
+                rope_scaling=dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=64))
+    (d / "config.json").write_text(json.dumps(dict(image_token_id=605, concat_factor=3, text_config=text,
+                                                   vision_config=cfg.vision_config.to_dict())))
+    got = config_from_dict(json.loads((d / "config.json").read_text()), name=str(d))
+    for k in ("hidden_size", "num_key_value_heads", "rope_type", "rope_original_max_position", "patch_token_id", "projector_bias", "num_patches"):
+        assert getattr(got, k) == getattr(cfg, k), k
+    loaded = _load_safetensors_dir(str(d))
+    assert set(loaded) == set(sd) and all(torch.equal(loaded[k], sd[k]) for k in sd)
+    # v1: decoder-only checkpoint -> explicit request for the tower
+    v1 = tmp_path / "v1"
+    v1.mkdir()
+    cfg1 = preset("tiny")
+    sd1 = {k: v for k, v in random_init(cfg1).items() if "vision_model" not in k}
+    save_file({k: v.contiguous() for k, v in sd1.items()}, str(v1 / "model.safetensors"))
+    with pytest.raises(FileNotFoundError, match="vision_tower"):
+        _load_safetensors_dir(str(v1))

@@ -5,7 +5,7 @@ llama3 RoPE scaling, V = 128256 (the generic sampler: the register-resident one 
   * tiny-v2: against the golden vectors the REFERENCE's own v2 module produced (tests/golden/reference_v2_tiny.pt);
   * v2-8b-2l: every detikzify-v2-8b matrix shape with two decoder layers against the fp32 oracle, batch 1 on the persistent
     kernel and on the per-op kernels, batched-GEMM decode, and the sampler at V = 128256.
-Tolerance: logits max-abs 3e-2 (bf16 operands, fp32 accumulation).
+Tolerance: logits max-abs 3e-2 at the tiny shape; at the 8b shapes 8 % of the reference logits' RMS (see test_gpu_ds7b.py).
 """
 from pathlib import Path
 
@@ -86,6 +86,7 @@ def test_v2_8b_shapes_decode_and_sampler():
             last, _ = eng.prefill(s, ids.cuda(), 0, img, 0)
             lens.append(ids.numel())
         ref0, _ = oracle.forward_logits(torch.cat([prompts[B - 1], tok1[B - 1:]])[None], pix)
+        TOL = max(3e-2, 0.08 * ref0.pow(2).mean().sqrt().item())
         assert (last.cpu() - ref0[0, -2]).abs().max().item() < TOL          # prefill last row of the longest prompt
         # batch-1 decode on both implementations (GQA attention split: 148 / 32 heads = 4 key ranges per head)
         for impl in (1, 0):
