@@ -48,6 +48,8 @@ SYMBOLS = {
     "dtk_last_error": (C.c_char_p, [_P]),
     "dtk_vit_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "dtk_project": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "dtk_image_preprocess": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_float,
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P]),
     "dtk_seq_alloc": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "dtk_seq_free": (C.c_int, [_P, C.c_int]),
     "dtk_seq_fork": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),

@@ -756,6 +756,18 @@ int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_ou
   return DTK_OK;
 }
 
+int dtk_image_preprocess(dtk_engine* eng, const uint8_t* rgb, int h, int w, int S, const int32_t* bounds_h, const int32_t* coef_h,
+                         int ksize_h, const int32_t* bounds_v, const int32_t* coef_v, int ksize_v, float rescale,
+                         const float* mean3_host, const float* std3_host, uint8_t* tmp, float* out, uint8_t* out_u8, void* stream) {
+  if (!eng) return DTK_ERR_INVALID;
+  DTK_REQUIRE(rgb && bounds_h && coef_h && bounds_v && coef_v && mean3_host && std3_host && tmp && out, "null pointer");
+  DTK_REQUIRE(h > 0 && w > 0 && S > 0 && ksize_h > 0 && ksize_v > 0, "sizes");
+  DTK_CK(cudaSetDevice(eng->device));
+  DTK_CK(launch_image_preprocess(rgb, h, w, S, bounds_h, coef_h, ksize_h, bounds_v, coef_v, ksize_v, rescale, mean3_host, std3_host,
+                                 tmp, out, out_u8, (cudaStream_t)stream, &eng->launches));
+  return DTK_OK;
+}
+
 int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out, void* stream) {
   if (!eng) return DTK_ERR_INVALID;
   DTK_REQUIRE(tokens && out && B > 0, "tokens/out/B");

@@ -210,6 +210,11 @@ cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint
 int64_t mega_tiled_elems(int N, int K, int mode, int* groups, int* tpg);
 cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cudaStream_t s);
 
+// device image preprocessing (Pillow-exact 8-bit bicubic resize + rescale + normalise): rgb uint8 [h, w, 3] -> fp32 [3, S, S]
+cudaError_t launch_image_preprocess(const uint8_t* rgb, int h, int w, int S, const int* bounds_h, const int* coef_h, int ksize_h,
+                                    const int* bounds_v, const int* coef_v, int ksize_v, float rescale, const float* mean,
+                                    const float* std, uint8_t* tmp, float* out, uint8_t* out_u8, cudaStream_t s, uint64_t* counter);
+
 // single-query attention of the SigLIP attention-pool head: q fp32 [heads*72] (shared by all images),
 // kv bf16 [B*N, 2*D] -> out bf16 [B, D]
 cudaError_t launch_pool_attn(const float* q, const bf16* kv, int B, int N, int D, int heads, float scale,

@@ -252,6 +252,23 @@ class Engine:
         self._check(self.lib.dtk_vit_encode(self._h, self._ptr(pixels), B, self._ptr(tokens), self._ptr(pooled), self._stream()), "dtk_vit_encode")
         return tokens, pooled
 
+    def image_preprocess(self, rgb: torch.Tensor, size: int, rescale: float, mean, std, out: torch.Tensor,
+                         want_uint8: bool = False) -> Optional[torch.Tensor]:
+        """rgb uint8 [h, w, 3] on the device -> ``out`` fp32 [3, size, size] (Pillow-exact bicubic resize, rescale, normalise)."""
+        from .model.processing import pil_resample_coeffs
+        h, w, ch = rgb.shape
+        assert ch == 3 and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        bh, chh, kh = pil_resample_coeffs(w, size)
+        bv, cvv, kv = pil_resample_coeffs(h, size)
+        dev = [t.to(self.device, non_blocking=True) for t in (bh, chh, bv, cvv)]
+        tmp = torch.empty(h, size, 3, dtype=torch.uint8, device=self.device)
+        u8 = torch.empty(size, size, 3, dtype=torch.uint8, device=self.device) if want_uint8 else None
+        m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        self._check(self.lib.dtk_image_preprocess(self._h, self._ptr(rgb), h, w, size, self._ptr(dev[0]), self._ptr(dev[1]), kh,
+                                                  self._ptr(dev[2]), self._ptr(dev[3]), kv, float(rescale), m3, s3,
+                                                  self._ptr(tmp), self._ptr(out), self._ptr(u8), self._stream()), "dtk_image_preprocess")
+        return u8
+
     def project(self, tokens: torch.Tensor) -> torch.Tensor:
         tokens = tokens.to(self.device, torch.float32).contiguous()
         B = tokens.shape[0]

@@ -57,14 +57,22 @@ class ImageSim:
         """SelfSim of several candidate renders against one reference figure: all images go through ONE batched ViT pass
         (the renders of a batch of parallel MCTS rollouts), the fp64 cosines are taken on the device and read back with a
         single transfer. Same values as ``get_similarity`` per pair (reference evaluate/imagesim.py:91-125)."""
-        pix = []
+        images = []
         for image in [reference, *candidates]:
             image = load(image)
             if self.preprocess:
                 image = expand(image, max(image.size), do_trim=True)
-            pix.append(self.processor(images=image, return_tensors="pt")["pixel_values"])
+            images.append(image)
+        owner = getattr(self.model, "_owner", None)
         with torch.inference_mode():
-            out = self.model(pixel_values=torch.cat(pix))
+            if owner is not None and owner.device.type == "cuda" and hasattr(self.processor, "preprocess_device"):
+                # resize + normalise on the device (bit-identical to the PIL path), straight into the ViT batch
+                with owner._lock, owner._on_stream():
+                    pixel_values = self.processor.preprocess_device(images, owner.engine)
+                    owner._sync()
+            else:
+                pixel_values = torch.cat([self.processor(images=im, return_tensors="pt")["pixel_values"] for im in images])
+            out = self.model(pixel_values=pixel_values)
             feats = out.pooler_output if self.mode == "cos" else out.last_hidden_state.mean(dim=1)
             feats = feats.double()
             return F.cosine_similarity(feats[1:], feats[:1].expand_as(feats[1:]), dim=1).tolist()

@@ -43,6 +43,85 @@ class BatchFeature(dict):
         return out
 
 
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic(x: float) -> float:
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_COEFF_CACHE: Dict = {}
+
+
+def pil_resample_coeffs(in_size: int, out_size: int):
+    """Pillow's 8-bit bicubic resampling taps for one axis (third party: Pillow src/libImaging/Resample.c,
+    ``precompute_coeffs`` + ``normalize_coeffs_8bpc``; restated, double arithmetic in the same order) ->
+    (bounds int32 [out, 2] = {first input index, tap count}, coef int32 [out, ksize] 22-bit fixed point, ksize).
+    The device resize (csrc/preprocess.cu) applies them exactly like Pillow does, so it is bit-identical to
+    ``Image.resize(..., BICUBIC)``."""
+    key = (in_size, out_size)
+    if key in _COEFF_CACHE:
+        return _COEFF_CACHE[key]
+    import math
+    support0 = 2.0
+    scale = float(in_size) / out_size
+    filterscale = scale if scale >= 1.0 else 1.0
+    support = support0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    coef = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        for x in range(xmax):
+            v = k[x] / ww if ww != 0.0 else k[x]
+            coef[xx, x] = int(-0.5 + v * (1 << _PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    out = (torch.from_numpy(bounds), torch.from_numpy(coef), ksize)
+    _COEFF_CACHE[key] = out
+    return out
+
+
+def pil_resample_reference(arr: np.ndarray, out_size: int) -> np.ndarray:
+    """numpy restatement of the two-pass fixed-point resize (what the device kernels compute): uint8 [h, w, 3] -> [S, S, 3]."""
+    h, w, _ = arr.shape
+    bh, ch, _ = pil_resample_coeffs(w, out_size)
+    bv, cv, _ = pil_resample_coeffs(h, out_size)
+    bh, ch, bv, cv = bh.numpy(), ch.numpy().astype(np.int64), bv.numpy(), cv.numpy().astype(np.int64)
+    half = 1 << (_PRECISION_BITS - 1)
+    tmp = np.zeros((h, out_size, 3), dtype=np.uint8)
+    a64 = arr.astype(np.int64)
+    for x in range(out_size):
+        x0, n = bh[x]
+        acc = half + (a64[:, x0:x0 + n, :] * ch[x, :n, None]).sum(axis=1)
+        tmp[:, x, :] = np.clip(acc >> _PRECISION_BITS, 0, 255)
+    out = np.zeros((out_size, out_size, 3), dtype=np.uint8)
+    t64 = tmp.astype(np.int64)
+    for y in range(out_size):
+        y0, n = bv[y]
+        acc = half + (t64[y0:y0 + n, :, :] * cv[y, :n, None, None]).sum(axis=0)
+        out[y] = np.clip(acc >> _PRECISION_BITS, 0, 255)
+    return out
+
+
 class DetikzifyImageProcessor:
     model_input_names = ["pixel_values"]
 
@@ -77,6 +156,28 @@ class DetikzifyImageProcessor:
         return BatchFeature(pixel_values=torch.from_numpy(data) if return_tensors == "pt" else data)
 
     __call__ = preprocess
+
+    def preprocess_device(self, images, engine) -> torch.Tensor:
+        """Same result as ``preprocess`` (bit-identical resize, fp32 normalisation), computed on the engine's device: the
+        uint8 pixels are uploaded and resized / normalised by ``dtk_image_preprocess``. Returns ``[B, 3, S, S]`` fp32 on the
+        device, ready for ``dtk_vit_encode`` — the path for bursts of candidate renders from parallel MCTS rollouts."""
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        if self.resample != 3:
+            raise ValueError("device preprocessing implements the bicubic resampler only")
+        S = self.size["height"]
+        out = torch.empty(len(images), 3, S, S, dtype=torch.float32, device=engine.device)
+        for i, im in enumerate(images):
+            if isinstance(im, torch.Tensor):
+                im = im.numpy()
+            if not isinstance(im, np.ndarray):
+                im = np.asarray(im.convert("RGB"), dtype=np.uint8)
+            arr = torch.from_numpy(np.ascontiguousarray(im.astype(np.uint8)))
+            if engine.device.type == "cuda":
+                arr = arr.pin_memory()
+            engine.image_preprocess(arr.to(engine.device, non_blocking=True), S, self.rescale_factor, self.image_mean,
+                                    self.image_std, out[i])
+        return out
 
 
 class SyntheticTokenizer:

@@ -110,6 +110,18 @@ DTK_API const char* dtk_last_error(const dtk_engine* eng);
 DTK_API int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_out,
                    float* pooled_out, void* stream);
 
+/* ---- image preprocessing on the device. Replaces DetikzifyImageProcessor.preprocess for images already uploaded as
+ *      uint8 (detikzify/model/v1/processing_detikzify.py:242-251: bicubic resize to SxS, x 1/255, (x - mean) / std, CHW).
+ *      rgb: device uint8 [h, w, 3]; the resize is Pillow's 8-bit resampler bit for bit: bounds_* int32 [S][2] = {first
+ *      input index, tap count}, coef_* int32 [S][ksize_*] = 22-bit fixed-point taps for the horizontal / vertical pass
+ *      (host-computed from (w -> S) and (h -> S), see model/processing.py::pil_resample_coeffs); tmp: device uint8
+ *      [h, S, 3] scratch; out: device fp32 [3, S, S]; out_u8 (may be NULL): the resized uint8 image [S, S, 3] (tests). ---- */
+DTK_API int dtk_image_preprocess(dtk_engine* eng, const uint8_t* rgb, int h, int w, int S,
+                                 const int32_t* bounds_h, const int32_t* coef_h, int ksize_h,
+                                 const int32_t* bounds_v, const int32_t* coef_v, int ksize_v,
+                                 float rescale, const float* mean3_host, const float* std3_host,
+                                 uint8_t* tmp, float* out, uint8_t* out_u8, void* stream);
+
 /* ---- concat-3 + mm_projector (v1/modeling_detikzify.py:132-137,163).
  *      tokens fp32 [B,N,D] -> out fp32 [B,P,H]; the reshape is folded into addressing. ------ */
 DTK_API int dtk_project(dtk_engine* eng, const float* tokens, int B, float* out, void* stream);

@@ -36,7 +36,7 @@ int main(void) {
   c.head_dim = 64;                                   /* unsupported shape must be refused, not crash */
   if (dtk_arena_bytes(&c) != 0) { fprintf(stderr, "bad config accepted\n"); return 9; }
   /* link-time presence of the device entry points (not called: no GPU in this test) */
-  void* syms[] = {(void*)dtk_create, (void*)dtk_destroy, (void*)dtk_last_error, (void*)dtk_vit_encode, (void*)dtk_project,
+  void* syms[] = {(void*)dtk_create, (void*)dtk_destroy, (void*)dtk_last_error, (void*)dtk_vit_encode, (void*)dtk_project, (void*)dtk_image_preprocess,
                   (void*)dtk_seq_alloc, (void*)dtk_seq_free, (void*)dtk_seq_fork, (void*)dtk_seq_share, (void*)dtk_prefill, (void*)dtk_decode,
                   (void*)dtk_sample, (void*)dtk_gen_begin, (void*)dtk_gen_step, (void*)dtk_gen_wait, (void*)dtk_gen_end,
                   (void*)dtk_set_option, (void*)dtk_get_option, (void*)dtk_launch_count};

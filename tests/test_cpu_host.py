@@ -461,3 +461,15 @@ def test_checkpoint_directory_config_and_state_dict(tmp_path):
     save_file({k: v.contiguous() for k, v in sd1.items()}, str(v1 / "model.safetensors"))
     with pytest.raises(FileNotFoundError, match="vision_tower"):
         _load_safetensors_dir(str(v1))
+
+
+def test_pil_resample_restatement_is_bit_exact():
+    """The fixed-point bicubic resize the device kernels implement (model/processing.py::pil_resample_reference, taps from
+    pil_resample_coeffs) equals Pillow's ``Image.resize(BICUBIC)`` bit for bit, up- and down-scaling, non-square inputs."""
+    import numpy as np
+    from detikzify_b200.model.processing import pil_resample_reference
+    rng = np.random.default_rng(1)
+    for h, w, S in [(300, 300, 56), (56, 56, 56), (61, 147, 56), (40, 40, 96), (700, 433, 384)]:
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(arr).resize((S, S), resample=Image.Resampling.BICUBIC))
+        assert np.array_equal(pil_resample_reference(arr, S), ref), (h, w, S)

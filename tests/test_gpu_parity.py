@@ -186,3 +186,30 @@ def test_shared_prefix_rollouts_against_oracle():
         for s in subs:
             eng.seq_free(s)
         eng.seq_free(base)
+
+
+def test_device_image_preprocessing_is_pillow_exact():
+    """dtk_image_preprocess: the resized uint8 image equals Pillow's bicubic resize bit for bit and the normalised fp32 pixels
+    equal the host image processor's (reference v1/processing_detikzify.py:242-251), for ragged input sizes."""
+    import numpy as np
+    from PIL import Image
+    from detikzify_b200.model import build_processor
+    name = "tiny2"
+    cfg, sd, oracle = model_bundle(name)
+    eng = engine_for(name)
+    ip = build_processor(cfg).image_processor
+    S = cfg.vision_config.image_size
+    rng = np.random.default_rng(5)
+    ims = []
+    for h, w in [(500, 500), (S, S), (97, 233), (640, 200), (60, 60)]:
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        arr[: h // 3] = 255                                    # renders are mostly white
+        ims.append(Image.fromarray(arr))
+        out = torch.empty(3, S, S, device="cuda")
+        u8 = eng.image_preprocess(torch.from_numpy(arr).cuda(), S, ip.rescale_factor, ip.image_mean, ip.image_std, out, want_uint8=True)
+        ref_u8 = np.asarray(ims[-1].resize((S, S), resample=Image.Resampling.BICUBIC))
+        assert np.array_equal(u8.cpu().numpy(), ref_u8), (h, w)
+    host = ip.preprocess(ims)["pixel_values"]
+    dev = ip.preprocess_device(ims, eng)
+    torch.cuda.synchronize()
+    assert (dev.cpu() - host).abs().max().item() < 1e-6
