@@ -380,8 +380,10 @@ def run_ours(args):
     # rollouts per figure forked off one prefilled 243-token image prompt. Extra keys; the headline stays configs[1].
     ds7b = None
     t7 = torch.zeros(3, dtype=torch.float64)
+    bytes_dec = sum(eng.decode_bytes(P + 1 + i) for i in range(n_new - 1))   # (taken before the engine may be released)
+    persistent = eng.get_option("decode_persistent") == 1
+    eng.seq_free(slot)
     if not args.no_7b:
-        eng.seq_free(slot)
         del model, eng
         torch.cuda.empty_cache()
         R, F, NT7 = args.rollouts, args.figures_per_rank, args.rollout_tokens
@@ -415,9 +417,11 @@ def run_ours(args):
             def figure7(fi: int):
                 """ViT + projector + prefill of figure fi, fork to R rollouts, NT7 sampled tokens each -> [R] last tokens"""
                 img = e7.image_embeds(pix7[fi:fi + 1])[0]
+                for sl in slots7[1:]:
+                    e7.seq_share(slots7[0], sl, 0)            # release the previous figure's prefix
                 last, _ = e7.prefill(slots7[0], ids7, 0, img, 0)
                 for sl in slots7[1:]:
-                    e7.seq_fork(slots7[0], sl, P7)
+                    e7.seq_share(slots7[0], sl, P7)           # rollouts READ the image prefix from slot 0 (no copy)
                 first, _ = e7.sample(last[None].expand(R, -1).contiguous(), nuc, suppress=[0] * R, steps=[0] * R, seq_ids=list(range(R)))
                 e7.gen_begin(slots7, [P7] * R, [int(t) for t in first.tolist()], nuc, list(range(R)))
                 for _ in range(NT7 - 1):
@@ -467,7 +471,7 @@ def run_ours(args):
             "rollouts": {"figures_per_rank": F, "figures_total": int(t7[2]) if world == 1 else F * world, "rollouts_per_figure": R, "new_tokens": NT7,
                          "sampling": "temperature 0.8, top-p 0.95", "seconds": roll_s7,
                          "tokens_per_s": world * F * R * NT7 / roll_s7, "ms_per_figure": roll_s7 / F * 1e3,
-                         "includes": "ViT + projector + 243-token prefill + fork to 32 KV slots + decode, per figure; max over ranks",
+                         "includes": "ViT + projector + 243-token prefill + 31 shared-prefix borrowers (dtk_seq_share) + decode, per figure; max over ranks",
                          "roofline_unique_kv": {"bytes_per_figure": d["weights_bytes"] * steps7 + kv_uniq,
                                                 "frac_of_hbm_peak": F * (d["weights_bytes"] * steps7 + kv_uniq) / roll_s7 / 1e9 / peak7},
                          "roofline_private_kv": {"bytes_per_figure": d["weights_bytes"] * steps7 + kv_priv,
@@ -479,10 +483,8 @@ def run_ours(args):
         new_per_step = n_new
         value = world * args.steps * new_per_step / t_all
         # roofline of the decode region (dominant: the per-token decode step = weights + KV stream)
-        bytes_dec = sum(eng.decode_bytes(P + 1 + i) for i in range(n_new - 1))
         peak, peak_src = peaks()
         achieved = bytes_dec * args.steps / t_dec / 1e9
-        persistent = eng.get_option("decode_persistent") == 1
         kernel_name = ("decode_mega_kernel (persistent cooperative weight-streaming decode kernel, 1 launch per token) + sample_kernel"
                        if persistent else "decode step (CUDA graph: fused RMSNorm+GEMV / split-K attention / sampler kernels of one token)")
         traffic = ncu_traffic("decode_mega_kernel") if persistent else None

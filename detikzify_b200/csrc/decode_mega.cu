@@ -271,19 +271,20 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags,
   if (src) {
     const int npair = K >> 1;
     float2* xs2 = reinterpret_cast<float2*>(xs);
-    for (int p0 = 0; p0 < npair; p0 += 4 * CONSUMER_THREADS) {
-      ulonglong2 w[4];
+    constexpr int PP = 12;   // pairs per thread in flight (one pass covers K = 6144: a single L2 round trip per pass)
+    for (int p0 = 0; p0 < npair; p0 += PP * CONSUMER_THREADS) {
+      ulonglong2 w[PP];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < PP; ++u) {
         const int pi = p0 + u * CONSUMER_THREADS + tid;
         if (pi < npair) w[u] = strong_first ? ld_strong2(src + 2 * pi) : ld_weak2(src + 2 * pi);
       }
       // words whose tag is still old are re-read coherently, ALL of them per round (one L2 round trip per round)
       Spin sp;
       for (;;) {
-        bool bad[4], any = false;
+        bool bad[PP], any = false;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PP; ++u) {
           const int pi = p0 + u * CONSUMER_THREADS + tid;
           bad[u] = pi < npair && !(tag_ok(w[u].x, tag) && tag_ok(w[u].y, tag));
           any = any || bad[u];
@@ -291,13 +292,13 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags,
         if (!any || nowait) break;
         sp.tick();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PP; ++u) {
           const int pi = p0 + u * CONSUMER_THREADS + tid;
           if (bad[u]) w[u] = ld_strong2(src + 2 * pi);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < PP; ++u) {
         const int pi = p0 + u * CONSUMER_THREADS + tid;
         if (pi < npair) xs2[pi] = make_float2(tag_val(w[u].x), tag_val(w[u].y));
       }
@@ -740,29 +741,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
       const int ntiles = cnt * tpg;
       uint32_t j = ((uint32_t)warp + NCW - (nb0 & (NCW - 1))) & (NCW - 1);
-      // Software pipeline over the warp's tiles: [A] wait for tile n, issue its shared-memory loads; [C] finish the
-      // bookkeeping of tile n-1 (its group counter atomic was issued at the end of the previous iteration, so its latency
-      // and a possible group epilogue overlap the loads of tile n); [B] mma of tile n, partial sums, counter atomic.
-      // (Measured on resident tiles, tools/tile_bench.py: 516 cycles per round of 8 tiles for the loads alone, +260 for the
-      // mma, +240 for the bookkeeping when the three run back to back.)
-      bool more = (int)j < ntiles, pend = false;
-      uint32_t sl = 0, use = 0, k = 0, ks = 0;
-      if (more) {
+      if ((int)j < ntiles) {
         const uint32_t n00 = nb0 + j;
-        sl = n00 % (uint32_t)nslots; use = n00 / (uint32_t)nslots;
-        k = j / (uint32_t)tpg; ks = j - k * (uint32_t)tpg;
-      }
-      uint32_t pk = 0, pgslot = 0;
-      int pold = 0;
-      while (more || pend) {
-        uint32_t a[16][4];
-        uint2 b[16];
-        uint32_t ta = 0;
-        long long* trow = nullptr;
-        if (more) {
-          // ---- [A] one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
-          // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
-          // column 0 and W.lo in column 1.
+        uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
+        uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
+        for (; (int)j < ntiles; j += NCW) {
+          long long* trow = nullptr;
           if (DBG && ctr) {
             const uint32_t row = nb0 + j - ctr_nb0;
             if (row < 160u) trow = ctr + row * 4;
@@ -771,25 +755,76 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           mbar_wait(full0 + 8 * sl, use & 1);
           if (DBG && trow && lane == 0) trow[1] = clock64();
           cur_slot = sl;
-          ta = ring_u32 + sl * TILE_BYTES + lane * 16;
+          // ---- one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
+          // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
+          // column 0 and W.lo in column 1. The B fragments are loaded first and the A fragments in batches of four
+          // k-steps interleaved with the mma of earlier batches, so that the tensor pipe starts while the rest of the
+          // tile is still being read (shared-memory returns are in order; all 16 ldmatrix in front of the first mma made
+          // the two pipes take turns: 0.53 us per tile, the sum of both).
+          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          {
+            const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
+            const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
+            uint2 b[16];
 #pragma unroll
-          for (int s = 0; s < 8; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-        }
-        if (pend) {
-          // ---- [C] previous tile: did it complete its group? then sum the group's partials in k order (deterministic)
-          // and run the fused epilogue for its 16 rows
-          pend = false;
-          const int last = __shfl_sync(0xffffffffu, pold == tpg - 1, 0);
+            for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
+            uint32_t a[16][4];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+#pragma unroll
+            for (int bq = 0; bq < 4; ++bq) {
+              if (bq < 2) {
+#pragma unroll
+                for (int s = 8 + 4 * bq; s < 12 + 4 * bq; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
+              }
+              if (bq == 1) release();
+              if (!(dflags & 1)) {
+#pragma unroll
+                for (int s = 4 * bq; s < 4 * bq + 4; s += 2) {
+                  mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
+                  mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
+                }
+              }
+            }
+            // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
+            acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
+            acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
+          }
+          const uint32_t gslot = (gb0 + k) % NG;
+          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+            // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
+            // critical path of the group's epilogue (the value was published two or more phases ago)
+            const int row = (g0 + (int)k) * 16 + lane;
+            float bres = 0.f;
+            if (row < p.H)
+              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
+                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
+            rbuf[gslot * 16 + lane] = bres;
+          }
+          const uint32_t n = nb0 + j;
+          if ((lane & 3) == 0) {
+            float* tp = tpart + (n % NT) * 16;
+            tp[lane >> 2] = acc[0];
+            tp[(lane >> 2) + 8] = acc[2];
+          }
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
           if (last) {
             __threadfence_block();
-            const uint32_t n0 = nb0 + pk * tpg;
+            // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
+            const uint32_t n0 = nb0 + k * tpg;
             float v = 0.f;
             if (lane < 16)
               for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
             const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
-            if (lane == 0) gcnt[pgslot] = 0;
+            if (lane == 0) gcnt[gslot] = 0;
             if (lane < 8) {
-              const int gi = g0 + (int)pk, r = lane;
+              const int gi = g0 + (int)k, r = lane;
               if (ph == PH_QKV) {
                 const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
                 const int row0 = hb * 128 + i;
@@ -819,7 +854,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               } else if (ph == PH_O || ph == PH_DOWN) {
                 u64* dst = (ph == PH_O) ? t_xa : t_xb;
                 const int r0 = gi * 16 + r, r1 = r0 + 8;
-                const float b0 = *reinterpret_cast<volatile float*>(rbuf + pgslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + pgslot * 16 + r + 8);
+                const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
                 if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
                 if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
               } else if (ph == PH_GU) {
@@ -832,58 +867,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               }
             }
           }
-        }
-        if (more) {
-          // ---- [B] the A fragments come in batches of four k-steps interleaved with the mma of earlier batches
-          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-          const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
-#pragma unroll
-          for (int s = 0; s < 16; ++s) b[s] = xp[s * 8];
-#pragma unroll
-          for (int bq = 0; bq < 4; ++bq) {
-            if (bq < 2) {
-#pragma unroll
-              for (int s = 8 + 4 * bq; s < 12 + 4 * bq; ++s) ldmatrix_x4(a[s][0], a[s][1], a[s][2], a[s][3], ta + s * 512);
-            }
-            if (bq == 1) release();
-            if (!(dflags & 1)) {
-#pragma unroll
-              for (int s = 4 * bq; s < 4 * bq + 4; s += 2) {
-                mma_bf16_16816(acc, a[s], b[s].x, b[s].y);
-                mma_bf16_16816(c1, a[s + 1], b[s + 1].x, b[s + 1].y);
-              }
-            }
-          }
-          // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
-          acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
-          acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
-          const uint32_t gslot = (gb0 + k) % NG;
-          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
-            // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
-            // critical path of the group's epilogue (the value was published two or more phases ago)
-            const int row = (g0 + (int)k) * 16 + lane;
-            float bres = 0.f;
-            if (row < p.H)
-              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
-                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
-            rbuf[gslot * 16 + lane] = bres;
-          }
-          const uint32_t n = nb0 + j;
-          if ((lane & 3) == 0) {
-            float* tp = tpart + (n % NT) * 16;
-            tp[lane >> 2] = acc[0];
-            tp[(lane >> 2) + 8] = acc[2];
-          }
-          __syncwarp();
-          pold = 0;
-          if (lane == 0) {
-            __threadfence_block();
-            pold = atomicAdd(&gcnt[gslot], 1);     // consumed in [C] of the next iteration
-          }
-          pk = k; pgslot = gslot; pend = true;
           if (DBG && trow && lane == 0) trow[2] = clock64();
-          j += NCW;
-          more = (int)j < ntiles;
           sl += NCW;
           if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
           ks += NCW;
@@ -897,8 +881,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     }
     // hint barrier after every phase except qkv (the attention phase polls its head's q itself) and lm_head
     if (ph != PH_QKV && ph != PH_LM) {
-      bar_target += G;
-      hint_barrier(p.bar_count, bar_target, dflags);
+      if (p.variant & 2) consumer_sync();   // dev A/B: no arrival counter at all, the next staging polls the tagged data directly
+      else { bar_target += G; hint_barrier(p.bar_count, bar_target, dflags); }
     }
     stamp(3);
     if (++ph == 5) { ph = 0; ++l; }

@@ -25,9 +25,13 @@ def timeit(label):
 import subprocess
 print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 timeit("default")
-for variant in (1, 0, 1, 0):
+for variant in (1, 2, 3, 0, 2, 0):
     eng.set_option("mega_variant", variant)
-    timeit(f"variant={variant} (bit 0: coherent loads first when staging)")
+    timeit(f"variant={variant} (bit 0: coherent loads first when staging, bit 1: no arrival counter - poll the data)")
+    lgv = eng.decode([slot], [ctx], tok)[0].clone()
+    if variant == 1:
+        lg_ref = lgv
+    print(f"   logits vs variant 1: max diff {(lgv - lg_ref).abs().max().item():.2e}")
 for flags in (1, 2, 0):
     eng.set_option("mega_flags", flags)
     timeit(f"flags={flags} (1=no mma, 2=no waiting at all)")
