@@ -445,7 +445,7 @@ def run_ours(args):
         kvb = e7.decode_bytes(1) - e7.decode_bytes(0)
         ds7b_local = {"decode_bytes_ctx512": e7.decode_bytes(ctx7), "weights_bytes": e7.decode_bytes(0), "kv_bytes_per_pos": kvb,
                       "launches": int(launches7), "persistent": e7.get_option("decode_persistent") == 1}
-        for sl in slots7:
+        for sl in reversed(slots7):      # borrowers before the slot that lends them the image prefix
             e7.seq_free(sl)
     barrier()
 

@@ -879,10 +879,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
       stamp(2);
     }
-    // hint barrier after every phase except qkv (the attention phase polls its head's q itself) and lm_head
+    // phase boundary (none after qkv: the attention phase polls its head's q itself; none after lm_head)
     if (ph != PH_QKV && ph != PH_LM) {
-      if (p.variant & 2) consumer_sync();   // dev A/B: no arrival counter at all, the next staging polls the tagged data directly
-      else { bar_target += G; hint_barrier(p.bar_count, bar_target, dflags); }
+      // No grid-wide arrival counter by default: the next phase's staging polls the tagged words it needs (weak load,
+      // then coherent re-reads with a short back-off) — measured 0.80 vs 0.91 ms per token with the counter in front
+      // (profiles/r2_decode_variants.txt). variant bit 1 restores the counter for A/B runs.
+      if (p.variant & 2) { bar_target += G; hint_barrier(p.bar_count, bar_target, dflags); }
+      else consumer_sync();
     }
     stamp(3);
     if (++ph == 5) { ph = 0; ++l; }

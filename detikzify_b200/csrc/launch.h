@@ -197,7 +197,7 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // arrival counter; bar_base[0] = arrivals, [1] = tag epoch of past launches
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
-  int variant;                                                // dev A/B switches (option "mega_variant"): bit 0 = coherent loads first when staging
+  int variant;                                                // dev A/B switches (option "mega_variant"): bit 0 = coherent loads first when staging, bit 1 = grid-wide arrival counter in front of every staging
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
   long long* dbg2;                                            // optional: [grid][MEGA_DBG2_ROWS][4] clock64 per-tile trace of layer dbg_layer

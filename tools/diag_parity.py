@@ -28,7 +28,14 @@ for name in sys.argv[1:] or ["ds-7b-2l"]:
         errs, rows = [], []
         for t in range(T0, T0 + steps - 1):
             lg = eng.decode([slot], [t], ref_ids[t:t + 1].cuda())[0].cpu()
-            errs.append((lg - ref_all[0, t]).abs().max().item()); rows.append(lg)
+            d = (lg - ref_all[0, t]).abs()
+            errs.append(d.max().item()); rows.append(lg)
+            if d.max() > 0.5:
+                bad = (d > 0.5).nonzero().flatten()
+                print(f"    step {t}: {bad.numel()} logits off by > 0.5, index range [{int(bad.min())}, {int(bad.max())}], "
+                      f"first {bad[:8].tolist()}, lg {lg[bad[:4]].tolist()} ref {ref_all[0, t][bad[:4]].tolist()}")
+                again = eng.decode([slot], [t], ref_ids[t:t + 1].cuda())[0].cpu()
+                print(f"    same step launched again: err {(again - ref_all[0, t]).abs().max():.4f}")
         out[impl] = torch.stack(rows)
         print(f"  impl {impl}: decode errs " + " ".join(f"{e:.4f}" for e in errs))
     print(f"  persistent vs per-op max diff {(out[1] - out[0]).abs().max():.5f}")

@@ -27,7 +27,7 @@ print(subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power
 timeit("default")
 for variant in (1, 2, 3, 0, 2, 0):
     eng.set_option("mega_variant", variant)
-    timeit(f"variant={variant} (bit 0: coherent loads first when staging, bit 1: no arrival counter - poll the data)")
+    timeit(f"variant={variant} (bit 0: coherent loads first when staging, bit 1: arrival counter before staging)")
     lgv = eng.decode([slot], [ctx], tok)[0].clone()
     if variant == 1:
         lg_ref = lgv
