@@ -527,6 +527,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   u64* const t_h = t_att + qd;
   u64* const t_part = t_h + p.tg_I;
 
+  float best_v = -INFINITY;   // greedy tail: this thread's best (logit, index) over the lm_head rows it finished
+  int best_i = 0x7fffffff;
   for (it = 0; it < nphase; ++it) {
     if (it == nphase - 1) { ph = PH_LM; l = 0; }
     const uint32_t tag = epoch + (uint32_t)it + 1u;   // tags of this phase's outputs; its inputs carry tag - 1
@@ -595,10 +597,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
           for (int i = 0; i < 8; ++i) o[i] *= alpha;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            float vf[8];
-            unpack8(vr[u], vf);
+            if (valid[u]) {   // (positions past the range may hold uninitialised cache memory: 0 * NaN must not reach o)
+              float vf[8];
+              unpack8(vr[u], vf);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += pj[u] * vf[i];
+              for (int i = 0; i < 8; ++i) o[i] += pj[u] * vf[i];
+            }
           }
           m = mx;
         };
@@ -741,11 +745,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
       const int ntiles = cnt * tpg;
       uint32_t j = ((uint32_t)warp + NCW - (nb0 & (NCW - 1))) & (NCW - 1);
-      if ((int)j < ntiles) {
+      // The warps walk their tiles in ROUNDS (tile j + 8 r in round r) and meet every fourth round: a ring slot belongs to
+      // one consumer warp, so nothing else stops a warp pair from running many groups ahead of another one, and a warp that
+      // gets NT tiles ahead would overwrite its own partial sums of a group whose epilogue has not run yet (seen at the
+      // v2-8b shape: 880 lm_head tiles per CTA, HBM-bound, scattered wrong logits). Drift <= 32 tiles + one group < NT.
+      const int rounds = (ntiles + NCW - 1) / NCW;
+      {
         const uint32_t n00 = nb0 + j;
         uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
         uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-        for (; (int)j < ntiles; j += NCW) {
+        for (int rd = 0; rd < rounds; ++rd, j += NCW) {
+          if ((rd & 3) == 3) consumer_sync();
+          if ((int)j >= ntiles) continue;
           long long* trow = nullptr;
           if (DBG && ctr) {
             const uint32_t row = nb0 + j - ctr_nb0;
@@ -862,8 +873,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                 if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
               } else {
                 const int r0 = gi * 16 + r, r1 = r0 + 8;
-                if (r0 < p.V) p.logits[r0] = v * rn;
-                if (r1 < p.V) p.logits[r1] = v1 * rn;
+                const float l0 = v * rn, l1 = v1 * rn;
+                if (r0 < p.V) p.logits[r0] = l0;
+                if (r1 < p.V) p.logits[r1] = l1;
+                if (p.fuse_greedy) {   // rows are visited in increasing order per thread: '>' keeps the lowest index on ties
+                  if (r0 < p.V && r0 != p.bad_token && l0 > best_v) { best_v = l0; best_i = r0; }
+                  if (r1 < p.V && r1 != p.bad_token && l1 > best_v) { best_v = l1; best_i = r1; }
+                }
               }
             }
           }
@@ -889,6 +905,41 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     }
     stamp(3);
     if (++ph == 5) { ph = 0; ++l; }
+  }
+  if (p.fuse_greedy) {
+    // ---- greedy tail (HF argmax after NoBadWords; lowest index wins ties): CTA-local argmax, one 64-bit atomicMax per CTA
+    // on {order-preserving logit bits, ~index}; the last CTA to arrive publishes the token exactly as the sampler does
+    // (device state of the loop + ONE 8-byte store to the mapped host ring) — no second launch per token.
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
+    int* red_i = reinterpret_cast<int*>(red + 8);
+    if (lane == 0) { red[warp] = best_v; red_i[warp] = best_i; }
+    consumer_sync();
+    if (tid == 0) {
+      for (int wv = 1; wv < NCW; ++wv)
+        if (red[wv] > best_v || (red[wv] == best_v && red_i[wv] < best_i)) { best_v = red[wv]; best_i = red_i[wv]; }
+      uint32_t u = __float_as_uint(best_v);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)best_i);
+      atomicMax(p.amax, key);
+      unsigned long long prev;
+      asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;\n" : "=l"(prev) : "l"(p.amax + 1) : "memory");
+      if (prev == (unsigned long long)G - 1ull) {
+        const unsigned long long best = atomicExch(p.amax, 0ull);
+        const int token = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+        const unsigned long long gstep = *p.gen_step;
+        p.gen_tok[0] = token;
+        p.gen_pos[0] = min(pos + 1, p.max_pos);
+        const unsigned long long entry = ((gstep + 1ull) << 32) | (unsigned long long)(unsigned)token;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p.host_ring + (gstep % (unsigned long long)p.ring)), "l"(entry) : "memory");
+        *p.gen_step = gstep + 1ull;
+        p.amax[1] = 0ull;
+      }
+    }
   }
   // publish the arrival count and the tag epoch for the next launch (stream-ordered): every CTA made 4L arrivals and
   // the launch used tags epoch + 1 .. epoch + 5L + 1

@@ -152,6 +152,8 @@ struct dtk_engine {
   int decode_impl = 1;       // 1 = persistent weight-streaming kernel (default), 0 = per-op kernels / CUDA graph
   int decode_gemm_min_batch = 4;  // B >= this: batched decode runs the dense matrices as tensor-core GEMMs (weights once per step)
   bool gen_mega = false;
+  bool gen_fused = false;    // greedy generation on the persistent kernel: argmax + token publication in the kernel tail
+  unsigned long long* d_amax = nullptr;
   SampleArgs gen_sample{};
   unsigned long long* d_bar = nullptr;  // [0] counter, [1] epoch base
   unsigned int* d_head_cnt = nullptr;
@@ -163,6 +165,7 @@ struct dtk_engine {
   int mega_debug = 0;
   int mega_flags = 0;
   int mega_variant = 0;
+  int fuse_greedy = 1;
 };
 
 namespace {
@@ -397,6 +400,11 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
     m.variant = eng->mega_variant;
+    m.fuse_greedy = 0;
+    if (eng->gen_fused && logits == eng->d_logits) {   // inside the greedy generation loop
+      m.fuse_greedy = 1; m.bad_token = eng->gen_sample.bad_token; m.ring = eng->ring; m.max_pos = eng->cfg.max_len - 1;
+      m.amax = eng->d_amax; m.gen_tok = eng->d_tok; m.gen_pos = eng->d_pos; m.gen_step = eng->d_gen; m.host_ring = eng->dev_ring;
+    }
     m.dbg2 = (eng->mega_debug && eng->mega_trace_layer >= 0) ? eng->d_dbg2 : nullptr;
     m.dbg_layer = eng->mega_trace_layer;
     DTK_CK(launch_decode_mega(m, eng->mega_grid, s, lc));
@@ -666,6 +674,8 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
         DTK_CK(cudaMemset(eng->d_tagged, 0, (size_t)words * sizeof(unsigned long long)));
         m.tg = eng->d_tagged;
       }
+      DTK_ALLOC(eng->d_amax, 2);
+      DTK_CK(cudaMemset(eng->d_amax, 0, 2 * sizeof(unsigned long long)));
       DTK_ALLOC(eng->d_bar, 4);
       DTK_CK(cudaMemset(eng->d_bar, 0, 4 * sizeof(unsigned long long)));
       m.bar_count = eng->d_bar; m.bar_base = eng->d_bar + 1;
@@ -696,7 +706,7 @@ int dtk_destroy(dtk_engine* eng) {
   for (auto& g : eng->vit_graphs) cudaGraphExecDestroy(g.second.exec);
   void* ptrs[] = {eng->v_pix_in, eng->v_tok_out, eng->v_pool_out, eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
-                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len, eng->d_gen, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
+                  eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len, eng->d_gen, eng->d_amax, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (eng->cap_stream) cudaStreamDestroy(eng->cap_stream);
@@ -1033,7 +1043,8 @@ int dtk_gen_begin(dtk_engine* eng, const int* slots, const int* positions, const
     a.done_counter = eng->d_counters + (int64_t)c.max_batch * c.heads;
   }
   eng->gen_mega = (B == 1 && eng->decode_impl == 1 && eng->mega_ok);
-  if (eng->gen_mega) {  // one cooperative launch + sampler per token: no graph needed
+  eng->gen_fused = eng->gen_mega && eng->fuse_greedy && !eng->gen_sample.do_sample;
+  if (eng->gen_mega) {  // one cooperative launch (+ sampler when sampling) per token: no graph needed
     eng->gen_graph = nullptr;
     return DTK_OK;
   }
@@ -1079,7 +1090,7 @@ int dtk_gen_step(dtk_engine* eng, void* stream) {
   if (eng->gen_mega) {
     int r = decode_launches(eng, 1, nullptr, eng->d_logits, (cudaStream_t)stream);
     if (r != DTK_OK) return r;
-    DTK_CK(launch_sample(eng->gen_sample, (cudaStream_t)stream, &eng->launches));
+    if (!eng->gen_fused) DTK_CK(launch_sample(eng->gen_sample, (cudaStream_t)stream, &eng->launches));
     return DTK_OK;
   }
   DTK_REQUIRE(eng->gen_graph != nullptr, "dtk_gen_begin not called");
@@ -1133,6 +1144,7 @@ int dtk_gen_end(dtk_engine* eng) {
   }
   eng->gen_graph = nullptr;
   eng->gen_mega = false;
+  eng->gen_fused = false;
   eng->gen_B = 0;
   return DTK_OK;
 }
@@ -1166,6 +1178,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "mega_debug") == 0) {
     eng->mega_debug = value ? 1 : 0;
+    return DTK_OK;
+  }
+  if (std::strcmp(key, "fuse_greedy") == 0) {  // 1 (default): greedy generation loops take the argmax in the decode kernel's tail
+    eng->fuse_greedy = value ? 1 : 0;
     return DTK_OK;
   }
   if (std::strcmp(key, "vit_graph") == 0) {  // 1 (default) = ViT chunks replayed from CUDA graphs, 0 = direct launches

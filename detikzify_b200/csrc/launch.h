@@ -197,6 +197,11 @@ struct MegaArgs {
   unsigned int* head_cnt;                                     // [heads] arrival counters (zero-initialised, self-resetting)
   unsigned long long *bar_count, *bar_base;                   // arrival counter; bar_base[0] = arrivals, [1] = tag epoch of past launches
   int nslots, act_floats;                                     // shared-memory ring geometry (mega_configure)
+  // greedy generation loop: argmax of the masked logits in the kernel tail + token publication (replaces the sampler launch)
+  int fuse_greedy, bad_token, ring, max_pos;
+  unsigned long long* amax;                                   // [0] packed (ordered logit, ~index) max cell, [1] arrival counter; zero-initialised, self-resetting
+  int *gen_tok, *gen_pos;
+  unsigned long long *gen_step, *host_ring;
   int variant;                                                // dev A/B switches (option "mega_variant"): bit 0 = coherent loads first when staging, bit 1 = grid-wide arrival counter in front of every staging
   int dbg_flags;                                              // dev only: 1 = skip tile math, 2 = skip grid barriers, 4/8 = relaxed arrive/poll
   long long* dbg;                                             // optional: [grid][5L+1][4] globaltimer stamps (null = off)
