@@ -748,14 +748,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       // The warps walk their tiles in ROUNDS (tile j + 8 r in round r) and meet every fourth round: a ring slot belongs to
       // one consumer warp, so nothing else stops a warp pair from running many groups ahead of another one, and a warp that
       // gets NT tiles ahead would overwrite its own partial sums of a group whose epilogue has not run yet (seen at the
-      // v2-8b shape: 880 lm_head tiles per CTA, HBM-bound, scattered wrong logits). Drift <= 32 tiles + one group < NT.
+      // v2-8b shape: 880 lm_head tiles per CTA, HBM-bound, scattered wrong logits). The interval is as long as the
+      // partial-sum window allows: drift (interval rounds) + one group + the round in flight <= NT.
       const int rounds = (ntiles + NCW - 1) / NCW;
+      const int sync_every = max(1, (NT - tpg - 2 * NCW) / NCW);
+      int since_sync = 0;
       {
         const uint32_t n00 = nb0 + j;
         uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
         uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
         for (int rd = 0; rd < rounds; ++rd, j += NCW) {
-          if ((rd & 3) == 3) consumer_sync();
+          if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
           if ((int)j >= ntiles) continue;
           long long* trow = nullptr;
           if (DBG && ctr) {

@@ -1167,6 +1167,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     set_gemm_impl((int)value);
     return DTK_OK;
   }
+  if (std::strcmp(key, "gemm_skinny_swap") == 0) {  // process-wide dev switch
+    set_gemm_skinny_swap(value ? 1 : 0);
+    return DTK_OK;
+  }
   if (std::strcmp(key, "sample_impl") == 0) {  // process-wide: 0 = register-resident sampler when V fits, 1 = generic kernel
     DTK_REQUIRE(value == 0 || value == 1, "sample_impl must be 0 or 1");
     set_sample_impl((int)value);

@@ -195,6 +195,118 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __g
   }
 }
 
+// ---- swapped-operand tile for the batched decode step (M = rollouts <= 64): out[b, n] = sum_k X[b, k] W[n, k].
+// The weight rows are the UMMA M dimension (128 rows of W per CTA, K-major, straight from the arena) and the few batch rows
+// are the N dimension (NB = 32 or 64 columns): per 64-wide k-block a CTA moves 16 KB of weights (bytes that must come from
+// HBM once per step anyway) and only NB x 128 B of activations (L2 resident), instead of a 16 KB activation box that is
+// mostly zero fill next to 4 KB of weights as in the 128 x 32 tile above. The accumulator comes out transposed (TMEM lane =
+// output feature n, column = batch row b): for a fixed b the 32 lanes of a warp store 32 consecutive outputs (coalesced).
+// Epilogue: bias, residual, SwiGLU (gate_i / up_i are adjacent ROWS of W = adjacent lanes: one shuffle), fp32 or bf16 out.
+template <int NB, int TSTAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap mapW,
+                                                                    const __grid_constant__ CUtensorMap mapX, const GemmArgs p) {
+  constexpr int X_BYTES = NB * TBK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + X_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  const uint32_t bars = sbase + TSTAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull = bars + 16 * TSTAGES, tptr = tfull + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TBM;
+  const int KT = (p.K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
+    tc_mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tptr), "n"(NB));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tptr));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES, use = kt / TSTAGES;
+        if (use > 0) tc_wait(empty0 + 8 * s, (use - 1) & 1);
+        const uint32_t sw = sbase + s * STAGE_BYTES, sx = sw + A_BYTES;
+        tc_expect_tx(full0 + 8 * s, STAGE_BYTES);
+        tma_load_2d(sw, &mapW, kt * TBK, n0, full0 + 8 * s);
+        tma_load_2d(sx, &mapX, kt * TBK, 0, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 5) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES, use = kt / TSTAGES;
+        tc_wait(full0 + 8 * s, use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sw = sbase + s * STAGE_BYTES, sx = sw + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TBK / 16; ++k) umma_f16(tmem, umma_desc(sw + k * 32), umma_desc(sx + k * 32), idesc, (kt | k) != 0);
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // epilogue warps 0..3: TMEM lanes 32w..32w+31 = output features n0 + 32w + lane, columns = batch rows
+    tc_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int n = n0 + warp * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    float bias = 0.f;
+    if (p.bias && n < p.N) bias = __bfloat162float(p.bias[n]);
+#pragma unroll 1
+    for (int cb = 0; cb < NB; cb += 32) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(trow + (uint32_t)cb));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int b = cb + j;            // batch row (warp-uniform)
+        if (b >= p.M) break;
+        float v = __uint_as_float(r[j]) + bias;
+        if (p.glu) {
+          const float other = __shfl_xor_sync(0xffffffffu, v, 1);   // lane pairs (gate, up)
+          if (!(lane & 1) && n + 1 < p.N + 1 && n < p.N) {
+            const float rr = silu(v) * other;
+            const int64_t o = (int64_t)b * p.ldo + (n >> 1);
+            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rr);
+            else p.out_f32[o] = rr;
+          }
+          continue;
+        }
+        if (n < p.N) {
+          if (p.resid) v += p.resid[(int64_t)b * p.ldr + n];
+          const int64_t o = (int64_t)b * p.ldo + n;
+          if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(v);
+          else p.out_f32[o] = v;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(NB));
+  }
+}
+
 // ---- tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda)
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -254,8 +366,33 @@ static cudaError_t launch_tc_variant(const GemmArgs& a, cudaStream_t s, uint64_t
   return cudaGetLastError();
 }
 
+template <int NB, int TSTAGES>
+static cudaError_t launch_tc_swap(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  CUtensorMap mapW, mapX;
+  if (!make_map(&mapW, a.W, a.N, a.K, a.ldw, TBM) || !make_map(&mapX, a.A, a.M, a.K, a.lda, NB)) return cudaErrorInvalidValue;
+  constexpr int smem = TSTAGES * (A_BYTES + NB * TBK * 2) + 1024 + 256;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(gemm_tc_swap_kernel<NB, TSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  gemm_tc_swap_kernel<NB, TSTAGES><<<(a.N + TBM - 1) / TBM, TC_THREADS, smem, s>>>(mapW, mapX, a);
+  if (counter) ++*counter;
+  return cudaGetLastError();
+}
+
+static int g_skinny_swap = 1;   // dev switch (dtk_set_option "gemm_skinny_swap"): 1 = swapped-operand tile for M < 64
+void set_gemm_skinny_swap(int v) { g_skinny_swap = v; }
+
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
+  if (a.M < 64 && g_skinny_swap && a.act == ACT_NONE && !a.rowbias) {   // batched decode: weights are the M side
+    return a.M <= 32 ? launch_tc_swap<32, 8>(a, s, counter) : launch_tc_swap<64, 8>(a, s, counter);
+  }
   if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
   return launch_tc_variant<128, 3, 2>(a, s, counter);
 }

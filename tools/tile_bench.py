@@ -33,8 +33,9 @@ if __name__ == "__main__":
              2: "ldmatrix, 4 chains, bookkeeping", 3: "LDS.128, 4 chains, bookkeeping", 4: "ldmatrix, 2 chains, no bookkeeping",
              5: "LDS.128, 2 chains, no bookkeeping", 6: "ldmatrix, 4 chains, no bookkeeping", 7: "LDS.128, 4 chains, no bookkeeping",
              8: "ldmatrix, NO mma, bookkeeping", 9: "LDS.128, NO mma, bookkeeping", 12: "ldmatrix, NO mma, no bookkeeping",
-             13: "LDS.128, NO mma, no bookkeeping"}
-    for grid in (1, 148):
+             13: "LDS.128, NO mma, no bookkeeping", 16: "TWO tiles interleaved per warp iteration, bookkeeping",
+             20: "TWO tiles interleaved per warp iteration, no bookkeeping"}
+    for grid in (148,):
         print(f"grid {grid}:")
         for v, nm in names.items():
             for _ in range(2):
