@@ -133,7 +133,9 @@ struct dtk_engine {
   struct VitGraph { cudaGraphExec_t exec; uint64_t launches; };
   std::map<int, VitGraph> vit_graphs;
   float *v_pix_in = nullptr, *v_tok_out = nullptr, *v_pool_out = nullptr;
+  bf16* v_vt = nullptr;      // per-layer V^T copy for the tcgen05 attention
   int vit_graph = 1;
+  int attn_impl = 1;         // ViT attention: 1 = tcgen05 (attn_tc.cu), 0 = mma.sync flash attention (attn_mma.cu)
 
   // generation loop
   int gen_B = 0;
@@ -253,6 +255,7 @@ int ensure_vit_ws(dtk_engine* eng, int /*B*/) {
   DTK_ALLOC(eng->v_pix_in, (int64_t)B * 3 * c.v_image * c.v_image);
   DTK_ALLOC(eng->v_tok_out, rows * c.v_hidden);
   DTK_ALLOC(eng->v_pool_out, (int64_t)B * c.v_hidden);
+  DTK_ALLOC(eng->v_vt, (int64_t)B * c.v_heads * 80 * attn_tc_vt_cols(v_tokens(c)));
   eng->vit_cap = B;
   return DTK_OK;
 }
@@ -293,7 +296,9 @@ int vit_forward(dtk_engine* eng, const float* pixels, int B, float* tokens_out, 
       g.bias = W(eng, LN("vit.L", l, "bqkv")); g.out_bf16 = eng->v_qkv; g.ldo = 3 * D;
       DTK_CK(launch_gemm(g, s, lc));
     }
-    {
+    if (eng->attn_impl == 1 && attn_tc_supported()) {
+      DTK_CK(launch_attn_tc(eng->v_qkv, eng->v_vt, eng->v_att, B, c.v_heads, N, 1.0f / sqrtf(72.f), s, lc));
+    } else {
       AttnArgs a{};
       a.q = eng->v_qkv; a.k = eng->v_qkv + D; a.v = eng->v_qkv + 2 * D; a.o = eng->v_att;
       a.q_bs = a.k_bs = a.v_bs = (int64_t)N * 3 * D; a.q_hs = a.k_hs = a.v_hs = 72; a.q_rs = a.k_rs = a.v_rs = 3 * D;
@@ -704,7 +709,7 @@ int dtk_destroy(dtk_engine* eng) {
   cudaDeviceSynchronize();
   for (auto& g : eng->graphs) cudaGraphExecDestroy(g.second);
   for (auto& g : eng->vit_graphs) cudaGraphExecDestroy(g.second.exec);
-  void* ptrs[] = {eng->v_pix_in, eng->v_tok_out, eng->v_pool_out, eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
+  void* ptrs[] = {eng->v_pix_in, eng->v_tok_out, eng->v_pool_out, eng->v_vt, eng->kv, eng->rope_cs, eng->p_x, eng->p_qkv, eng->p_xn, eng->p_q, eng->p_att, eng->p_h, eng->d_x, eng->d_q,
                   eng->d_att, eng->d_h, eng->d_logits, eng->d_scratch, eng->d_part_o, eng->d_part_ml, eng->d_counters,
                   eng->d_slots, eng->d_pos, eng->d_tok, eng->d_share_slot, eng->d_share_len, eng->d_gen, eng->d_amax, eng->d_bar, eng->d_dbg, eng->d_dbg2, eng->d_head_cnt, eng->d_tiled, eng->d_tagged, eng->v_x, eng->v_small_f, eng->v_pq, eng->v_xn,
                   eng->v_qkv, eng->v_att, eng->v_h, eng->v_small_b};
@@ -738,7 +743,7 @@ int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_ou
       if (r != DTK_OK) return r;
       continue;
     }
-    const int key = nb | (tok ? 1 << 8 : 0) | (pool ? 1 << 9 : 0) | (get_gemm_impl() << 10);
+    const int key = nb | (tok ? 1 << 8 : 0) | (pool ? 1 << 9 : 0) | (get_gemm_impl() << 10) | (eng->attn_impl << 11);
     auto it = eng->vit_graphs.find(key);
     if (it == eng->vit_graphs.end()) {
       if (!eng->cap_stream) DTK_CK(cudaStreamCreateWithFlags(&eng->cap_stream, cudaStreamNonBlocking));
@@ -1184,6 +1189,11 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->mega_debug = value ? 1 : 0;
     return DTK_OK;
   }
+  if (std::strcmp(key, "attn_impl") == 0) {  // ViT attention: 1 (default) = tcgen05, 0 = mma.sync
+    DTK_REQUIRE(value == 0 || value == 1, "attn_impl must be 0 or 1");
+    eng->attn_impl = (int)value;
+    return DTK_OK;
+  }
   if (std::strcmp(key, "fuse_greedy") == 0) {  // 1 (default): greedy generation loops take the argmax in the decode kernel's tail
     eng->fuse_greedy = value ? 1 : 0;
     return DTK_OK;
@@ -1264,6 +1274,12 @@ int dtk_dbg_flash_attn(const void* q, const void* k, const void* v, void* o, int
   a.B = B; a.heads = heads; a.kv_group = 1; a.Tq = Tq; a.Tk = Tk; a.q_pos0 = q_pos0; a.causal = causal;
   a.head_dim = head_dim; a.scale = scale;
   return launch_flash_attn(a, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+}
+
+int dtk_dbg_attn_tc(const void* qkv, void* vt_scratch, void* o, int B, int heads, int N, float scale, void* stream) {
+  if (!qkv || !vt_scratch || !o || B <= 0 || heads <= 0 || N <= 0) return DTK_ERR_INVALID;
+  if (!attn_tc_supported()) return DTK_ERR_UNSUPPORTED;
+  return launch_attn_tc((const bf16*)qkv, (bf16*)vt_scratch, (bf16*)o, B, heads, N, scale, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
 }
 
 int dtk_dbg_gemv(const void* Wm, const float* x, const void* norm_w, float eps, int N, int K, int mode, float* out,

@@ -61,6 +61,12 @@ struct AttnArgs {
 };
 cudaError_t launch_flash_attn(const AttnArgs& a, cudaStream_t s, uint64_t* counter);
 
+// ---------------------------------------------------------------- ViT attention on tcgen05 (attn_tc.cu): head_dim 72, non-causal
+// qkv bf16 [B*N, 3*heads*72] (q | k | v column blocks); vT: scratch bf16 [B*heads*80, attn_tc_vt_cols(N)]; o bf16 [B*N, heads*72]
+bool attn_tc_supported();
+int attn_tc_vt_cols(int N);
+cudaError_t launch_attn_tc(const bf16* qkv, bf16* vT, bf16* o, int B, int heads, int N, float scale, cudaStream_t s, uint64_t* counter);
+
 // ---------------------------------------------------------------- row-wise / elementwise
 // y = LN(x) * w + b  (fp32 stats); x fp32 [M, D]; writes bf16 and/or fp32 outputs
 cudaError_t launch_layernorm(const float* x, const bf16* w, const bf16* b, float eps, int M, int D,

@@ -209,6 +209,9 @@ DTK_API int dtk_dbg_gemm(const void* A_bf16, const void* W_bf16, const void* bia
 DTK_API int dtk_dbg_flash_attn(const void* q, const void* k, const void* v, void* o, int B,
                                int heads, int Tq, int Tk, int head_dim, int causal, int q_pos0,
                                float scale, void* stream);
+/* ViT attention on tcgen05: qkv bf16 [B*N, 3*heads*72] (q | k | v column blocks), vt_scratch bf16 [B*heads*80, ceil(N/128)*128],
+ * o bf16 [B*N, heads*72]; non-causal, head_dim 72 */
+DTK_API int dtk_dbg_attn_tc(const void* qkv, void* vt_scratch, void* o, int B, int heads, int N, float scale, void* stream);
 /* y = W[N,K] * rmsnorm?(x[K]) ; mode 0 store / 1 add / 2 glu (out[N/2]) */
 DTK_API int dtk_dbg_gemv(const void* W_bf16, const float* x, const void* norm_w_bf16, float eps,
                          int N, int K, int mode, float* out, void* stream);

@@ -129,6 +129,26 @@ def test_flash_attention_matches_torch(B, heads, Tq, Tk, D, causal, q_pos0):
     torch.testing.assert_close(o.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("B,heads,N", [(2, 16, 729), (1, 2, 16), (3, 3, 81), (1, 16, 900), (5, 4, 130), (64, 16, 729)])
+def test_tcgen05_vit_attention_matches_torch(B, heads, N):
+    """attn_tc.cu: the ViT attention on tcgen05 (fused qkv layout in, head_dim 72 padded to 80 by TMA zero fill, ragged last
+    key block masked) against fp32 softmax attention of the same bf16 inputs; 729 = v1 tower, 900 = v2 tower."""
+    torch.manual_seed(B * 31 + N)
+    dev, D = "cuda", heads * 72
+    qkv = torch.randn(B * N, 3 * D, device=dev).bfloat16()
+    NP = (N + 127) // 128 * 128
+    vt = torch.full((B * heads * 80, NP), float("nan"), device=dev, dtype=torch.bfloat16)
+    o = torch.full((B * N, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(72)
+    rc = _lib().dtk_dbg_attn_tc(_p(qkv), _p(vt), _p(o), B, heads, N, scale, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    q, k, v = (t.reshape(B, N, heads, 72).float() for t in qkv.split(D, dim=1))
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), v).reshape(B * N, D)
+    torch.testing.assert_close(o.float(), ref, rtol=2e-2, atol=2e-2)
+
+
 GEMV_CASES = [
     # (N, K, mode, norm)
     (6144, 2048, 0, True),     # 1.3b qkv-shaped rows (store mode exercises the same inner loop)
