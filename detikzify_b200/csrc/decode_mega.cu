@@ -360,7 +360,7 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags,
 // then lm_head) with a single copy of the tile code and a run-time phase switch in the epilogue: the per-token
 // instruction footprint of a warp stays inside the SM's 32 KB instruction cache (the fully specialised version was
 // ~160 KB, re-fetched from L2 every layer: the first tiles of every phase ran 3-6x slower than the steady state).
-template <bool DBG>
+template <bool DBG, bool PAIR>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -757,26 +757,76 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         const uint32_t n00 = nb0 + j;
         uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
         uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-        for (int rd = 0; rd < rounds; ++rd, j += NCW) {
-          if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
-          if ((int)j >= ntiles) continue;
+        for (int rd = 0; rd < rounds; rd += PAIR ? 2 : 1) {
+          if (PAIR) {
+            if (since_sync + 2 > sync_every) { consumer_sync(); since_sync = 0; }
+            since_sync += 2;
+          } else if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
+          if ((int)j >= ntiles) { j += PAIR ? 2 * NCW : NCW; continue; }
           long long* trow = nullptr;
           if (DBG && ctr) {
             const uint32_t row = nb0 + j - ctr_nb0;
             if (row < 160u) trow = ctr + row * 4;
           }
           if (DBG && trow && lane == 0) trow[3] = clock64();
+          // second tile of this iteration (PAIR): the warp's tile of the next round
+          const bool two = PAIR && (int)(j + NCW) < ntiles;
+          uint32_t slB = sl + NCW, useB = use, ksB = ks + NCW, kB = k;
+          if (slB >= (uint32_t)nslots) { slB -= nslots; ++useB; }
+          while (ksB >= (uint32_t)tpg) { ksB -= tpg; ++kB; }
           mbar_wait(full0 + 8 * sl, use & 1);
+          if (two) mbar_wait(full0 + 8 * slB, useB & 1);
           if (DBG && trow && lane == 0) trow[1] = clock64();
-          cur_slot = sl;
           // ---- one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
           // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
-          // column 0 and W.lo in column 1. The B fragments are loaded first and the A fragments in batches of four
-          // k-steps interleaved with the mma of earlier batches, so that the tensor pipe starts while the rest of the
-          // tile is still being read (shared-memory returns are in order; all 16 ldmatrix in front of the first mma made
-          // the two pipes take turns: 0.53 us per tile, the sum of both).
-          float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-          {
+          // column 0 and W.lo in column 1. The A fragments are loaded in batches interleaved with the mma of earlier
+          // batches, so that the tensor pipe starts while the rest of the tile is still being read (shared-memory returns
+          // are in order; all 16 ldmatrix in front of the first mma made the two pipes take turns: 0.53 us per tile).
+          // PAIR: two tiles per iteration, half tiles interleaved (loads of one under the mma of the other) and both
+          // tiles' bookkeeping behind one warp sync: 819 instead of 1025 cycles per round in tools/tile_bench.
+          float rA0, rA2, rB0 = 0.f, rB2 = 0.f;
+          if (two) {
+            const uint32_t ta0 = ring_u32 + sl * TILE_BYTES + lane * 16, ta1 = ring_u32 + slB * TILE_BYTES + lane * 16;
+            const uint2* xp0 = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
+            const uint2* xp1 = reinterpret_cast<const uint2*>(xb + (size_t)ksB * 64 + (lane & 3)) + ((lane >> 2) & 1);
+            uint32_t X[8][4], Y[8][4], Z[8][4];
+            uint2 bp[8], bq[8];
+            float a0[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, a1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(X[s][0], X[s][1], X[s][2], X[s][3], ta0 + s * 512);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) bp[s] = xp0[s * 8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(Y[s][0], Y[s][1], Y[s][2], Y[s][3], ta1 + s * 512);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) bq[s] = xp1[s * 8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mma_bf16_16816(a0[s & 1], X[s], bp[s].x, bp[s].y);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(Z[s][0], Z[s][1], Z[s][2], Z[s][3], ta0 + (s + 8) * 512);
+            cur_slot = sl;
+            release();
+#pragma unroll
+            for (int s = 0; s < 8; ++s) bp[s] = xp0[(s + 8) * 8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mma_bf16_16816(a1[s & 1], Y[s], bq[s].x, bq[s].y);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) ldmatrix_x4(X[s][0], X[s][1], X[s][2], X[s][3], ta1 + (s + 8) * 512);
+            cur_slot = slB;
+            release();
+#pragma unroll
+            for (int s = 0; s < 8; ++s) bq[s] = xp1[(s + 8) * 8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mma_bf16_16816(a0[s & 1], Z[s], bp[s].x, bp[s].y);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mma_bf16_16816(a1[s & 1], X[s], bq[s].x, bq[s].y);
+            rA0 = (a0[0][0] + a0[1][0]) + (a0[0][1] + a0[1][1]);
+            rA2 = (a0[0][2] + a0[1][2]) + (a0[0][3] + a0[1][3]);
+            rB0 = (a1[0][0] + a1[1][0]) + (a1[0][1] + a1[1][1]);
+            rB2 = (a1[0][2] + a1[1][2]) + (a1[0][3] + a1[1][3]);
+          } else {
+            cur_slot = sl;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
             const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
             const uint2* xp = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
             uint2 b[16];
@@ -801,95 +851,110 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               }
             }
             // lanes with (lane & 3) == 0 hold columns 0 (hi) and 1 (lo) of rows g (c[0], c[1]) and g + 8 (c[2], c[3])
-            acc[0] = (acc[0] + c1[0]) + (acc[1] + c1[1]);
-            acc[2] = (acc[2] + c1[2]) + (acc[3] + c1[3]);
+            rA0 = (acc[0] + c1[0]) + (acc[1] + c1[1]);
+            rA2 = (acc[2] + c1[2]) + (acc[3] + c1[3]);
           }
-          const uint32_t gslot = (gb0 + k) % NG;
-          if (ks == 0 && (ph == PH_O || ph == PH_DOWN) && lane < 16) {
+          const uint32_t gsA = (gb0 + k) % NG, gsB = (gb0 + kB) % NG;
+          if ((ph == PH_O || ph == PH_DOWN) && lane < 16) {
             // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
             // critical path of the group's epilogue (the value was published two or more phases ago)
-            const int row = (g0 + (int)k) * 16 + lane;
-            float bres = 0.f;
-            if (row < p.H)
-              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
-                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
-            rbuf[gslot * 16 + lane] = bres;
-          }
-          const uint32_t n = nb0 + j;
-          if ((lane & 3) == 0) {
-            float* tp = tpart + (n % NT) * 16;
-            tp[lane >> 2] = acc[0];
-            tp[(lane >> 2) + 8] = acc[2];
-          }
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) {
-            __threadfence_block();
-            last = (atomicAdd(&gcnt[gslot], 1) == tpg - 1);
-          }
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {
-            __threadfence_block();
-            // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
-            const uint32_t n0 = nb0 + k * tpg;
-            float v = 0.f;
-            if (lane < 16)
-              for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
-            const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
-            if (lane == 0) gcnt[gslot] = 0;
-            if (lane < 8) {
-              const int gi = g0 + (int)k, r = lane;
-              if (ph == PH_QKV) {
-                const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
-                const int row0 = hb * 128 + i;
-                const float a0 = v * rn, a1 = v1 * rn;
-                if (row0 < qd + kd) {
-                  const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-                  const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
-                  if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
-                  else {
-                    const int kh = (row0 - qd) >> 7;
-                    bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-                    const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
-                    dd[i] = z0;
-                    dd[i + 64] = z1;
-                    st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
-                    st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-                  }
-                } else {
-                  const int kh = (row0 - qd - kd) >> 7;
-                  bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-                  const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
-                  dd[i] = z0;
-                  dd[i + 64] = z1;
-                  st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
-                  st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-                }
-              } else if (ph == PH_O || ph == PH_DOWN) {
-                u64* dst = (ph == PH_O) ? t_xa : t_xb;
-                const int r0 = gi * 16 + r, r1 = r0 + 8;
-                const float b0 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + gslot * 16 + r + 8);
-                if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
-                if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
-              } else if (ph == PH_GU) {
-                const int i = gi * 8 + r;
-                if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
-              } else {
-                const int r0 = gi * 16 + r, r1 = r0 + 8;
-                const float l0 = v * rn, l1 = v1 * rn;
-                if (r0 < p.V) p.logits[r0] = l0;
-                if (r1 < p.V) p.logits[r1] = l1;
-                if (p.fuse_greedy) {   // rows are visited in increasing order per thread: '>' keeps the lowest index on ties
-                  if (r0 < p.V && r0 != p.bad_token && l0 > best_v) { best_v = l0; best_i = r0; }
-                  if (r1 < p.V && r1 != p.bad_token && l1 > best_v) { best_v = l1; best_i = r1; }
-                }
-              }
+#pragma unroll 1
+            for (int t = 0; t < (two ? 2 : 1); ++t) {
+              if ((t ? ksB : ks) != 0) continue;
+              const int row = (g0 + (int)(t ? kB : k)) * 16 + lane;
+              float bres = 0.f;
+              if (row < p.H)
+                bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
+                                              : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
+              rbuf[(t ? gsB : gsA) * 16 + lane] = bres;
             }
           }
+          if ((lane & 3) == 0) {
+            float* tp = tpart + ((nb0 + j) % NT) * 16;
+            tp[lane >> 2] = rA0;
+            tp[(lane >> 2) + 8] = rA2;
+            if (two) {
+              float* tq = tpart + ((nb0 + j + NCW) % NT) * 16;
+              tq[lane >> 2] = rB0;
+              tq[(lane >> 2) + 8] = rB2;
+            }
+          }
+          __syncwarp();
+          int oldA = -1, oldB = -1;
+          if (lane == 0) {
+            __threadfence_block();
+            oldA = atomicAdd(&gcnt[gsA], 1);
+            if (two) oldB = atomicAdd(&gcnt[gsB], 1);   // same group as A (tpg > 8): only this one can come last
+          }
+          const int lastA = __shfl_sync(0xffffffffu, oldA == tpg - 1, 0);
+          const int lastB = PAIR ? __shfl_sync(0xffffffffu, oldB == tpg - 1, 0) : 0;
+#pragma unroll 1
+          for (int t = 0; t < (PAIR ? 2 : 1); ++t) {
+            if (!(t ? lastB : lastA)) continue;
+            const uint32_t ek = t ? kB : k, egs = t ? gsB : gsA;
+              __threadfence_block();
+              // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
+              const uint32_t n0 = nb0 + ek * tpg;
+              float v = 0.f;
+              if (lane < 16)
+                for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
+              const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
+              if (lane == 0) gcnt[egs] = 0;
+              if (lane < 8) {
+                const int gi = g0 + (int)ek, r = lane;
+                if (ph == PH_QKV) {
+                  const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
+                  const int row0 = hb * 128 + i;
+                  const float a0 = v * rn, a1 = v1 * rn;
+                  if (row0 < qd + kd) {
+                    const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+                    const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
+                    if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
+                    else {
+                      const int kh = (row0 - qd) >> 7;
+                      bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
+                      const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
+                      dd[i] = z0;
+                      dd[i + 64] = z1;
+                      st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
+                      st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                    }
+                  } else {
+                    const int kh = (row0 - qd - kd) >> 7;
+                    bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
+                    const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
+                    dd[i] = z0;
+                    dd[i + 64] = z1;
+                    st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
+                    st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                  }
+                } else if (ph == PH_O || ph == PH_DOWN) {
+                  u64* dst = (ph == PH_O) ? t_xa : t_xb;
+                  const int r0 = gi * 16 + r, r1 = r0 + 8;
+                  const float b0 = *reinterpret_cast<volatile float*>(rbuf + egs * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + egs * 16 + r + 8);
+                  if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
+                  if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
+                } else if (ph == PH_GU) {
+                  const int i = gi * 8 + r;
+                  if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
+                } else {
+                  const int r0 = gi * 16 + r, r1 = r0 + 8;
+                  const float l0 = v * rn, l1 = v1 * rn;
+                  if (r0 < p.V) p.logits[r0] = l0;
+                  if (r1 < p.V) p.logits[r1] = l1;
+                  if (p.fuse_greedy) {   // rows are visited in increasing order per thread: '>' keeps the lowest index on ties
+                    if (r0 < p.V && r0 != p.bad_token && l0 > best_v) { best_v = l0; best_i = r0; }
+                    if (r1 < p.V && r1 != p.bad_token && l1 > best_v) { best_v = l1; best_i = r1; }
+                  }
+                }
+              }
+          }
           if (DBG && trow && lane == 0) trow[2] = clock64();
-          sl += NCW;
-          if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
-          ks += NCW;
+          const int adv = two ? 2 * NCW : NCW;   // (a lone last tile: the loop ends anyway)
+          j += PAIR ? 2 * NCW : NCW;
+          sl += adv;
+          while (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+          ks += adv;
           while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
         }
       }
@@ -1023,7 +1088,9 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
 cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint64_t* counter) {
   const int smem = mega_smem_bytes(a);
   const bool dbgk = a.dbg != nullptr || a.dbg2 != nullptr || a.dbg_flags != 0;
-  const void* fn = dbgk ? (const void*)decode_mega_kernel<true> : (const void*)decode_mega_kernel<false>;
+  const bool pair = (a.variant & 4) != 0;   // two tiles per consumer-warp iteration
+  const void* fn = dbgk ? (pair ? (const void*)decode_mega_kernel<true, true> : (const void*)decode_mega_kernel<true, false>)
+                        : (pair ? (const void*)decode_mega_kernel<false, true> : (const void*)decode_mega_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&a};

@@ -1172,6 +1172,11 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     set_gemm_impl((int)value);
     return DTK_OK;
   }
+  if (std::strcmp(key, "gemm_swap_split") == 0) {  // process-wide dev switch: split-K factor of the batched-decode GEMM
+    DTK_REQUIRE(value >= 0 && value <= 8, "gemm_swap_split must be 0 (heuristic) .. 8");
+    set_gemm_swap_split((int)value);
+    return DTK_OK;
+  }
   if (std::strcmp(key, "gemm_skinny_swap") == 0) {  // process-wide dev switch
     set_gemm_skinny_swap(value ? 1 : 0);
     return DTK_OK;
@@ -1249,7 +1254,10 @@ int dtk_dbg_mega_trace(dtk_engine* eng, long long* out_host, int max_values) {
 }
 
 int dtk_dbg_gemm_impl(int impl) {
-  if (impl >= 0) set_gemm_impl(impl);
+  if (impl >= 0) {
+    set_gemm_impl(impl & 0xff);
+    set_gemm_swap_split((impl >> 8) & 0xf);   // forced split-K factor of the batched-decode tile (0 = heuristic)
+  }
   return get_gemm_impl();
 }
 

@@ -202,9 +202,29 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __g
 // mostly zero fill next to 4 KB of weights as in the 128 x 32 tile above. The accumulator comes out transposed (TMEM lane =
 // output feature n, column = batch row b): for a fixed b the 32 lanes of a warp store 32 consecutive outputs (coalesced).
 // Epilogue: bias, residual, SwiGLU (gate_i / up_i are adjacent ROWS of W = adjacent lanes: one shuffle), fp32 or bf16 out.
+//
+// Split-K over a thread-block cluster: a decode GEMM has only N / 128 weight tiles (32 for a 4096-wide projection), far fewer
+// than 2 x 148 CTA slots, and a CTA's bytes in flight are bounded by its ring. `nsplit` CTAs of one cluster share a tile, each
+// streams a contiguous K range into its own TMEM accumulator, ranks > 0 park their fp32 partial tile in their shared memory
+// and rank 0 adds them IN RANK ORDER through distributed shared memory (deterministic) and runs the epilogue. No workspace in
+// HBM, no atomics. Two CTAs per SM (5-stage rings) keep ~200 KB of weights in flight per SM.
+DTK_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+DTK_DEV void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+DTK_DEV float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
 template <int NB, int TSTAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap mapW,
-                                                                    const __grid_constant__ CUtensorMap mapX, const GemmArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap mapW,
+                                                                    const __grid_constant__ CUtensorMap mapX, const GemmArgs p,
+                                                                    const int nsplit) {
   constexpr int X_BYTES = NB * TBK * 2;
   constexpr int STAGE_BYTES = A_BYTES + X_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -213,8 +233,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __gri
   const uint32_t bars = sbase + TSTAGES * STAGE_BYTES;
   const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull = bars + 16 * TSTAGES, tptr = tfull + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TBM;
-  const int KT = (p.K + TBK - 1) / TBK;
+  const uint32_t rank = nsplit > 1 ? cluster_ctarank() : 0u;
+  const int n0 = (blockIdx.x / nsplit) * TBM;
+  const int KTall = (p.K + TBK - 1) / TBK;
+  const int kt0 = (int)((int64_t)KTall * rank / nsplit), KT = (int)((int64_t)KTall * (rank + 1) / nsplit) - kt0;   // this CTA's k-blocks
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
@@ -238,8 +260,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __gri
         if (use > 0) tc_wait(empty0 + 8 * s, (use - 1) & 1);
         const uint32_t sw = sbase + s * STAGE_BYTES, sx = sw + A_BYTES;
         tc_expect_tx(full0 + 8 * s, STAGE_BYTES);
-        tma_load_2d(sw, &mapW, kt * TBK, n0, full0 + 8 * s);
-        tma_load_2d(sx, &mapX, kt * TBK, 0, full0 + 8 * s);
+        tma_load_2d(sw, &mapW, (kt0 + kt) * TBK, n0, full0 + 8 * s);
+        tma_load_2d(sx, &mapX, (kt0 + kt) * TBK, 0, full0 + 8 * s);
       }
     }
   } else if (warp == 5) {
@@ -256,7 +278,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __gri
       }
       umma_commit(tfull);
     }
-  } else {
+  }
+  // partial tiles of ranks > 0: [NB][128] fp32 in the (drained) ring, column-major so that lanes write consecutive words
+  const uint32_t part = sbase + (uint32_t)(warp * 32 + lane) * 4;
+  if (warp < 4 && rank != 0) {
+    tc_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < NB; cb += 32) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(trow + (uint32_t)cb));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(part + (uint32_t)(cb + j) * 512u), "r"(r[j]) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  if (nsplit > 1) cluster_sync_all();   // partials of every rank are visible to rank 0
+  if (warp < 4 && rank == 0) {
     // epilogue warps 0..3: TMEM lanes 32w..32w+31 = output features n0 + 32w + lane, columns = batch rows
     tc_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -279,7 +326,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __gri
       for (int j = 0; j < 32; ++j) {
         const int b = cb + j;            // batch row (warp-uniform)
         if (b >= p.M) break;
-        float v = __uint_as_float(r[j]) + bias;
+        float v = __uint_as_float(r[j]);
+        for (uint32_t q = 1; q < (uint32_t)nsplit; ++q) v += ld_dsmem_f32(part + (uint32_t)b * 512u, q);   // K ranges in order
+        v += bias;
         if (p.glu) {
           const float other = __shfl_xor_sync(0xffffffffu, v, 1);   // lane pairs (gate, up)
           if (!(lane & 1) && n + 1 < p.N + 1 && n < p.N) {
@@ -300,6 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_swap_kernel(const __gri
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
+  if (nsplit > 1) cluster_sync_all();   // rank 0 has read every partial: the other CTAs' shared memory may go away
   __syncthreads();
   if (warp == 5) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -366,6 +416,9 @@ static cudaError_t launch_tc_variant(const GemmArgs& a, cudaStream_t s, uint64_t
   return cudaGetLastError();
 }
 
+static int g_swap_split = 0;   // dev switch (dtk_set_option "gemm_swap_split"): 0 = heuristic, 1..8 = forced split-K factor
+void set_gemm_swap_split(int v) { g_swap_split = v; }
+
 template <int NB, int TSTAGES>
 static cudaError_t launch_tc_swap(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   CUtensorMap mapW, mapX;
@@ -380,9 +433,43 @@ static cudaError_t launch_tc_swap(const GemmArgs& a, cudaStream_t s, uint64_t* c
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  gemm_tc_swap_kernel<NB, TSTAGES><<<(a.N + TBM - 1) / TBM, TC_THREADS, smem, s>>>(mapW, mapX, a);
+  // split-K factor: fewest waves over 2 x SMs CTA slots per unit of K, at least 8 k-blocks per CTA, a small price per rank
+  static int slots[64] = {};
+  if (dev >= 0 && dev < 64 && !slots[dev]) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    slots[dev] = 2 * sms;
+  }
+  const int nslot = (dev >= 0 && dev < 64) ? slots[dev] : 296;
+  const int tiles = (a.N + TBM - 1) / TBM, KT = (a.K + TBK - 1) / TBK;
+  int nsplit = 1;
+  if (g_swap_split == 0) {
+    double best = 1e30;
+    for (int sp = 1; sp <= 8; ++sp) {
+      if (sp > 1 && KT / sp < 8) break;
+      const double waves = (double)((tiles * sp + nslot - 1) / nslot);
+      const double cost = waves / sp + 0.02 * sp;
+      if (cost < best - 1e-9) { best = cost; nsplit = sp; }
+    }
+  } else {
+    nsplit = g_swap_split;
+    while (nsplit > 1 && KT / nsplit < 1) --nsplit;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tiles * nsplit));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nsplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gemm_tc_swap_kernel<NB, TSTAGES>, mapW, mapX, a, nsplit);
   if (counter) ++*counter;
-  return cudaGetLastError();
+  return e;
 }
 
 static int g_skinny_swap = 1;   // dev switch (dtk_set_option "gemm_skinny_swap"): 1 = swapped-operand tile for M < 64
@@ -391,7 +478,7 @@ void set_gemm_skinny_swap(int v) { g_skinny_swap = v; }
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaSuccess;
   if (a.M < 64 && g_skinny_swap && a.act == ACT_NONE && !a.rowbias) {   // batched decode: weights are the M side
-    return a.M <= 32 ? launch_tc_swap<32, 8>(a, s, counter) : launch_tc_swap<64, 8>(a, s, counter);
+    return a.M <= 32 ? launch_tc_swap<32, 5>(a, s, counter) : launch_tc_swap<64, 4>(a, s, counter);
   }
   if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
   return launch_tc_variant<128, 3, 2>(a, s, counter);

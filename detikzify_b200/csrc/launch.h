@@ -36,6 +36,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter);  
 cudaError_t launch_gemm_mma(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter);
 bool gemm_tc_supported(const GemmArgs& a);
+void set_gemm_swap_split(int v);    // dev: 0 (default) = heuristic split-K factor of the swapped tile, 1..8 = forced
 void set_gemm_skinny_swap(int v);   // dev: 1 (default) = swapped-operand tcgen05 tile for M < 64, 0 = 128 x 32 tile
 void set_gemm_impl(int impl);   // 0 = mma.sync everywhere, 1 = tcgen05 where supported (process-wide dev switch)
 int get_gemm_impl();

@@ -199,7 +199,8 @@ DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_val
  * rows 160..164 = the layer's five phases {start, staged, items done, barrier done}; returns the value count */
 DTK_API int dtk_dbg_mega_trace(dtk_engine* eng, long long* out_host, int max_values);
 /* select the dense GEMM implementation used by dtk_dbg_gemm and the engines of this process:
- * 0 = mma.sync, 1 = tcgen05/TMEM where supported, -1 = query only; returns the current setting */
+ * 0 = mma.sync, 1 = tcgen05/TMEM where supported, -1 = query only; returns the current setting. Bits 8..11 of a
+ * non-negative value force the split-K factor (cluster size 1..8) of the batched-decode tile; 0 = heuristic. */
 DTK_API int dtk_dbg_gemm_impl(int impl);
 /* C = act(A[M,K] * W[N,K]^T + bias) (+resid); glu: out[m, n/2] = silu(c[m,n]) * c[m,n+1] */
 DTK_API int dtk_dbg_gemm(const void* A_bf16, const void* W_bf16, const void* bias_bf16,

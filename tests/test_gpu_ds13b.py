@@ -71,6 +71,12 @@ def test_ds13b_prefill_decode_and_2k_context():
         assert (lastp.cpu() - ref_long[0, 2046]).abs().max() < TOL
         lg = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()
         assert (lg - ref_long[0, 2047]).abs().max() < TOL
+        # scheduling variants of the persistent kernel are bit-identical (same summation order)
+        for variant in (2, 4):
+            eng.set_option("mega_variant", variant)
+            lgv = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()
+            assert torch.equal(lgv, lg), variant
+        eng.set_option("mega_variant", 0)
         # per-op implementation at the same point
         eng.set_option("decode_impl", 0)
         lg0 = eng.decode([slot], [2047], long_ids[2047:].cuda())[0].cpu()

@@ -64,6 +64,29 @@ def test_gemm_matches_torch(M, N, K, bias, act, resid, glu, obf, impl):
         _lib().dtk_dbg_gemm_impl(prev)
 
 
+SPLIT_SHAPES = [
+    # (M, N, K, bias, resid, glu, out_bf16): the batched-decode tile (weights as the UMMA M side) with cluster split-K
+    (32, 4096, 4096, False, True, False, False),      # 7b o-proj + residual
+    (32, 4096, 11008, False, True, False, False),     # 7b down + residual
+    (32, 22016, 4096, False, False, True, True),      # 7b gate/up GLU
+    (48, 6144, 2048, True, False, False, False),      # NB = 64 tile, bias
+    (5, 1000, 264, False, False, False, False),       # ragged N and K, fewer k-blocks than ranks allow
+]
+
+
+@pytest.mark.parametrize("split", [0, 1, 2, 3, 8])
+@pytest.mark.parametrize("M,N,K,bias,resid,glu,obf", SPLIT_SHAPES)
+def test_batched_decode_gemm_cluster_split_k(M, N, K, bias, resid, glu, obf, split):
+    """Split-K over a thread-block cluster with the DSMEM reduction on rank 0: every factor gives the torch result, and the
+    result does not depend on run-to-run timing (ranks are added in order)."""
+    prev = _lib().dtk_dbg_gemm_impl(-1)
+    _lib().dtk_dbg_gemm_impl(1 | (split << 8))
+    try:
+        _gemm_case(M, N, K, bias, 0, resid, glu, obf)
+    finally:
+        _lib().dtk_dbg_gemm_impl(prev)
+
+
 def _gemm_case(M, N, K, bias, act, resid, glu, obf):
     torch.manual_seed(M * 131 + N * 7 + K)
     dev = "cuda"

@@ -357,6 +357,29 @@ def test_persistent_and_per_op_decode_agree():
     assert (out[0] - out[1]).abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("name", ["tiny", "tiny2"])
+def test_persistent_decode_variants_are_bit_identical(name):
+    """mega_variant bit 1 (arrival counter in front of the staging) and bit 2 (two tiles per consumer-warp iteration)
+    change scheduling only: partial sums are added in the same order, so the logits must be bit-identical."""
+    cfg, sd, oracle = model_bundle(name)
+    eng = engine_for(name)
+    ids = _prompt(cfg, n_text=40).cuda()
+    img = eng.image_embeds(_pixels(cfg, 1).cuda())[0]
+    slot = eng.seq_alloc()
+    try:
+        eng.prefill(slot, ids, 0, img, 0)
+        out = {}
+        for variant in (0, 2, 4, 6):
+            eng.set_option("mega_variant", variant)
+            out[variant] = torch.stack([eng.decode([slot], [ids.numel() + i], torch.tensor([23 + i], device="cuda"))[0].clone() for i in range(6)])
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("mega_variant", 0)
+        eng.seq_free(slot)
+    for variant in (2, 4, 6):
+        assert torch.equal(out[variant], out[0]), variant
+
+
 # ---------------------------------------------------------------- against the reference's own generate() output
 @pytest.mark.parametrize("name", ["tiny", "tiny2"])
 def test_public_generate_matches_reference_golden_ids(name):

@@ -94,6 +94,12 @@ def test_v2_8b_shapes_decode_and_sampler():
             lg = eng.decode([slots[B - 1]], [lens[B - 1]], tok1[B - 1:].cuda())[0].cpu()
             assert (lg - ref0[0, -1]).abs().max().item() < TOL, impl
         eng.set_option("decode_impl", 1)
+        # kernel variants (bit 1: arrival counter, bit 2: two tiles per consumer-warp iteration) sum in the same order
+        base = eng.decode([slots[B - 1]], [lens[B - 1]], tok1[B - 1:].cuda())[0].clone()
+        for variant in (2, 4, 6):
+            eng.set_option("mega_variant", variant)
+            assert torch.equal(eng.decode([slots[B - 1]], [lens[B - 1]], tok1[B - 1:].cuda())[0], base), variant
+        eng.set_option("mega_variant", 0)
         # batched-GEMM decode of all 8 sequences (rewrites the same KV rows)
         step = eng.decode(slots, lens, tok1.cuda()).clone()
         for i in (0, 3, B - 1):

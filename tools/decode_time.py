@@ -12,14 +12,18 @@ ids = torch.randint(0, 30000, (ctx,), generator=torch.Generator().manual_seed(1)
 eng.prefill(slot, ids, 0, None, 0)
 tok = torch.tensor([5], device="cuda")
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
 for rep in range(3):
-    for _ in range(5):
-        eng.decode([slot], [ctx], tok)
-    torch.cuda.synchronize(); ev0.record()
-    for _ in range(20):
-        eng.decode([slot], [ctx], tok)
-    ev1.record(); torch.cuda.synchronize()
-    print(f"ctx {ctx}: ms/token {ev0.elapsed_time(ev1) / 20:.4f}")
+    for variant in variants:
+        eng.set_option("mega_variant", variant)
+        for _ in range(5):
+            eng.decode([slot], [ctx], tok)
+        torch.cuda.synchronize(); ev0.record()
+        for _ in range(20):
+            eng.decode([slot], [ctx], tok)
+        ev1.record(); torch.cuda.synchronize()
+        print(f"ctx {ctx} variant {variant}: ms/token {ev0.elapsed_time(ev1) / 20:.4f}")
+eng.set_option("mega_variant", 0)
 lg1 = eng.decode([slot], [ctx], tok)[0].clone()
 eng.set_option("decode_impl", 0)
 lg0 = eng.decode([slot], [ctx], tok)[0].clone()
