@@ -236,18 +236,6 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   return a;
 }
 
-// sum over the 256 consumer threads (fixed order: identical in every CTA)
-DTK_DEV float consumer_sum(float v, float* red) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  consumer_sync();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < NCW; ++i) t += red[i];
-  consumer_sync();
-  return t;
-}
-
 // Stage a K-vector into shared memory as the B operand of mma.m16n8k16:
 // entry [kstep S][t] (uint4) = { hi(x[16S+2t], x[16S+2t+1]), hi(x[16S+2t+8], +9), lo(..2t..), lo(..2t+8..) }
 // where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad column reads
@@ -349,9 +337,21 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags,
 #pragma unroll
     for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
   }
-  float r = 1.f;
-  if (norm_w) r = rsqrtf(consumer_sum(ss, red) / K + eps);
+  // sum of squares: per-warp partials, ONE barrier (the one that publishes the staged vector), every thread adds the eight
+  // partials in the same order (identical r in every CTA). `red` is rewritten by the next normed staging only, which is
+  // behind at least one more consumer barrier.
+  if (norm_w) {
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+  }
   consumer_sync();
+  float r = 1.f;
+  if (norm_w) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCW; ++i) t += red[i];
+    r = rsqrtf(t / K + eps);
+  }
   return r;
 }
 
@@ -985,6 +985,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
     }
     int* red_i = reinterpret_cast<int*>(red + 8);
+    consumer_sync();   // every warp has read the final norm's partial sums out of `red`
     if (lane == 0) { red[warp] = best_v; red_i[warp] = best_i; }
     consumer_sync();
     if (tid == 0) {

@@ -1168,7 +1168,7 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     return DTK_OK;
   }
   if (std::strcmp(key, "gemm_impl") == 0) {  // process-wide dev switch: 0 = mma.sync, 1 = tcgen05 where supported
-    DTK_REQUIRE(value == 0 || value == 1, "gemm_impl must be 0 or 1");
+    DTK_REQUIRE(value >= 0 && value <= 2, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);
     return DTK_OK;
   }

@@ -156,14 +156,14 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_tn_kernel(const GemmArgs p)
 
 }  // namespace
 
-static int g_gemm_impl = 1;  // 1 = tcgen05/TMA/TMEM kernel for M >= 64 (default), 0 = mma.sync kernel everywhere (dtk_set_option "gemm_impl")
+static int g_gemm_impl = 1;  // 0 = mma.sync everywhere, 1 = tcgen05 one-tile-per-CTA 128 x 128 kernel, 2 = persistent 128 x 256 tcgen05 kernel (dtk_set_option "gemm_impl")
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 int get_gemm_impl() { return g_gemm_impl; }
 
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
   // large-M dense contractions go to the tcgen05/TMEM kernel; tiny M (pool head, M = B) stays on mma.sync
   // (M < 4: pool-head probes and other tiny products stay on mma.sync; 4 <= M < 64 takes the skinny tcgen05 tile)
-  if (g_gemm_impl == 1 && a.M >= 4 && gemm_tc_supported(a)) return launch_gemm_tc(a, s, counter);
+  if (g_gemm_impl >= 1 && a.M >= 4 && gemm_tc_supported(a)) return launch_gemm_tc(a, s, counter);
   return launch_gemm_mma(a, s, counter);
 }
 

@@ -195,6 +195,163 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __g
   }
 }
 
+// ---- persistent 128 x 256 kernel (gemm_impl = 2): the dense ViT / prefill contractions.
+// One CTA per SM walks the output tiles (m fastest: concurrent CTAs share a 256-row band of W); three pipelines:
+//   warp 4  TMA producer : 4-stage ring of {A 128 x 64, W 256 x 64} SWIZZLE_128B boxes (48 KB per stage), runs ahead across
+//                          tile boundaries
+//   warp 5  MMA issuer   : tcgen05.mma M128 x N256 x K16 into one of TWO 256-column TMEM accumulators (all 512 columns):
+//                          the next tile's main loop starts while the epilogue warps drain the previous accumulator
+//   warps 0-3 epilogue   : tcgen05.ld 32x32b (thread = row) -> padded shared-memory transpose (33-word rows) -> thread =
+//                          COLUMN: bias / activation / position rows / residual / SwiGLU are read and written as whole
+//                          128-byte row segments (the one-tile kernel above stores 8 bytes per thread at row stride: 32
+//                          sectors per instruction; that epilogue, not the tensor pipe, bounded it at ~300 TF/s in the ViT)
+constexpr int PBN = 256, PSTAGES = 4;
+constexpr int PB_BYTES = PBN * TBK * 2;                    // 32 KB
+constexpr int PSTAGE_BYTES = A_BYTES + PB_BYTES;           // 48 KB
+constexpr int PSTG_WORDS = 32 * 33;                        // per epilogue warp: 32 rows x 32 columns, padded
+constexpr int PSMEM = PSTAGES * PSTAGE_BYTES + 4 * PSTG_WORDS * 4 + 256 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                        const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  const uint32_t stg0 = sbase + PSTAGES * PSTAGE_BYTES;
+  const uint32_t bars = stg0 + 4 * PSTG_WORDS * 4;
+  const uint32_t full0 = bars, empty0 = bars + 8 * PSTAGES, afull0 = bars + 16 * PSTAGES, aempty0 = afull0 + 16, tptr = aempty0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KT = (p.K + TBK - 1) / TBK;
+  const int MT = (p.M + TBM - 1) / TBM, NT = (p.N + PBN - 1) / PBN;
+  const int tiles = MT * NT;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { tc_mbar_init(afull0 + 8 * a, 1); tc_mbar_init(aempty0 + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tptr), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tptr));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;   // k-blocks issued so far (ring position across tiles)
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile % MT) * TBM, n0 = (tile / MT) * PBN;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const uint32_t s = it % PSTAGES, use = it / PSTAGES;
+          if (use > 0) tc_wait(empty0 + 8 * s, (use - 1) & 1);
+          const uint32_t sa = sbase + s * PSTAGE_BYTES, sb = sa + A_BYTES;
+          tc_expect_tx(full0 + 8 * s, PSTAGE_BYTES);
+          tma_load_2d(sa, &mapA, kt * TBK, m0, full0 + 8 * s);
+          tma_load_2d(sb, &mapB, kt * TBK, n0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    if (lane == 0) {
+      uint32_t it = 0, nt = 0;   // k-blocks / tiles consumed so far
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
+        const uint32_t acc = nt & 1, ause = nt >> 1;
+        if (ause > 0) tc_wait(aempty0 + 8 * acc, (ause - 1) & 1);   // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t tacc = tmem + acc * PBN;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const uint32_t s = it % PSTAGES, use = it / PSTAGES;
+          tc_wait(full0 + 8 * s, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t sa = sbase + s * PSTAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) umma_f16(tacc, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (kt | k) != 0);
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(afull0 + 8 * acc);
+      }
+    }
+  } else {
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg0 - sraw)) + warp * PSTG_WORDS;
+    uint32_t nt = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
+      const uint32_t acc = nt & 1, ause = nt >> 1;
+      const int m0 = (tile % MT) * TBM, n0 = (tile / MT) * PBN;
+      tc_wait(afull0 + 8 * acc, ause & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t trow = tmem + acc * PBN + ((uint32_t)(warp * 32) << 16);
+      const int mrow0 = m0 + warp * 32;
+      const int nrows = min(32, p.M - mrow0);   // rows of this warp inside the matrix (may be <= 0)
+#pragma unroll 1
+      for (int cb = 0; cb < PBN; cb += 32) {
+        if (n0 + cb >= p.N) break;
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(trow + (uint32_t)cb));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (cb + 32 >= PBN || n0 + cb + 32 >= p.N) {
+          // last chunk of this tile is in registers: hand the accumulator back before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(aempty0 + 8 * acc) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // thread = row: bank (lane + j) % 32
+        __syncwarp();
+        // thread = column n: whole 128-byte row segments from here on
+        const int n = n0 + cb + lane;
+        const bool nin = n < p.N;
+        float bias = 0.f;
+        if (p.bias && nin) bias = __bfloat162float(p.bias[n]);
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr >= nrows) break;
+          const int m = mrow0 + rr;
+          float v = stg[rr * 33 + lane] + bias;
+          if (p.act == ACT_GELU_TANH) v = gelu_tanh(v);
+          else if (p.act == ACT_GELU_ERF) v = gelu_erf(v);
+          if (p.glu) {   // columns (gate, up) are adjacent lanes; out[m, n / 2]
+            const float up = __shfl_down_sync(0xffffffffu, v, 1);
+            if (!(lane & 1) && nin) {
+              const float rv = silu(v) * up;
+              const int64_t o = (int64_t)m * p.ldo + (n >> 1);
+              if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rv);
+              else p.out_f32[o] = rv;
+            }
+            continue;
+          }
+          if (nin) {
+            if (p.rowbias) v += __bfloat162float(p.rowbias[(int64_t)(m % p.rowbias_mod) * p.N + n]);
+            if (p.resid) v += p.resid[(int64_t)m * p.ldr + n];
+          }
+          if (p.out_bf16) {
+            const float hi = __shfl_down_sync(0xffffffffu, v, 1);
+            if (!(lane & 1) && nin) *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)m * p.ldo + n) = pack_bf16x2(v, hi);   // N is even
+          } else if (nin) {
+            p.out_f32[(int64_t)m * p.ldo + n] = v;
+          }
+        }
+        __syncwarp();   // the staging tile is rewritten by the next chunk
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+  }
+}
+
 // ---- swapped-operand tile for the batched decode step (M = rollouts <= 64): out[b, n] = sum_k X[b, k] W[n, k].
 // The weight rows are the UMMA M dimension (128 rows of W per CTA, K-major, straight from the arena) and the few batch rows
 // are the N dimension (NB = 32 or 64 columns): per 64-wide k-block a CTA moves 16 KB of weights (bytes that must come from
@@ -213,11 +370,14 @@ DTK_DEV void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-DTK_DEV float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+DTK_DEV uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {   // same offset in the shared memory of CTA `rank`
   uint32_t ra;
-  float v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+  return ra;
+}
+DTK_DEV float4 ld_dsmem_v4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
   return v;
 }
 
@@ -279,8 +439,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __gri
       umma_commit(tfull);
     }
   }
-  // partial tiles of ranks > 0: [NB][128] fp32 in the (drained) ring, column-major so that lanes write consecutive words
-  const uint32_t part = sbase + (uint32_t)(warp * 32 + lane) * 4;
+  // partial tiles of ranks > 0: [128 rows][NB] fp32 in the (drained) ring, a row = one thread's NB values as 16-byte chunks,
+  // chunk index XOR (row & 7): conflict-free 128-bit stores here and 128-bit distributed-shared-memory loads on rank 0
+  const uint32_t prow = sbase + (uint32_t)(warp * 32 + lane) * (NB * 4);
+  const uint32_t psw = (uint32_t)(lane & 7);
   if (warp < 4 && rank != 0) {
     tc_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -297,8 +459,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __gri
           : "r"(trow + (uint32_t)cb));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(part + (uint32_t)(cb + j) * 512u), "r"(r[j]) : "memory");
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(prow + ((((uint32_t)(cb >> 2) + c) ^ psw) << 4)), "r"(r[4 * c]),
+                     "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
+                     : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
@@ -322,13 +486,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __gri
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(trow + (uint32_t)cb));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      // partial sums of the other ranks, K ranges in order: eight independent 16-byte loads per rank in flight
+#pragma unroll 1
+      for (uint32_t q = 1; q < (uint32_t)nsplit; ++q) {
+        const uint32_t rrow = dsmem_addr(prow, q);
+        float4 t[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = ld_dsmem_v4(rrow + ((((uint32_t)(cb >> 2) + c) ^ psw) << 4));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          r[4 * c] = __float_as_uint(__uint_as_float(r[4 * c]) + t[c].x);
+          r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + t[c].y);
+          r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + t[c].z);
+          r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + t[c].w);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int b = cb + j;            // batch row (warp-uniform)
         if (b >= p.M) break;
-        float v = __uint_as_float(r[j]);
-        for (uint32_t q = 1; q < (uint32_t)nsplit; ++q) v += ld_dsmem_f32(part + (uint32_t)b * 512u, q);   // K ranges in order
-        v += bias;
+        float v = __uint_as_float(r[j]) + bias;
         if (p.glu) {
           const float other = __shfl_xor_sync(0xffffffffu, v, 1);   // lane pairs (gate, up)
           if (!(lane & 1) && n + 1 < p.N + 1 && n < p.N) {
@@ -433,24 +610,14 @@ static cudaError_t launch_tc_swap(const GemmArgs& a, cudaStream_t s, uint64_t* c
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  // split-K factor: fewest waves over 2 x SMs CTA slots per unit of K, at least 8 k-blocks per CTA, a small price per rank
-  static int slots[64] = {};
-  if (dev >= 0 && dev < 64 && !slots[dev]) {
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    slots[dev] = 2 * sms;
-  }
-  const int nslot = (dev >= 0 && dev < 64) ? slots[dev] : 296;
+  // split-K factor. A CTA alone pulls ~65 GB/s through its ring (5 stages x 20 KB per ~1.5 us of latency), so about 110
+  // resident CTAs saturate HBM: GEMMs with that many weight tiles are not split (measured: splitting them only adds the
+  // reduction). Projections with few tiles (N = 4096: 32) get the smallest factor that reaches ~110 CTAs, at least 8
+  // k-blocks per rank.
   const int tiles = (a.N + TBM - 1) / TBM, KT = (a.K + TBK - 1) / TBK;
   int nsplit = 1;
   if (g_swap_split == 0) {
-    double best = 1e30;
-    for (int sp = 1; sp <= 8; ++sp) {
-      if (sp > 1 && KT / sp < 8) break;
-      const double waves = (double)((tiles * sp + nslot - 1) / nslot);
-      const double cost = waves / sp + 0.02 * sp;
-      if (cost < best - 1e-9) { best = cost; nsplit = sp; }
-    }
+    while (nsplit < 8 && tiles * nsplit < 110 && KT / (nsplit + 1) >= 8) ++nsplit;
   } else {
     nsplit = g_swap_split;
     while (nsplit > 1 && KT / nsplit < 1) --nsplit;
@@ -472,6 +639,27 @@ static cudaError_t launch_tc_swap(const GemmArgs& a, cudaStream_t s, uint64_t* c
   return e;
 }
 
+static cudaError_t launch_tc_persist(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  CUtensorMap mapA, mapB;
+  if (!make_map(&mapA, a.A, a.M, a.K, a.lda, TBM) || !make_map(&mapB, a.W, a.N, a.K, a.ldw, PBN)) return cudaErrorInvalidValue;
+  static bool attr_done[64] = {};
+  static int sms[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_done[dev]) {
+    e = cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
+    if (e != cudaSuccess) return e;
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = 148;
+    attr_done[dev] = true;
+  }
+  const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + PBN - 1) / PBN);
+  gemm_tc_persist_kernel<<<tiles < sms[dev] ? tiles : sms[dev], TC_THREADS, PSMEM, s>>>(mapA, mapB, a);
+  if (counter) ++*counter;
+  return cudaGetLastError();
+}
+
 static int g_skinny_swap = 1;   // dev switch (dtk_set_option "gemm_skinny_swap"): 1 = swapped-operand tile for M < 64
 void set_gemm_skinny_swap(int v) { g_skinny_swap = v; }
 
@@ -481,6 +669,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter)
     return a.M <= 32 ? launch_tc_swap<32, 5>(a, s, counter) : launch_tc_swap<64, 4>(a, s, counter);
   }
   if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
+  if (get_gemm_impl() == 2) return launch_tc_persist(a, s, counter);   // persistent 128 x 256, overlapped epilogue
   return launch_tc_variant<128, 3, 2>(a, s, counter);
 }
 

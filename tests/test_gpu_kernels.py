@@ -42,6 +42,9 @@ GEMM_SHAPES = [
     (1, 1152, 1152, True, 0, False, False, False),      # M = 1 (pool head probe)
     (130, 264, 72, False, 0, False, False, False),      # ragged everything
     (300, 32256, 256, False, 0, False, False, False),   # wide N (lm_head all-logits path)
+    (5832, 4304, 1152, True, 1, False, False, True),    # ViT fc1 at B = 8: 782 tiles of 128 x 256 over 148 persistent CTAs
+    (5832, 1152, 4304, True, 0, True, False, False),    # ViT fc2 at B = 8 (fp32 out + residual, ragged K)
+    (2047, 11008, 2048, False, 0, False, True, True),   # prefill gate/up at the 2k context (GLU, bf16 out)
     # batched decode (M = number of rollouts): the skinny 128 x 32 tcgen05 tile
     (32, 6144, 2048, False, 0, False, False, False),    # qkv, 32 rollouts
     (32, 2048, 5504, False, 0, True, False, False),     # down + residual, ragged K tile
@@ -52,10 +55,11 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["mma_sync", "tcgen05", "tcgen05_persistent"])
 @pytest.mark.parametrize("M,N,K,bias,act,resid,glu,obf", GEMM_SHAPES)
 def test_gemm_matches_torch(M, N, K, bias, act, resid, glu, obf, impl):
-    """Both dense-GEMM implementations (mma.sync bring-up kernel, tcgen05/TMA/TMEM kernel) against torch fp32."""
+    """The dense-GEMM implementations (mma.sync bring-up kernel, one-tile tcgen05/TMA/TMEM kernel, persistent 128 x 256
+    tcgen05 kernel with two TMEM accumulators and the transposing epilogue) against torch fp32."""
     prev = _lib().dtk_dbg_gemm_impl(-1)
     _lib().dtk_dbg_gemm_impl(impl)
     try:
