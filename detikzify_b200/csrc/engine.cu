@@ -743,7 +743,7 @@ int dtk_vit_encode(dtk_engine* eng, const float* pixels, int B, float* tokens_ou
       if (r != DTK_OK) return r;
       continue;
     }
-    const int key = nb | (tok ? 1 << 8 : 0) | (pool ? 1 << 9 : 0) | (get_gemm_impl() << 10) | (eng->attn_impl << 11);
+    const int key = nb | (tok ? 1 << 8 : 0) | (pool ? 1 << 9 : 0) | (get_gemm_impl() << 10) | (eng->attn_impl << 12);
     auto it = eng->vit_graphs.find(key);
     if (it == eng->vit_graphs.end()) {
       if (!eng->cap_stream) DTK_CK(cudaStreamCreateWithFlags(&eng->cap_stream, cudaStreamNonBlocking));

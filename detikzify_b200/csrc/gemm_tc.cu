@@ -197,27 +197,40 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __g
 
 // ---- persistent 128 x 256 kernel (gemm_impl = 2): the dense ViT / prefill contractions.
 // One CTA per SM walks the output tiles (m fastest: concurrent CTAs share a 256-row band of W); three pipelines:
-//   warp 4  TMA producer : 4-stage ring of {A 128 x 64, W 256 x 64} SWIZZLE_128B boxes (48 KB per stage), runs ahead across
+//   warp 8  TMA producer : 4-stage ring of {A 128 x 64, W 256 x 64} SWIZZLE_128B boxes (48 KB per stage), runs ahead across
 //                          tile boundaries
-//   warp 5  MMA issuer   : tcgen05.mma M128 x N256 x K16 into one of TWO 256-column TMEM accumulators (all 512 columns):
+//   warp 9  MMA issuer   : tcgen05.mma M128 x N256 x K16 into one of TWO 256-column TMEM accumulators (all 512 columns):
 //                          the next tile's main loop starts while the epilogue warps drain the previous accumulator
-//   warps 0-3 epilogue   : tcgen05.ld 32x32b (thread = row) -> padded shared-memory transpose (33-word rows) -> thread =
+//   warps 0-7 epilogue   : tcgen05.ld 32x32b (thread = row) -> padded shared-memory transpose (33-word rows) -> thread =
 //                          COLUMN: bias / activation / position rows / residual / SwiGLU are read and written as whole
-//                          128-byte row segments (the one-tile kernel above stores 8 bytes per thread at row stride: 32
-//                          sectors per instruction; that epilogue, not the tensor pipe, bounded it at ~300 TF/s in the ViT)
+//                          128-byte row segments, eight rows per step as independent dependency chains. (The one-tile
+//                          kernel above stores 8 bytes per thread at row stride — 32 sectors per instruction; a first
+//                          persistent version with four epilogue warps and one row per step was latency-bound in the
+//                          epilogue: ~100 k cycles per tile, 176 TF/s on the ViT qkv shape.)
+// L2 feeds an SM at ~43 B/clk (6300 B/clk chip-wide): a 128 x 256 x 64 step moves 48 KB for 512 tensor-pipe cycles, so this
+// 1-CTA tile tops out near 45 % of the tensor peak; the pair tile (cta_group::2, 256 x 256, W halves shared) is the next step.
 constexpr int PBN = 256, PSTAGES = 4;
 constexpr int PB_BYTES = PBN * TBK * 2;                    // 32 KB
 constexpr int PSTAGE_BYTES = A_BYTES + PB_BYTES;           // 48 KB
+constexpr int PEPI_WARPS = 8;                              // two per TMEM lane quarter: columns [0,128) and [128,256)
+constexpr int PTHREADS = (PEPI_WARPS + 2) * 32;
 constexpr int PSTG_WORDS = 32 * 33;                        // per epilogue warp: 32 rows x 32 columns, padded
-constexpr int PSMEM = PSTAGES * PSTAGE_BYTES + 4 * PSTG_WORDS * 4 + 256 + 1024;
+constexpr int PSMEM = PSTAGES * PSTAGE_BYTES + PEPI_WARPS * PSTG_WORDS * 4 + 256 + 1024;
+static_assert(PSMEM <= 232448, "persistent GEMM shared memory");
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                        const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+// 0.5 x (1 + tanh(u)) = x * sigmoid(2u): two MUFU ops instead of the libm tanhf (error ~1e-7 relative, far below bf16 output rounding)
+DTK_DEV float gelu_tanh_fast(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.f + __expf(-2.f * u));
+}
+
+__global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                      const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sraw = smem_u32(smem_raw);
   const uint32_t sbase = (sraw + 1023u) & ~1023u;
   const uint32_t stg0 = sbase + PSTAGES * PSTAGE_BYTES;
-  const uint32_t bars = stg0 + 4 * PSTG_WORDS * 4;
+  const uint32_t bars = stg0 + PEPI_WARPS * PSTG_WORDS * 4;
   const uint32_t full0 = bars, empty0 = bars + 8 * PSTAGES, afull0 = bars + 16 * PSTAGES, aempty0 = afull0 + 16, tptr = aempty0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KT = (p.K + TBK - 1) / TBK;
@@ -226,10 +239,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { tc_mbar_init(afull0 + 8 * a, 1); tc_mbar_init(aempty0 + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { tc_mbar_init(afull0 + 8 * a, 1); tc_mbar_init(aempty0 + 8 * a, PEPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == PEPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tptr), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tptr));
 
-  if (warp == 4) {
+  if (warp == PEPI_WARPS) {
     if (lane == 0) {
       uint32_t it = 0;   // k-blocks issued so far (ring position across tiles)
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == PEPI_WARPS + 1) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
     if (lane == 0) {
       uint32_t it = 0, nt = 0;   // k-blocks / tiles consumed so far
@@ -276,19 +289,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
       }
     }
   } else {
+    // ===== epilogue: warp w drains TMEM lanes 32 (w % 4) .. + 31 (hardware lane-quarter rule), columns 128 (w / 4) .. + 127
     float* stg = reinterpret_cast<float*>(smem_raw + (stg0 - sraw)) + warp * PSTG_WORDS;
+    const int quarter = warp & 3, chalf = warp >> 2;
     uint32_t nt = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
       const uint32_t acc = nt & 1, ause = nt >> 1;
       const int m0 = (tile % MT) * TBM, n0 = (tile / MT) * PBN;
       tc_wait(afull0 + 8 * acc, ause & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t trow = tmem + acc * PBN + ((uint32_t)(warp * 32) << 16);
-      const int mrow0 = m0 + warp * 32;
+      const uint32_t trow = tmem + acc * PBN + ((uint32_t)(quarter * 32) << 16);
+      const int mrow0 = m0 + quarter * 32;
       const int nrows = min(32, p.M - mrow0);   // rows of this warp inside the matrix (may be <= 0)
+      const int cb0 = chalf * 128;
+      const int cb1 = min(cb0 + 128, (p.N - n0 + 31) & ~31);   // end of this warp's columns inside the matrix
+      if (cb0 >= cb1) {   // nothing to drain: hand the accumulator back at once
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(aempty0 + 8 * acc) : "memory");
+        continue;
+      }
 #pragma unroll 1
-      for (int cb = 0; cb < PBN; cb += 32) {
-        if (n0 + cb >= p.N) break;
+      for (int cb = cb0; cb < cb1; cb += 32) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
@@ -298,8 +319,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(trow + (uint32_t)cb));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (cb + 32 >= PBN || n0 + cb + 32 >= p.N) {
-          // last chunk of this tile is in registers: hand the accumulator back before the stores
+        if (cb + 32 >= cb1) {
+          // this warp's last chunk of the tile is in registers: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(aempty0 + 8 * acc) : "memory");
@@ -307,37 +328,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // thread = row: bank (lane + j) % 32
         __syncwarp();
-        // thread = column n: whole 128-byte row segments from here on
+        // thread = column n: whole 128-byte row segments from here on; eight rows per step as independent chains
         const int n = n0 + cb + lane;
         const bool nin = n < p.N;
         float bias = 0.f;
         if (p.bias && nin) bias = __bfloat162float(p.bias[n]);
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          if (rr >= nrows) break;
-          const int m = mrow0 + rr;
-          float v = stg[rr * 33 + lane] + bias;
-          if (p.act == ACT_GELU_TANH) v = gelu_tanh(v);
-          else if (p.act == ACT_GELU_ERF) v = gelu_erf(v);
+#pragma unroll 1
+        for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = stg[(rr0 + u) * 33 + lane] + bias;
+          if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = gelu_tanh_fast(v[u]);
+          } else if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = gelu_erf(v[u]);
+          }
           if (p.glu) {   // columns (gate, up) are adjacent lanes; out[m, n / 2]
-            const float up = __shfl_down_sync(0xffffffffu, v, 1);
-            if (!(lane & 1) && nin) {
-              const float rv = silu(v) * up;
-              const int64_t o = (int64_t)m * p.ldo + (n >> 1);
-              if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rv);
-              else p.out_f32[o] = rv;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float up = __shfl_down_sync(0xffffffffu, v[u], 1);
+              if (!(lane & 1) && nin && rr0 + u < nrows) {
+                const float rv = silu(v[u]) * up;
+                const int64_t o = (int64_t)(mrow0 + rr0 + u) * p.ldo + (n >> 1);
+                if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rv);
+                else p.out_f32[o] = rv;
+              }
             }
             continue;
           }
-          if (nin) {
-            if (p.rowbias) v += __bfloat162float(p.rowbias[(int64_t)(m % p.rowbias_mod) * p.N + n]);
-            if (p.resid) v += p.resid[(int64_t)m * p.ldr + n];
+          if (p.rowbias) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              t[u] = (nin && rr0 + u < nrows) ? __bfloat162float(p.rowbias[(int64_t)((mrow0 + rr0 + u) % p.rowbias_mod) * p.N + n]) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] += t[u];
+          }
+          if (p.resid) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (nin && rr0 + u < nrows) ? p.resid[(int64_t)(mrow0 + rr0 + u) * p.ldr + n] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] += t[u];
           }
           if (p.out_bf16) {
-            const float hi = __shfl_down_sync(0xffffffffu, v, 1);
-            if (!(lane & 1) && nin) *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)m * p.ldo + n) = pack_bf16x2(v, hi);   // N is even
-          } else if (nin) {
-            p.out_f32[(int64_t)m * p.ldo + n] = v;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float hi = __shfl_down_sync(0xffffffffu, v[u], 1);
+              if (!(lane & 1) && nin && rr0 + u < nrows)
+                *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)(mrow0 + rr0 + u) * p.ldo + n) = pack_bf16x2(v[u], hi);   // N is even
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (nin && rr0 + u < nrows) p.out_f32[(int64_t)(mrow0 + rr0 + u) * p.ldo + n] = v[u];
           }
         }
         __syncwarp();   // the staging tile is rewritten by the next chunk
@@ -346,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_persist_kernel(const __
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == PEPI_WARPS + 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
   }
@@ -477,6 +523,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __gri
     if (p.bias && n < p.N) bias = __bfloat162float(p.bias[n]);
 #pragma unroll 1
     for (int cb = 0; cb < NB; cb += 32) {
+      // residual rows of this chunk: all loads in flight before the accumulator is read (one row at a time inside the
+      // store loop below cost 32 dependent L2 round trips, ~10 us of a 30 us o-proj)
+      float rs[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rs[j] = (p.resid && !p.glu && n < p.N && cb + j < p.M) ? p.resid[(int64_t)(cb + j) * p.ldr + n] : 0.f;
       uint32_t r[32];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
@@ -517,7 +568,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __gri
           continue;
         }
         if (n < p.N) {
-          if (p.resid) v += p.resid[(int64_t)b * p.ldr + n];
+          v += rs[j];
           const int64_t o = (int64_t)b * p.ldo + n;
           if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(v);
           else p.out_f32[o] = v;
@@ -655,7 +706,7 @@ static cudaError_t launch_tc_persist(const GemmArgs& a, cudaStream_t s, uint64_t
     attr_done[dev] = true;
   }
   const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + PBN - 1) / PBN);
-  gemm_tc_persist_kernel<<<tiles < sms[dev] ? tiles : sms[dev], TC_THREADS, PSMEM, s>>>(mapA, mapB, a);
+  gemm_tc_persist_kernel<<<tiles < sms[dev] ? tiles : sms[dev], PTHREADS, PSMEM, s>>>(mapA, mapB, a);
   if (counter) ++*counter;
   return cudaGetLastError();
 }
