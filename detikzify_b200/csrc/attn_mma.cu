@@ -35,7 +35,7 @@ DTK_DEV void load_rows(uint32_t sdst, const bf16* base, int64_t row_stride, int 
   }
 }
 
-template <int D, int DP, bool CAUSAL>
+template <int D, int DP, bool CAUSAL, bool PARTIAL>
 __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) {
   using S = AttnSmem<D, DP>;
   constexpr int DPS = S::DPS;
@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK0 = sQ + S::TILE, sV0 = sK0 + 2 * S::TILE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  // PARTIAL: one query tile (Tq <= 64 rows = the rollouts of a batched decode step), blockIdx.x = key-tile range
+  const int qt = PARTIAL ? 0 : blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int kvh = head / p.kv_group;
   const bf16* qb = p.q + (int64_t)b * p.q_bs + (int64_t)head * p.q_hs;
   const bf16* kb = p.k + (int64_t)b * p.k_bs + (int64_t)kvh * p.k_hs;
@@ -66,11 +67,12 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
     int last = p.q_pos0 + min(q0 + BQ, p.Tq);  // one past the last visible key for this query tile
     tk = min(tk, last);
   }
-  const int ntiles = (tk + BKV - 1) / BKV;
+  const int jt0 = PARTIAL ? (int)blockIdx.x * p.part_tiles : 0;
+  const int ntiles = PARTIAL ? min((tk + BKV - 1) / BKV, jt0 + p.part_tiles) : (tk + BKV - 1) / BKV;
 
   load_rows<D, DP>(sQ, qb, p.q_rs, q0, p.Tq, tid);
-  load_rows<D, DP>(sK0, kb, p.k_rs, 0, tk, tid, kb2, p.split_row);
-  load_rows<D, DP>(sV0, vb, p.v_rs, 0, tk, tid, vb2, p.split_row);
+  load_rows<D, DP>(sK0 + (jt0 & 1) * S::TILE, kb, p.k_rs, jt0 * BKV, tk, tid, kb2, p.split_row);
+  load_rows<D, DP>(sV0 + (jt0 & 1) * S::TILE, vb, p.v_rs, jt0 * BKV, tk, tid, vb2, p.split_row);
   cp_async_commit();
 
   float o[D / 8][4];
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   const float sl2 = p.scale * 1.4426950408889634f;
   const int g = lane >> 2, tq4 = lane & 3;
 
-  for (int j = 0; j < ntiles; ++j) {
+  for (int j = jt0; j < ntiles; ++j) {
     const int st = j & 1;
     if (j + 1 < ntiles) {
       load_rows<D, DP>(sK0 + (st ^ 1) * S::TILE, kb, p.k_rs, (j + 1) * BKV, tk, tid, kb2, p.split_row);
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (j == 0) {
+    if (j == jt0) {
 #pragma unroll
       for (int kk = 0; kk < DP / 16; ++kk) {
         int row = warp * 16 + (lane & 15);
@@ -196,6 +198,23 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
     l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
     l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
   }
+  if (PARTIAL) {
+    // flash state of this key range, in the convention of decode_attn_kernel's partials (merged there)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int qrow = warp * 16 + g + h * 8;
+      if (qrow >= p.Tq) continue;
+      const int64_t pi = ((int64_t)qrow * p.heads + head) * p.part_np + p.part_idx0 + blockIdx.x;
+      if (tq4 == 0) {
+        p.part_ml[pi * 2] = m_run[h] == -INFINITY ? -INFINITY : m_run[h] * sl2;
+        p.part_ml[pi * 2 + 1] = l_run[h];
+      }
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i)
+        *reinterpret_cast<float2*>(p.part_o + pi * 128 + i * 8 + tq4 * 2) = make_float2(o[i][h * 2], o[i][h * 2 + 1]);
+    }
+    return;
+  }
   bf16* ob = p.o + (int64_t)b * p.o_bs + (int64_t)head * p.o_hs;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(ATHREADS) flash_attn_kernel(const AttnArgs p) 
   }
 }
 
-template <int D, int DP, bool CAUSAL>
+template <int D, int DP, bool CAUSAL, bool PARTIAL>
 cudaError_t launch_t(const AttnArgs& a, cudaStream_t s) {
   const int smem = AttnSmem<D, DP>::BYTES;
   // the attribute is per device; set once per device (not per launch: launches may be captured into a CUDA graph)
@@ -220,12 +239,12 @@ cudaError_t launch_t(const AttnArgs& a, cudaStream_t s) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    e = cudaFuncSetAttribute(flash_attn_kernel<D, DP, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(flash_attn_kernel<D, DP, CAUSAL, PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  dim3 grid((a.Tq + BQ - 1) / BQ, a.heads, a.B);
-  flash_attn_kernel<D, DP, CAUSAL><<<grid, ATHREADS, smem, s>>>(a);
+  dim3 grid(PARTIAL ? (((a.Tk + BKV - 1) / BKV + a.part_tiles - 1) / a.part_tiles) : (a.Tq + BQ - 1) / BQ, a.heads, a.B);
+  flash_attn_kernel<D, DP, CAUSAL, PARTIAL><<<grid, ATHREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -233,9 +252,14 @@ cudaError_t launch_t(const AttnArgs& a, cudaStream_t s) {
 
 cudaError_t launch_flash_attn(const AttnArgs& a, cudaStream_t s, uint64_t* counter) {
   if (a.Tq <= 0 || a.B <= 0) return cudaSuccess;
+  if (a.part_o) {   // shared-prefix partials of a batched decode step
+    if (a.head_dim != 128 || a.causal || a.Tq > BQ || a.B != 1 || a.part_tiles <= 0 || a.Tk <= 0 || !a.part_ml) return cudaErrorInvalidValue;
+    if (counter) ++*counter;
+    return launch_t<128, 128, false, true>(a, s);
+  }
   if (counter) ++*counter;
-  if (a.head_dim == 72) return a.causal ? launch_t<72, 80, true>(a, s) : launch_t<72, 80, false>(a, s);
-  if (a.head_dim == 128) return a.causal ? launch_t<128, 128, true>(a, s) : launch_t<128, 128, false>(a, s);
+  if (a.head_dim == 72) return a.causal ? launch_t<72, 80, true, false>(a, s) : launch_t<72, 80, false, false>(a, s);
+  if (a.head_dim == 128) return a.causal ? launch_t<128, 128, true, false>(a, s) : launch_t<128, 128, false, false>(a, s);
   return cudaErrorInvalidValue;
 }
 

@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
   const int T = p.pos[b] + 1, slot = p.slots[b];
   const int kvh = head / p.kv_group;
-  int chunk = (T + p.nsplit - 1) / p.nsplit;
+  int chunk = (T - p.key_begin + p.nsplit - 1) / p.nsplit;   // key_begin > 0: the shared prefix was reduced by the prefix kernel
   chunk = (chunk + 7) & ~7;
-  const int j0 = split * chunk, j1 = min(T, j0 + chunk);
+  const int j0 = p.key_begin + split * chunk, j1 = min(T, j0 + chunk);
   const bf16* kb = p.kv_base + (int64_t)slot * p.kv_slot_stride + (int64_t)kvh * p.max_len * 128;
   const bf16* vb = kb + p.kv_v_offset;
   // shared prefix: positions below shlen live in another slot (one copy for all rollouts of a figure)
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
       L += sm_l[h] * w;
       O += sm_o[h][d] * w;
     }
-    const int64_t pi = ((int64_t)(b * p.heads + head) * p.nsplit + split);
+    const int64_t pi = ((int64_t)(b * p.heads + head) * p.np + split);
     p.part_o[pi * 128 + d] = O;
     if (d == 0) { p.part_ml[pi * 2] = M; p.part_ml[pi * 2 + 1] = L; }
   }
@@ -245,17 +245,19 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   if (sm_last) {
     __threadfence();
     const int d = tid;
-    const int64_t base = (int64_t)(b * p.heads + head) * p.nsplit;
+    const int64_t base = (int64_t)(b * p.heads + head) * p.np;
     float M = -INFINITY;
-    for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p.part_ml + (base + s) * 2));
+    for (int s = 0; s < p.np; ++s) M = fmaxf(M, __ldcg(p.part_ml + (base + s) * 2));
     float L = 0.f, O = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) {
+    for (int s = 0; s < p.np; ++s) {
       float ms = __ldcg(p.part_ml + (base + s) * 2);
       float w = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
       L += __ldcg(p.part_ml + (base + s) * 2 + 1) * w;
       O += __ldcg(p.part_o + (base + s) * 128 + d) * w;
     }
-    p.out[(int64_t)b * p.out_stride + head * 128 + d] = O / L;
+    const float res = O / L;
+    p.out[(int64_t)b * p.out_stride + head * 128 + d] = res;
+    if (p.out_bf16) p.out_bf16[(int64_t)b * p.out_stride + head * 128 + d] = __float2bfloat16_rn(res);
     if (tid == 0) p.counters[b * p.heads + head] = 0u;
   }
 }
@@ -296,7 +298,9 @@ cudaError_t launch_embed_tokens(const int* tok32, const int64_t* tok64, int B, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t s, uint64_t* counter) {
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a0, cudaStream_t s, uint64_t* counter) {
+  DecodeAttnArgs a = a0;
+  if (a.np < a.nsplit) a.np = a.nsplit;   // plain mode: np left at 0
   dim3 grid(a.heads, a.nsplit, a.B);
   decode_attn_kernel<<<grid, DA_THREADS, 0, s>>>(a);
   if (counter) ++*counter;

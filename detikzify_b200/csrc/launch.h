@@ -59,6 +59,13 @@ struct AttnArgs {
   // split_row are read from k2 / v2 (same strides), the rest from k / v. split_row = 0: everything from k / v.
   const bf16 *k2, *v2;
   int split_row;
+  // partial mode (shared-prefix attention of a batched decode step; part_o != null): the Tq <= 64 query rows are the
+  // rollouts of one figure, blockIdx.x selects a range of part_tiles key tiles, and instead of the normalised output the
+  // kernel exports the flash state of that range in the convention of decode_attn_kernel's partials:
+  //   part_ml[(row * heads + head) * part_np + part_idx0 + blockIdx.x] = { max score * scale * log2(e), sum exp2 },
+  //   part_o[... * 128 + d] = unnormalised output.
+  float *part_o, *part_ml;
+  int part_np, part_idx0, part_tiles;
 };
 cudaError_t launch_flash_attn(const AttnArgs& a, cudaStream_t s, uint64_t* counter);
 
@@ -86,7 +93,7 @@ cudaError_t launch_embed_splice(const int64_t* ids, int T, int start_pos, const 
 // prefill: qkv fp32 [T, qd+2kd] -> roped q bf16 [T, qd]; K/V bf16 into the cache at positions start_pos+t
 cudaError_t launch_rope_kv_decode(const float* qkv, int B, const int* slots, const int* pos, int heads, int kv_heads,
                                   const float* rope_cs, float* q_out, bf16* kv_base, int64_t kv_slot_stride,
-                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter);
+                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter, bf16* q_bf16 = nullptr);
 cudaError_t launch_rope_kv_prefill(const float* qkv, int T, int start_pos, int heads, int kv_heads,
                                    const float* rope_cs, bf16* q_out, bf16* kcache, bf16* vcache,
                                    int max_len, cudaStream_t s, uint64_t* counter);
@@ -130,11 +137,15 @@ struct DecodeAttnArgs {
   const int* share_len;       // device int[B]: 0 = nothing shared
   int B, heads, kv_group, max_len, nsplit;
   float scale;
-  float* part_o;              // [B, heads, nsplit, 128]
-  float* part_ml;             // [B, heads, nsplit, 2]
+  float* part_o;              // [B, heads, np, 128]
+  float* part_ml;             // [B, heads, np, 2]
   unsigned int* counters;     // [B * heads], zero-initialised, self-resetting
   float* out;                 // [B, q_dim] fp32
   int64_t out_stride;
+  // shared-prefix ("cascade") mode: keys [0, key_begin) were already reduced by launch_flash_attn in partial mode into the
+  // partial slots [nsplit, np); this kernel covers [key_begin, pos] and its merge adds all np partials. 0 / nsplit = off.
+  int key_begin, np;
+  bf16* out_bf16;             // optional bf16 copy of the output (the o-proj GEMM operand), same layout
 };
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t s, uint64_t* counter);
 

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(64) rope_kv_decode_kernel(const float* __restr
                                                             const int* __restrict__ posv, int heads, int kv_heads,
                                                             const float* __restrict__ rope_cs, float* __restrict__ q_out,
                                                             bf16* __restrict__ kv_base, int64_t kv_slot_stride,
-                                                            int64_t kv_v_offset, int max_len) {
+                                                            int64_t kv_v_offset, int max_len, bf16* __restrict__ q_bf16) {
   const int b = blockIdx.x, hh = blockIdx.y, i = threadIdx.x;
   const int qd = heads * 128, kd = kv_heads * 128;
   const int pos = posv[b];
@@ -232,8 +232,14 @@ __global__ void __launch_bounds__(64) rope_kv_decode_kernel(const float* __restr
   const float2 cs = *reinterpret_cast<const float2*>(rope_cs + ((int64_t)pos * 64 + i) * 2);
   if (hh < heads) {
     float* d = q_out + (int64_t)b * qd + hh * 128;
-    d[i] = a * cs.x - c * cs.y;
-    d[i + 64] = c * cs.x + a * cs.y;
+    const float y0 = a * cs.x - c * cs.y, y1 = c * cs.x + a * cs.y;
+    d[i] = y0;
+    d[i + 64] = y1;
+    if (q_bf16) {   // operand of the shared-prefix attention (tensor cores)
+      bf16* d16 = q_bf16 + (int64_t)b * qd + hh * 128;
+      d16[i] = __float2bfloat16_rn(y0);
+      d16[i + 64] = __float2bfloat16_rn(y1);
+    }
   } else if (hh < heads + kv_heads) {
     bf16* d = kv_base + (int64_t)slots[b] * kv_slot_stride + ((int64_t)(hh - heads) * max_len + pos) * 128;
     d[i] = __float2bfloat16_rn(a * cs.x - c * cs.y);
@@ -343,10 +349,10 @@ cudaError_t launch_rope_kv_prefill(const float* qkv, int T, int start_pos, int h
 }
 cudaError_t launch_rope_kv_decode(const float* qkv, int B, const int* slots, const int* pos, int heads, int kv_heads,
                                   const float* rope_cs, float* q_out, bf16* kv_base, int64_t kv_slot_stride,
-                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter) {
+                                  int64_t kv_v_offset, int max_len, cudaStream_t s, uint64_t* counter, bf16* q_bf16) {
   dim3 grid(B, heads + 2 * kv_heads);
   rope_kv_decode_kernel<<<grid, 64, 0, s>>>(qkv, slots, pos, heads, kv_heads, rope_cs, q_out, kv_base, kv_slot_stride,
-                                            kv_v_offset, max_len);
+                                            kv_v_offset, max_len, q_bf16);
   if (counter) ++*counter;
   return cudaGetLastError();
 }

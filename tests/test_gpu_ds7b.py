@@ -120,3 +120,40 @@ def test_ds7b_batched_gemm_decode_b32_and_nucleus(setup):
     finally:
         for s in slots:
             eng.seq_free(s)
+
+
+def test_ds7b_shared_prefix_cascade_attention(setup):
+    """32 rollouts that share one 7b-shaped prefix (image span + prompt): the shared-prefix tensor-core pass + per-row suffix
+    merge gives the logits of the per-row attention kernel (cascade_attn = 0), and the oracle's for the checked rows."""
+    cfg, oracle, eng, pix, img, prompts, tok1, tok2 = setup
+    g = torch.Generator().manual_seed(7100)
+    prefix = prompts[B - 1]
+    cut = prefix.numel()
+    base = eng.seq_alloc()
+    subs = [eng.seq_alloc() for _ in range(B)]         # fixture: max_seqs = B + 2
+    R = len(subs)
+    try:
+        eng.prefill(base, prefix.cuda(), 0, img, 0)
+        sufs = [torch.randint(0, 30000, (1 + (i % 5),), generator=g) for i in range(R)]
+        lens = []
+        for s_, suf in zip(subs, sufs):
+            eng.seq_share(base, s_, cut)
+            eng.prefill(s_, suf.cuda(), cut, None, 0)
+            lens.append(cut + suf.numel())
+        toks = tok1[:R]
+        out = {}
+        for cas in (1, 0):
+            eng.set_option("cascade_attn", cas)
+            out[cas] = eng.decode(subs, lens, toks.cuda()).clone()
+        torch.cuda.synchronize()
+        ref0, _ = oracle.forward_logits(torch.cat([prefix, sufs[0], toks[:1]])[None], pix)
+        TOL = _tol(ref0)
+        assert (out[1] - out[0]).abs().max().item() < TOL
+        assert (out[1][0].cpu() - ref0[0, -1]).abs().max().item() < TOL
+        refl, _ = oracle.forward_logits(torch.cat([prefix, sufs[R - 1], toks[R - 1:R]])[None], pix)
+        assert (out[1][R - 1].cpu() - refl[0, -1]).abs().max().item() < TOL
+    finally:
+        eng.set_option("cascade_attn", 1)
+        for s_ in subs:
+            eng.seq_free(s_)
+        eng.seq_free(base)

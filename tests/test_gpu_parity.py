@@ -188,6 +188,68 @@ def test_shared_prefix_rollouts_against_oracle():
         eng.seq_free(base)
 
 
+def test_shared_prefix_cascade_attention_matches_plain_and_oracle():
+    """Batched decode of rollouts that share one long prefix: the shared keys are reduced once per head by the tensor-core
+    prefix kernel (the rollouts are its query rows) and merged with each row's private suffix. Same logits as the per-row
+    path (option cascade_attn = 0) up to the bf16 rounding of q, and both match the oracle."""
+    name = "tiny2"
+    cfg, sd, oracle = model_bundle(name)
+    R = 6
+    eng = engine_for(name, max_seqs=R + 2, max_batch=R)
+    pix = _pixels(cfg, 1)
+    img = eng.image_embeds(pix.cuda())[0]
+    P = cfg.num_patches
+    g = torch.Generator().manual_seed(4200)
+    hi = min(cfg.vocab_size, cfg.patch_token_id)
+    prefix = torch.cat([torch.full((P,), cfg.patch_token_id), torch.randint(0, hi, (107 - P,), generator=g)]).long()
+    cut = prefix.numel()                      # 107: 96 positions shared (cascade needs >= 64), 11 copied
+    suffixes = [torch.randint(0, hi, (2 + 4 * i,), generator=g) for i in range(R)]
+    toks = torch.randint(0, hi, (R,), generator=g)
+    base = eng.seq_alloc()
+    subs = [eng.seq_alloc() for _ in range(R)]
+    try:
+        eng.prefill(base, prefix.cuda(), 0, img, 0)
+        refs, lens = [], []
+        for i, (s, suf) in enumerate(zip(subs, suffixes)):
+            eng.seq_share(base, s, cut)
+            eng.prefill(s, suf.cuda(), cut, None, 0)
+            full = torch.cat([prefix, suf])
+            ref, _ = oracle.forward_logits(torch.cat([full, toks[i:i + 1]])[None], pix)
+            refs.append(ref[0, -1]); lens.append(full.numel())
+        out = {}
+        for cas in (1, 0):
+            eng.set_option("cascade_attn", cas)
+            out[cas] = eng.decode(subs, lens, toks.cuda()).clone()
+        torch.cuda.synchronize()
+        assert (out[1] - out[0]).abs().max().item() < 2e-2
+        for i in range(R):
+            assert (out[1][i].cpu() - refs[i]).abs().max().item() < TOL, i
+        # the generation loop (CUDA graph keyed by the shared slot and length) agrees with stepwise decode + argmax
+        eng.set_option("cascade_attn", 1)
+        first = [int(out[1][i].argmax()) for i in range(R)]
+        params = eng.sampling(do_sample=False, bad_token=cfg.image_token_id)
+        eng.gen_begin(subs, [n + 1 for n in lens], first, params)
+        got = []
+        for step in range(3):
+            eng.gen_step()
+            got.append(eng.gen_wait(step))
+        eng.gen_end()
+        # stepwise: feed the same tokens through dtk_decode
+        cur, pos = first, [n + 1 for n in lens]
+        # rewind is implicit: decode rewrites the same KV rows
+        for step in range(3):
+            lg = eng.decode(subs, pos, torch.tensor(cur).cuda())
+            lg[:, cfg.image_token_id] = -float("inf")
+            cur = [int(x) for x in lg.argmax(-1)]
+            assert cur == [int(x) for x in got[step]], step
+            pos = [n + 1 for n in pos]
+    finally:
+        eng.set_option("cascade_attn", 1)
+        for s in subs:
+            eng.seq_free(s)
+        eng.seq_free(base)
+
+
 def test_device_image_preprocessing_is_pillow_exact():
     """dtk_image_preprocess: the resized uint8 image equals Pillow's bicubic resize bit for bit and the normalised fp32 pixels
     equal the host image processor's (reference v1/processing_detikzify.py:242-251), for ragged input sizes."""
