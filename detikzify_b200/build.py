@@ -62,11 +62,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(lambda j: _compile(j[0], j[1], verbose), jobs))
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+        tmp = LIB.with_suffix(".so.tmp")   # link beside the target and rename: a concurrent reader never sees a half-written library
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(tmp), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -428,8 +428,9 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     return DTK_OK;
   }
   DTK_CK(launch_embed_tokens(tok64 ? nullptr : eng->d_tok, tok64, B, W(eng, "dec.embed"), H, c.vocab, eng->d_x, s, lc));
-  const int nsplit = nsplit_for(c, B);
-  if (eng->decode_gemm_min_batch > 0 && B >= eng->decode_gemm_min_batch && B <= c.max_len) {   // (B rows fit the prefill buffers)
+  int nsplit = nsplit_for(c, B);
+  if (eng->decode_gemm_min_batch > 0 && B >= eng->decode_gemm_min_batch && B <= c.max_len) {
+    if (eng->cas_len > 0 && eng->cas_slot >= 0 && nsplit > 4) nsplit = 4;   // cascade: the per-row kernel covers the (short) private suffix only; 12+ partial slots stay for the prefix   // (B rows fit the prefill buffers)
     // ---- batched decode (MCTS rollouts / several figures): the B rows go through the dense matrices as ONE GEMM each, so
     // the weights are streamed once per step instead of once per sequence (the GEMV kernels below re-read them B times:
     // measured 59 ms/step for 32 ds-7b rollouts). Activations are rounded to bf16 GEMM operands exactly as in prefill
@@ -1203,7 +1204,7 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     return DTK_OK;
   }
   if (std::strcmp(key, "gemm_impl") == 0) {  // process-wide dev switch: 0 = mma.sync, 1 = tcgen05 where supported
-    DTK_REQUIRE(value >= 0 && value <= 2, "gemm_impl must be 0, 1 or 2");
+    DTK_REQUIRE(value >= 0 && value <= 3, "gemm_impl must be 0..3");
     set_gemm_impl((int)value);
     return DTK_OK;
   }

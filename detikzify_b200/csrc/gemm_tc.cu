@@ -195,6 +195,24 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) gemm_tc_kernel(const __g
   }
 }
 
+// ---- thread-block cluster helpers (split-K reduce of the batched-decode tile, CTA-pair GEMM)
+DTK_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+DTK_DEV void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+DTK_DEV uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {   // same offset in the shared memory of CTA `rank`
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+DTK_DEV float4 ld_dsmem_v4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
+  return v;
+}
+
+
 // ---- persistent 128 x 256 kernel (gemm_impl = 2): the dense ViT / prefill contractions.
 // One CTA per SM walks the output tiles (m fastest: concurrent CTAs share a 256-row band of W); three pipelines:
 //   warp 8  TMA producer : 4-stage ring of {A 128 x 64, W 256 x 64} SWIZZLE_128B boxes (48 KB per stage), runs ahead across
@@ -222,6 +240,105 @@ static_assert(PSMEM <= 232448, "persistent GEMM shared memory");
 DTK_DEV float gelu_tanh_fast(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
   return __fdividef(x, 1.f + __expf(-2.f * u));
+}
+
+// Epilogue of one 128-row accumulator (shared by the 1-CTA and the CTA-pair persistent kernels): warp w drains TMEM lanes
+// 32 (w % 4) .. + 31 (hardware lane-quarter rule), columns 128 (w / 4) .. + 127 of the 256-column accumulator at `tacc`.
+// `arrive` hands the accumulator back to the MMA issuer (called by lane 0 once this warp's last chunk is in registers).
+template <typename Arrive>
+DTK_DEV void persist_epilogue(const GemmArgs& p, float* stg, uint32_t tacc, int m0, int n0, int warp, int lane, Arrive arrive) {
+  const int quarter = warp & 3, chalf = warp >> 2;
+  const uint32_t trow = tacc + ((uint32_t)(quarter * 32) << 16);
+  const int mrow0 = m0 + quarter * 32;
+  const int nrows = min(32, p.M - mrow0);   // rows of this warp inside the matrix (may be <= 0)
+  const int cb0 = chalf * 128;
+  const int cb1 = min(cb0 + 128, (p.N - n0 + 31) & ~31);   // end of this warp's columns inside the matrix
+  if (cb0 >= cb1) {   // nothing to drain: hand the accumulator back at once
+    __syncwarp();
+    if (lane == 0) arrive();
+    return;
+  }
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 32) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(trow + (uint32_t)cb));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    if (cb + 32 >= cb1) {
+      // this warp's last chunk of the tile is in registers: hand the accumulator back before the stores
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) arrive();
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // thread = row: bank (lane + j) % 32
+    __syncwarp();
+    // thread = column n: whole 128-byte row segments from here on; eight rows per step as independent chains
+    const int n = n0 + cb + lane;
+    const bool nin = n < p.N;
+    float bias = 0.f;
+    if (p.bias && nin) bias = __bfloat162float(p.bias[n]);
+#pragma unroll 1
+    for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = stg[(rr0 + u) * 33 + lane] + bias;
+      if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = gelu_tanh_fast(v[u]);
+      } else if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = gelu_erf(v[u]);
+      }
+      if (p.glu) {   // columns (gate, up) are adjacent lanes; out[m, n / 2]
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float up = __shfl_down_sync(0xffffffffu, v[u], 1);
+          if (!(lane & 1) && nin && rr0 + u < nrows) {
+            const float rv = silu(v[u]) * up;
+            const int64_t o = (int64_t)(mrow0 + rr0 + u) * p.ldo + (n >> 1);
+            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rv);
+            else p.out_f32[o] = rv;
+          }
+        }
+        continue;
+      }
+      if (p.rowbias) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          t[u] = (nin && rr0 + u < nrows) ? __bfloat162float(p.rowbias[(int64_t)((mrow0 + rr0 + u) % p.rowbias_mod) * p.N + n]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] += t[u];
+      }
+      if (p.resid) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (nin && rr0 + u < nrows) ? p.resid[(int64_t)(mrow0 + rr0 + u) * p.ldr + n] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] += t[u];
+      }
+      if (p.out_bf16) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float hi = __shfl_down_sync(0xffffffffu, v[u], 1);
+          if (!(lane & 1) && nin && rr0 + u < nrows)
+            *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)(mrow0 + rr0 + u) * p.ldo + n) = pack_bf16x2(v[u], hi);   // N is even
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (nin && rr0 + u < nrows) p.out_f32[(int64_t)(mrow0 + rr0 + u) * p.ldo + n] = v[u];
+      }
+    }
+    __syncwarp();   // the staging tile is rewritten by the next chunk
+  }
+
 }
 
 __global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -289,105 +406,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_persist_kernel(const __gr
       }
     }
   } else {
-    // ===== epilogue: warp w drains TMEM lanes 32 (w % 4) .. + 31 (hardware lane-quarter rule), columns 128 (w / 4) .. + 127
+    // ===== epilogue warps 0..7
     float* stg = reinterpret_cast<float*>(smem_raw + (stg0 - sraw)) + warp * PSTG_WORDS;
-    const int quarter = warp & 3, chalf = warp >> 2;
     uint32_t nt = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
       const uint32_t acc = nt & 1, ause = nt >> 1;
       const int m0 = (tile % MT) * TBM, n0 = (tile / MT) * PBN;
       tc_wait(afull0 + 8 * acc, ause & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t trow = tmem + acc * PBN + ((uint32_t)(quarter * 32) << 16);
-      const int mrow0 = m0 + quarter * 32;
-      const int nrows = min(32, p.M - mrow0);   // rows of this warp inside the matrix (may be <= 0)
-      const int cb0 = chalf * 128;
-      const int cb1 = min(cb0 + 128, (p.N - n0 + 31) & ~31);   // end of this warp's columns inside the matrix
-      if (cb0 >= cb1) {   // nothing to drain: hand the accumulator back at once
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(aempty0 + 8 * acc) : "memory");
-        continue;
-      }
-#pragma unroll 1
-      for (int cb = cb0; cb < cb1; cb += 32) {
-        uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(trow + (uint32_t)cb));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (cb + 32 >= cb1) {
-          // this warp's last chunk of the tile is in registers: hand the accumulator back before the stores
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(aempty0 + 8 * acc) : "memory");
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // thread = row: bank (lane + j) % 32
-        __syncwarp();
-        // thread = column n: whole 128-byte row segments from here on; eight rows per step as independent chains
-        const int n = n0 + cb + lane;
-        const bool nin = n < p.N;
-        float bias = 0.f;
-        if (p.bias && nin) bias = __bfloat162float(p.bias[n]);
-#pragma unroll 1
-        for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = stg[(rr0 + u) * 33 + lane] + bias;
-          if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = gelu_tanh_fast(v[u]);
-          } else if (p.act == ACT_GELU_ERF) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = gelu_erf(v[u]);
-          }
-          if (p.glu) {   // columns (gate, up) are adjacent lanes; out[m, n / 2]
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float up = __shfl_down_sync(0xffffffffu, v[u], 1);
-              if (!(lane & 1) && nin && rr0 + u < nrows) {
-                const float rv = silu(v[u]) * up;
-                const int64_t o = (int64_t)(mrow0 + rr0 + u) * p.ldo + (n >> 1);
-                if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(rv);
-                else p.out_f32[o] = rv;
-              }
-            }
-            continue;
-          }
-          if (p.rowbias) {
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              t[u] = (nin && rr0 + u < nrows) ? __bfloat162float(p.rowbias[(int64_t)((mrow0 + rr0 + u) % p.rowbias_mod) * p.N + n]) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += t[u];
-          }
-          if (p.resid) {
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = (nin && rr0 + u < nrows) ? p.resid[(int64_t)(mrow0 + rr0 + u) * p.ldr + n] : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += t[u];
-          }
-          if (p.out_bf16) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float hi = __shfl_down_sync(0xffffffffu, v[u], 1);
-              if (!(lane & 1) && nin && rr0 + u < nrows)
-                *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)(mrow0 + rr0 + u) * p.ldo + n) = pack_bf16x2(v[u], hi);   // N is even
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (nin && rr0 + u < nrows) p.out_f32[(int64_t)(mrow0 + rr0 + u) * p.ldo + n] = v[u];
-          }
-        }
-        __syncwarp();   // the staging tile is rewritten by the next chunk
-      }
+      const uint32_t bar = aempty0 + 8 * acc;
+      persist_epilogue(p, stg, tmem + acc * PBN, m0, n0, warp, lane,
+                       [bar]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory"); });
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -395,6 +424,127 @@ __global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_persist_kernel(const __gr
   if (warp == PEPI_WARPS + 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+  }
+}
+
+// ---- CTA-pair persistent kernel (gemm_impl = 3): tcgen05.mma.cta_group::2, one 256 x 256 output tile per pair of SMs.
+// Each CTA of the pair stages 128 rows of A and HALF of the W tile (128 rows) per k-block — 32 KB instead of the 48 KB the
+// 1-CTA kernel moves for half the flops — and holds its 128 output rows x 256 columns in its own TMEM. Protocol (DeepGEMM /
+// CUTLASS 2-SM layout): both CTAs' TMA loads complete on the LEADER's full barrier (count 2: leader's arrive.expect_tx of
+// both halves' bytes + the peer's remote arrive); the leader's single MMA thread issues for both SMs and commits with
+// multicast to the empty / accumulator-full barriers of BOTH CTAs; the epilogue warps of both CTAs arrive on the leader's
+// accumulator-empty barrier (count 16). Epilogue = persist_epilogue on each CTA's own rows.
+constexpr int QSTAGES = 6;
+constexpr int QSTAGE_BYTES = 2 * A_BYTES;                  // A 128 x 64 + W half 128 x 64 = 32 KB
+constexpr int QSMEM = QSTAGES * QSTAGE_BYTES + PEPI_WARPS * PSTG_WORDS * 4 + 256 + 1024;
+static_assert(QSMEM <= 232448, "pair GEMM shared memory");
+
+DTK_DEV void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+               : "memory");
+}
+DTK_DEV void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DTK_DEV void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+DTK_DEV void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  const uint32_t stg0 = sbase + QSTAGES * QSTAGE_BYTES;
+  const uint32_t bars = stg0 + PEPI_WARPS * PSTG_WORDS * 4;
+  const uint32_t full0 = bars, empty0 = bars + 8 * QSTAGES, afull0 = bars + 16 * QSTAGES, aempty0 = afull0 + 16, tptr = aempty0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int KT = (p.K + TBK - 1) / TBK;
+  const int MT2 = (p.M + 2 * TBM - 1) / (2 * TBM), NT = (p.N + PBN - 1) / PBN;
+  const int tiles = MT2 * NT;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < QSTAGES; ++s) { tc_mbar_init(full0 + 8 * s, 2); tc_mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { tc_mbar_init(afull0 + 8 * a, 1); tc_mbar_init(aempty0 + 8 * a, 2 * PEPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit / 2-SM allocation
+  if (warp == PEPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tptr), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tptr));
+
+  if (warp == PEPI_WARPS) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < tiles; tile += npairs) {
+        const int m0 = (tile % MT2) * (2 * TBM) + (int)rank * TBM, n0 = (tile / MT2) * PBN + (int)rank * (PBN / 2);
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const uint32_t s = it % QSTAGES, use = it / QSTAGES;
+          if (use > 0) tc_wait(empty0 + 8 * s, (use - 1) & 1);
+          const uint32_t sa = sbase + s * QSTAGE_BYTES, sb = sa + A_BYTES;
+          const uint32_t lbar = dsmem_addr(full0 + 8 * s, 0);   // the leader's full barrier
+          if (rank == 0) tc_expect_tx(full0 + 8 * s, 2 * QSTAGE_BYTES);   // both CTAs' bytes land here
+          else mbar_arrive_cluster(lbar);
+          tma_load_2d_pair(sa, &mapA, kt * TBK, m0, lbar);
+          tma_load_2d_pair(sb, &mapB, kt * TBK, n0, lbar);
+        }
+      }
+    }
+  } else if (warp == PEPI_WARPS + 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PBN >> 3) << 17) | ((uint32_t)((2 * TBM) >> 4) << 24);
+    if (lane == 0 && rank == 0) {
+      uint32_t it = 0, nt = 0;
+      for (int tile = pair; tile < tiles; tile += npairs, ++nt) {
+        const uint32_t acc = nt & 1, ause = nt >> 1;
+        if (ause > 0) tc_wait(aempty0 + 8 * acc, (ause - 1) & 1);   // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t tacc = tmem + acc * PBN;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const uint32_t s = it % QSTAGES, use = it / QSTAGES;
+          tc_wait(full0 + 8 * s, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t sa = sbase + s * QSTAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) umma_f16_pair(tacc, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (kt | k) != 0);
+          umma_commit_pair(empty0 + 8 * s);
+        }
+        umma_commit_pair(afull0 + 8 * acc);
+      }
+    }
+  } else {
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg0 - sraw)) + warp * PSTG_WORDS;
+    uint32_t nt = 0;
+    for (int tile = pair; tile < tiles; tile += npairs, ++nt) {
+      const uint32_t acc = nt & 1, ause = nt >> 1;
+      const int m0 = (tile % MT2) * (2 * TBM) + (int)rank * TBM, n0 = (tile / MT2) * PBN;
+      tc_wait(afull0 + 8 * acc, ause & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t lbar = dsmem_addr(aempty0 + 8 * acc, 0);
+      persist_epilogue(p, stg, tmem + acc * PBN, m0, n0, warp, lane, [lbar]() { mbar_arrive_cluster(lbar); });
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  cluster_sync_all();   // no CTA of the pair leaves while the other may still signal its barriers
+  if (warp == PEPI_WARPS + 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
   }
 }
 
@@ -411,22 +561,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) gemm_tc_persist_kernel(const __gr
 // streams a contiguous K range into its own TMEM accumulator, ranks > 0 park their fp32 partial tile in their shared memory
 // and rank 0 adds them IN RANK ORDER through distributed shared memory (deterministic) and runs the epilogue. No workspace in
 // HBM, no atomics. Two CTAs per SM (5-stage rings) keep ~200 KB of weights in flight per SM.
-DTK_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
-DTK_DEV void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-DTK_DEV uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {   // same offset in the shared memory of CTA `rank`
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local_addr), "r"(rank));
-  return ra;
-}
-DTK_DEV float4 ld_dsmem_v4(uint32_t cluster_addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
-  return v;
-}
-
 template <int NB, int TSTAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap mapW,
                                                                     const __grid_constant__ CUtensorMap mapX, const GemmArgs p,
@@ -711,6 +845,40 @@ static cudaError_t launch_tc_persist(const GemmArgs& a, cudaStream_t s, uint64_t
   return cudaGetLastError();
 }
 
+static cudaError_t launch_tc_pair(const GemmArgs& a, cudaStream_t s, uint64_t* counter) {
+  CUtensorMap mapA, mapB;
+  if (!make_map(&mapA, a.A, a.M, a.K, a.lda, TBM) || !make_map(&mapB, a.W, a.N, a.K, a.ldw, PBN / 2)) return cudaErrorInvalidValue;
+  static bool attr_done[64] = {};
+  static int sms[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_done[dev]) {
+    e = cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    if (e != cudaSuccess) return e;
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = 148;
+    attr_done[dev] = true;
+  }
+  const int tiles = ((a.M + 2 * TBM - 1) / (2 * TBM)) * ((a.N + PBN - 1) / PBN);
+  const int pairs = tiles < sms[dev] / 2 ? tiles : sms[dev] / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(PTHREADS);
+  cfg.dynamicSmemBytes = QSMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel, mapA, mapB, a);
+  if (counter) ++*counter;
+  return e;
+}
+
 static int g_skinny_swap = 1;   // dev switch (dtk_set_option "gemm_skinny_swap"): 1 = swapped-operand tile for M < 64
 void set_gemm_skinny_swap(int v) { g_skinny_swap = v; }
 
@@ -721,6 +889,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter)
   }
   if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
   if (get_gemm_impl() == 2) return launch_tc_persist(a, s, counter);   // persistent 128 x 256, overlapped epilogue
+  if (get_gemm_impl() == 3) return launch_tc_pair(a, s, counter);      // CTA pairs, 256 x 256, cta_group::2
   return launch_tc_variant<128, 3, 2>(a, s, counter);
 }
 

@@ -214,3 +214,17 @@ def test_decode_gemv_matches_torch(N, K, mode, norm):
     assert rc == 0
     torch.cuda.synchronize()
     torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+# Last in the file on purpose: a protocol error in the CTA-pair kernel traps (bounded waits) and poisons the CUDA context of
+# this process; nothing else may depend on it.
+@pytest.mark.parametrize("M,N,K,bias,act,resid,glu,obf", [c for c in GEMM_SHAPES if c[0] >= 64])
+def test_gemm_cta_pair_matches_torch(M, N, K, bias, act, resid, glu, obf):
+    """tcgen05.mma.cta_group::2: 256 x 256 tiles on pairs of SMs, W halves staged by each CTA of the pair, multicast commits
+    (gemm_impl 3), against torch fp32 on every dense shape of the path."""
+    prev = _lib().dtk_dbg_gemm_impl(-1)
+    _lib().dtk_dbg_gemm_impl(3)
+    try:
+        _gemm_case(M, N, K, bias, act, resid, glu, obf)
+    finally:
+        _lib().dtk_dbg_gemm_impl(prev)

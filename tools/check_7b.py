@@ -49,3 +49,22 @@ for rep in range(2):
     dt = time.time() - t0
     eng.gen_end()
     print(f"32 rollouts x {steps} sampled tokens at ctx {ctx}..: {32 * steps / dt:.0f} tokens/s ({dt / steps * 1e3:.2f} ms/step), distinct last tokens {len(set(out))}", flush=True)
+
+# ---- the same rollouts READING one shared prefix (dtk_seq_share): shared-prefix attention on / off
+for s in slots:
+    eng.seq_free(s)
+base = eng.seq_alloc()
+eng.prefill(base, ids, 0, None, 0)
+slots = [eng.seq_alloc() for _ in range(32)]
+for s in slots:
+    eng.seq_share(base, s, ctx - 16)   # 496 positions shared, 16 copied
+for cas in (1, 0, 1):
+    eng.set_option("cascade_attn", cas)
+    eng.gen_begin(slots, [ctx] * 32, [7] * 32, params)
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(steps):
+        eng.gen_step()
+    out = eng.gen_wait(steps - 1)
+    dt = time.time() - t0
+    eng.gen_end()
+    print(f"shared prefix, cascade_attn={cas}: {32 * steps / dt:.0f} tokens/s ({dt / steps * 1e3:.2f} ms/step), distinct last tokens {len(set(out))}", flush=True)
