@@ -44,7 +44,8 @@ constexpr int MEGA_THREADS = (NCW + NPW) * 32;
 constexpr int CONSUMER_THREADS = NCW * 32;
 static_assert(NCW % NPW == 0, "slot ownership: NPW must divide NCW");
 constexpr int TILE_BYTES = 8192;             // ring slot = one weight tile = one 16-key K+V attention item
-constexpr int NT = 112;                      // per-tile partial-sum entries (>= max tiles/group + tiles in flight)
+constexpr int NT = 104;                      // per-tile partial-sum entries (>= max tiles/group + tiles in flight)
+constexpr int NS = 72;                       // 256-column slices of a staged input vector (>= max tiles per group)
 constexpr int NG = 48;                       // per-group arrival counters / prefetched residual rows (>= groups in flight)
 constexpr long long SPIN_CYCLES = 4000000000ll;  // bounded waits (~2 s): trap instead of hanging the GPU
 
@@ -132,7 +133,7 @@ struct Spin {   // bounded polling with a short back-off: trap instead of hangin
   uint32_t n = 0;
   long long t0 = 0;
   DTK_DEV void tick() {
-    __nanosleep(32);
+    __nanosleep(32);   // (0 .. 96 ns measured equal, 256 ns +1 %, 512 ns +3 %; pipelined re-polls slower: profiles/r2_decode_poll_sweep.txt)
     if ((++n & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -192,23 +193,6 @@ DTK_DEV void ld_pairs(const u64* const (&ptr)[N], const bool (&on)[N], uint32_t 
   for (int u = 0; u < N; ++u) out[u] = on[u] ? make_float2(tag_val(w[u].x), tag_val(w[u].y)) : make_float2(0.f, 0.f);
 }
 
-// grid-wide arrival counter over the consumer threads of all CTAs (producer warps never take part): a HINT, not a memory
-// barrier — relaxed arrive, relaxed poll. It tells a CTA when the other CTAs have issued their tagged stores.
-DTK_DEV void hint_barrier(unsigned long long* counter, unsigned long long target, int flags) {
-  consumer_sync();
-  if (flags & 2) return;
-  if (threadIdx.x == 0) {
-    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;\n" ::"l"(counter), "l"(1ull) : "memory");
-    Spin sp;
-    unsigned long long v;
-    do {
-      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(counter) : "memory");
-      if (v < target) sp.tick();
-    } while (v < target);
-  }
-  consumer_sync();
-}
-
 // ------------------------------------------------------------------ work description
 enum { PH_QKV = 0, PH_ATTN = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_LM = 5 };
 
@@ -236,123 +220,99 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
   return a;
 }
 
-// Stage a K-vector into shared memory as the B operand of mma.m16n8k16:
+// The B operand of mma.m16n8k16 for a GEMV: the input vector lives in shared memory as
 // entry [kstep S][t] (uint4) = { hi(x[16S+2t], x[16S+2t+1]), hi(x[16S+2t+8], +9), lo(..2t..), lo(..2t+8..) }
 // where hi = bf16(x), lo = bf16(x - hi). All 8 columns of B are the same vector, so every lane of a quad column reads
-// entry t = lane & 3. Entries for k >= K (padding up to Kp) are zero.
-// The source is a tagged global vector (or, for layer 0, the bf16 embedding row). With norm_w the staged vector is
-// x * w (RMSNorm gain) WITHOUT the 1/rms factor: the GEMV is linear, so the consumers multiply their results by the
-// returned r = rsqrt(mean(x^2) + eps) in the epilogue — the reduction is off the critical path of the staging.
-// Pass 1: coalesced 16-byte loads (one tagged pair per lane) -> fp32 vector in shared memory; pass 2: one thread per
-// k-step converts its 64 bytes in place (the fp32 k-step and its four B entries occupy the same bytes).
-// Deliberately NOT inlined: one copy keeps the whole per-token loop inside the 32 KB instruction cache.
-__device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags, const bf16* src_bf16, int K, int Kp,
-                                        const bf16* norm_w, float eps, float* xs, float* red) {
-  const bool nowait = (flags & 1) != 0, strong_first = (flags & 2) != 0;
-  const int tid = threadIdx.x;
-  // norm gains of this thread's first k-step: requested before the vector so that both L2 round trips overlap
-  uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
-  if (norm_w && tid * 16 < K) {
-    g0 = *reinterpret_cast<const uint4*>(norm_w + tid * 16);
-    if (tid * 16 + 8 < K) g1 = *reinterpret_cast<const uint4*>(norm_w + tid * 16 + 8);
+// entry t = lane & 3. Entries for k >= K (padding up to the 256-column tile) are zero.
+//
+// DATAFLOW STAGING (round 2): a tile (group, ks) needs only the 256-element SLICE ks of the vector, so the warp that owns
+// the tile stages that slice itself, when it gets there — ONE warp: 4 tagged pairs per lane in one coalesced L2 round trip,
+// re-read coherently until their tags match, converted in registers (the two halves of a B entry meet through one shuffle)
+// and written straight to the entries. No CTA-wide barrier in front of a phase: a warp starts multiplying as soon as ITS
+// slice has arrived, and when the slowest producer CTA of the previous phase finally publishes its rows, one warp per CTA
+// has a few tiles left instead of every warp a whole phase. With norm_w the staged slice is x * w (RMSNorm gain) WITHOUT the
+// 1/rms factor (the GEMV is linear: the epilogue scales by r); the slice's sum of squares goes to slice_ss[ks], and
+// r = rsqrt(sum over slices / K + eps) is formed by the epilogue warp (same order in every CTA: identical r everywhere).
+// The vector buffer is single: a slice may only be overwritten when every warp of the CTA is past the previous weight
+// phase (phase_done counts warps x phases); the L2 round trip comes first, so that wait is normally free.
+// Deliberately NOT inlined: one copy keeps the per-token loop inside the instruction cache.
+__device__ __noinline__ void stage_slice(const u64* src, uint32_t in_tag, bool nowait, const bf16* src_bf16, int K, int ks,
+                                         const bf16* norm_w, uint4* xb, float* slice_ss, volatile uint32_t* slice_tag,
+                                         uint32_t my_tag) {
+  const int lane = threadIdx.x & 31;
+  const int npair = K >> 1;
+  float2 v[4];
+  uint32_t gw[4];
+  bool on[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int pi = ks * 128 + u * 32 + lane;
+    on[u] = pi < npair;
+    gw[u] = (norm_w && on[u]) ? *reinterpret_cast<const uint32_t*>(norm_w + 2 * pi) : 0u;
   }
   if (src) {
-    const int npair = K >> 1;
-    float2* xs2 = reinterpret_cast<float2*>(xs);
-    constexpr int PP = 12;   // pairs per thread in flight (one pass covers K = 6144: a single L2 round trip per pass)
-    for (int p0 = 0; p0 < npair; p0 += PP * CONSUMER_THREADS) {
-      ulonglong2 w[PP];
+    ulonglong2 w[4];
 #pragma unroll
-      for (int u = 0; u < PP; ++u) {
-        const int pi = p0 + u * CONSUMER_THREADS + tid;
-        if (pi < npair) w[u] = strong_first ? ld_strong2(src + 2 * pi) : ld_weak2(src + 2 * pi);
+    for (int u = 0; u < 4; ++u)
+      if (on[u]) w[u] = ld_weak2(src + 2 * (ks * 128 + u * 32 + lane));
+    Spin sp;
+    for (;;) {
+      bool bad[4], any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bad[u] = on[u] && !(tag_ok(w[u].x, in_tag) && tag_ok(w[u].y, in_tag));
+        any = any || bad[u];
       }
-      // words whose tag is still old are re-read coherently, ALL of them per round (one L2 round trip per round)
-      Spin sp;
-      for (;;) {
-        bool bad[PP], any = false;
+      if (!any || nowait) break;
+      sp.tick();
 #pragma unroll
-        for (int u = 0; u < PP; ++u) {
-          const int pi = p0 + u * CONSUMER_THREADS + tid;
-          bad[u] = pi < npair && !(tag_ok(w[u].x, tag) && tag_ok(w[u].y, tag));
-          any = any || bad[u];
-        }
-        if (!any || nowait) break;
-        sp.tick();
-#pragma unroll
-        for (int u = 0; u < PP; ++u) {
-          const int pi = p0 + u * CONSUMER_THREADS + tid;
-          if (bad[u]) w[u] = ld_strong2(src + 2 * pi);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < PP; ++u) {
-        const int pi = p0 + u * CONSUMER_THREADS + tid;
-        if (pi < npair) xs2[pi] = make_float2(tag_val(w[u].x), tag_val(w[u].y));
-      }
+      for (int u = 0; u < 4; ++u)
+        if (bad[u]) w[u] = ld_strong2(src + 2 * (ks * 128 + u * 32 + lane));
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = on[u] ? make_float2(tag_val(w[u].x), tag_val(w[u].y)) : make_float2(0.f, 0.f);
   } else {
-    for (int e = tid * 8; e < K; e += CONSUMER_THREADS * 8) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(src_bf16 + e), f);
-      *reinterpret_cast<float4*>(xs + e) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(xs + e + 4) = make_float4(f[4], f[5], f[6], f[7]);
-    }
-  }
-  for (int e = K + tid; e < Kp; e += CONSUMER_THREADS) xs[e] = 0.f;
-  consumer_sync();
-  float ss = 0.f;
-  uint4* xb = reinterpret_cast<uint4*>(xs);
-  for (int S = tid; S < (Kp >> 4); S += CONSUMER_THREADS) {
-    float y[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(xs + S * 16 + i * 4);
-      y[4 * i] = a.x; y[4 * i + 1] = a.y; y[4 * i + 2] = a.z; y[4 * i + 3] = a.w;
-    }
-    if (norm_w) {
-      if (S != tid) {   // later k-steps of this thread (K > 4096): gains fetched here
-        g0 = g1 = make_uint4(0, 0, 0, 0);
-        if (S * 16 < K) g0 = *reinterpret_cast<const uint4*>(norm_w + S * 16);
-        if (S * 16 + 8 < K) g1 = *reinterpret_cast<const uint4*>(norm_w + S * 16 + 8);
+    for (int u = 0; u < 4; ++u) {
+      v[u] = make_float2(0.f, 0.f);
+      if (on[u]) {
+        const uint32_t e = *reinterpret_cast<const uint32_t*>(src_bf16 + 2 * (ks * 128 + u * 32 + lane));
+        v[u] = make_float2(__uint_as_float(e << 16), __uint_as_float(e & 0xffff0000u));
       }
-      float g[16];
-      { float t8[8]; unpack8(g0, t8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = t8[i];
-        unpack8(g1, t8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[8 + i] = t8[i]; }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { ss += y[i] * y[i]; y[i] *= g[i]; }
     }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a = y[2 * j], b = y[2 * j + 1];
-      const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-      hi[j] = pack_bf16x2(ah, bh);
-      lo[j] = pack_bf16x2(a - ah, b - bh);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) xb[S * 4 + t] = make_uint4(hi[t], hi[t + 4], lo[t], lo[t + 4]);
   }
-  // sum of squares: per-warp partials, ONE barrier (the one that publishes the staged vector), every thread adds the eight
-  // partials in the same order (identical r in every CTA). `red` is rewritten by the next normed staging only, which is
-  // behind at least one more consumer barrier.
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float a = v[u].x, b = v[u].y;
+    if (norm_w) {
+      ss += a * a + b * b;
+      a *= __uint_as_float(gw[u] << 16);
+      b *= __uint_as_float(gw[u] & 0xffff0000u);
+    }
+    const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+    const uint32_t hi = pack_bf16x2(ah, bh), lo = pack_bf16x2(a - ah, b - bh);
+    const uint32_t hi2 = __shfl_xor_sync(0xffffffffu, hi, 4), lo2 = __shfl_xor_sync(0xffffffffu, lo, 4);
+    if (!(lane & 4)) xb[(size_t)(ks * 16 + u * 4 + (lane >> 3)) * 4 + (lane & 3)] = make_uint4(hi, hi2, lo, lo2);
+  }
   if (norm_w) {
     ss = warp_sum(ss);
-    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    if (lane == 0) slice_ss[ks] = ss;
   }
-  consumer_sync();
-  float r = 1.f;
-  if (norm_w) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < NCW; ++i) t += red[i];
-    r = rsqrtf(t / K + eps);
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    slice_tag[ks] = my_tag;
   }
-  return r;
+  __syncwarp();
+}
+// r = rsqrt(mean(x^2) + eps) from the slices' sums of squares (fixed order: identical in every warp and CTA)
+DTK_DEV float slices_rn(const float* slice_ss, int nslice, int K, float eps) {
+  const int lane = threadIdx.x & 31;
+  float t = 0.f;
+  for (int i = lane; i < nslice; i += 32) t += *reinterpret_cast<const volatile float*>(slice_ss + i);
+  t = warp_sum(t);
+  return rsqrtf(t / K + eps);
 }
 
 // DBG = true: dev instrumentation (phase stamps, per-tile trace, timing-experiment flags) compiled in.
@@ -360,7 +320,7 @@ __device__ __noinline__ float stage_vec(const u64* src, uint32_t tag, int flags,
 // then lm_head) with a single copy of the tile code and a run-time phase switch in the epilogue: the per-token
 // instruction footprint of a warp stays inside the SM's 32 KB instruction cache (the fully specialised version was
 // ~160 KB, re-fetched from L2 every layer: the first tiles of every phase ran 3-6x slower than the steady state).
-template <bool DBG, bool PAIR>
+template <bool DBG>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -376,6 +336,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] tiles finished per group
   float* rbuf = reinterpret_cast<float*>(gcnt + NG);          // [NG][16] residuals prefetched at a group's first tile
   float* qkn = rbuf + NG * 16;                                // [3][128] q | new key | new value of the CTA's head
+  float* slice_ss = qkn + 384;                                // [NS] sum of squares of each staged slice (normed phases)
+  uint32_t* slice_tag = reinterpret_cast<uint32_t*>(slice_ss + NS);   // [NS] phase tag of the data a slice holds
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + nslots);
   const uint32_t ring_u32 = smem_u32(ring);
 
@@ -391,8 +353,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   int tok = p.tok[0];
   if (tok < 0 || tok >= p.V) tok = 0;
   const int qd = p.heads * 128, kd = p.kv_heads * 128;
-  if (tid < 128) rope_s[tid] = p.rope_cs[(int64_t)pos * 128 + tid];
   if (tid < NG) gcnt[tid] = 0;
+  if (tid < NS) slice_tag[tid] = (uint32_t)p.bar_base[1];   // the epoch: never a phase tag of this launch
+  if (tid < 128) rope_s[tid] = p.rope_cs[(int64_t)pos * 128 + tid];
   __syncthreads();
   const AttnSplit as = attn_split(p, c, G, pos);
   const int kvh = as.head / (p.heads / p.kv_heads);
@@ -725,19 +688,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       stamp(2);
     } else {
-      // ---------------- weight phase: stage the input vector, multiply the CTA's row groups, fused epilogue
+      // ---------------- weight phase: multiply the CTA's row groups (each warp stages the input slices of its own tiles), fused epilogue
       const MegaMat& m = p.mat[mat_of(ph)];
       int g0, cnt, nact;
       phase_span(w, m.groups, g0, cnt, nact);
       const int tpg = m.tpg;
-      float rn = 1.f;
-      if (cnt > 0) {   // idle CTAs skip the staging
-        const int64_t no = (int64_t)l * p.norm_stride;
-        const u64* src = ph == PH_QKV ? (l == 0 ? nullptr : t_xb) : ph == PH_O ? t_att : ph == PH_GU ? t_xa : ph == PH_DOWN ? t_h : t_xb;
-        const int K = ph == PH_O ? qd : ph == PH_DOWN ? p.I : p.H;
-        const bf16* nw = ph == PH_QKV ? p.norm1_0 + no : ph == PH_GU ? p.norm2_0 + no : ph == PH_LM ? p.final_norm : nullptr;
-        rn = stage_vec(src, tag - 1, (nowait ? 1 : 0) | ((p.variant & 1) ? 2 : 0), p.embed + (int64_t)tok * p.H, K, tpg * 256, nw, p.eps, actf, red);
-      }
+      const int64_t no = (int64_t)l * p.norm_stride;
+      const u64* src = ph == PH_QKV ? (l == 0 ? nullptr : t_xb) : ph == PH_O ? t_att : ph == PH_GU ? t_xa : ph == PH_DOWN ? t_h : t_xb;
+      const int K = ph == PH_O ? qd : ph == PH_DOWN ? p.I : p.H;
+      const bf16* nw = ph == PH_QKV ? p.norm1_0 + no : ph == PH_GU ? p.norm2_0 + no : ph == PH_LM ? p.final_norm : nullptr;
+      float rn = 0.f;   // RMSNorm scale of this phase's input: formed by the first epilogue this warp runs (0 = not yet)
       stamp(1);
       const uint32_t nb0 = w.nb, gb0 = w.gb;
       // residual source of the O / DOWN epilogues: the row's previous value in the other residual buffer
@@ -745,86 +705,40 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const uint32_t res_tag = (ph == PH_O) ? tag - 3 : tag - 2;   // O: x after the previous layer's MLP; DOWN: this layer's xa
       const int ntiles = cnt * tpg;
       uint32_t j = ((uint32_t)warp + NCW - (nb0 & (NCW - 1))) & (NCW - 1);
-      // The warps walk their tiles in ROUNDS (tile j + 8 r in round r) and meet every fourth round: a ring slot belongs to
-      // one consumer warp, so nothing else stops a warp pair from running many groups ahead of another one, and a warp that
+      // The warps walk their tiles in ROUNDS (tile j + 8 r in round r) and meet every sync_every rounds: a ring slot belongs
+      // to one consumer warp, so nothing else stops a warp from running many groups ahead of another one, and a warp that
       // gets NT tiles ahead would overwrite its own partial sums of a group whose epilogue has not run yet (seen at the
-      // v2-8b shape: 880 lm_head tiles per CTA, HBM-bound, scattered wrong logits). The interval is as long as the
-      // partial-sum window allows: drift (interval rounds) + one group + the round in flight <= NT.
+      // v2-8b shape: 880 lm_head tiles per CTA, scattered wrong logits). The interval is as long as the windows allow:
+      // drift (interval rounds) + one group + the round in flight <= NT partial sums, groups in flight <= NG / 2.
+      // (QKV -> attention has no barrier in between, but the attention phase writes no partial sums.)
       const int rounds = (ntiles + NCW - 1) / NCW;
-      const int sync_every = max(1, (NT - tpg - 2 * NCW) / NCW);
+      const int sync_every = max(1, min((NT - tpg - 2 * NCW) / NCW, NG * tpg / (2 * NCW)));
       int since_sync = 0;
       {
         const uint32_t n00 = nb0 + j;
         uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
         uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-        for (int rd = 0; rd < rounds; rd += PAIR ? 2 : 1) {
-          if (PAIR) {
-            if (since_sync + 2 > sync_every) { consumer_sync(); since_sync = 0; }
-            since_sync += 2;
-          } else if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
-          if ((int)j >= ntiles) { j += PAIR ? 2 * NCW : NCW; continue; }
+        for (int rd = 0; rd < rounds; ++rd) {
+          if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
+          if ((int)j >= ntiles) { j += NCW; continue; }
           long long* trow = nullptr;
           if (DBG && ctr) {
             const uint32_t row = nb0 + j - ctr_nb0;
             if (row < 160u) trow = ctr + row * 4;
           }
           if (DBG && trow && lane == 0) trow[3] = clock64();
-          // second tile of this iteration (PAIR): the warp's tile of the next round
-          const bool two = PAIR && (int)(j + NCW) < ntiles;
-          uint32_t slB = sl + NCW, useB = use, ksB = ks + NCW, kB = k;
-          if (slB >= (uint32_t)nslots) { slB -= nslots; ++useB; }
-          while (ksB >= (uint32_t)tpg) { ksB -= tpg; ++kB; }
+          // the tile's slice of the input vector (normally staged by this very warp at its previous tile of the same ks)
+          if (*reinterpret_cast<volatile uint32_t*>(slice_tag + ks) != tag)
+            stage_slice(src, tag - 1, nowait, p.embed + (int64_t)tok * p.H, K, (int)ks, nw, xb, slice_ss, slice_tag, tag);
           mbar_wait(full0 + 8 * sl, use & 1);
-          if (two) mbar_wait(full0 + 8 * slB, useB & 1);
           if (DBG && trow && lane == 0) trow[1] = clock64();
           // ---- one tile = 16 k-steps of (ldmatrix.x4, mma). B operand: even columns of the 16 x 8 B tile carry the hi
           // part of x, odd columns the lo part (column = lane >> 2), so ONE mma per k-step yields W.hi in accumulator
           // column 0 and W.lo in column 1. The A fragments are loaded in batches interleaved with the mma of earlier
           // batches, so that the tensor pipe starts while the rest of the tile is still being read (shared-memory returns
           // are in order; all 16 ldmatrix in front of the first mma made the two pipes take turns: 0.53 us per tile).
-          // PAIR: two tiles per iteration, half tiles interleaved (loads of one under the mma of the other) and both
-          // tiles' bookkeeping behind one warp sync: 819 instead of 1025 cycles per round in tools/tile_bench.
-          float rA0, rA2, rB0 = 0.f, rB2 = 0.f;
-          if (two) {
-            const uint32_t ta0 = ring_u32 + sl * TILE_BYTES + lane * 16, ta1 = ring_u32 + slB * TILE_BYTES + lane * 16;
-            const uint2* xp0 = reinterpret_cast<const uint2*>(xb + (size_t)ks * 64 + (lane & 3)) + ((lane >> 2) & 1);
-            const uint2* xp1 = reinterpret_cast<const uint2*>(xb + (size_t)ksB * 64 + (lane & 3)) + ((lane >> 2) & 1);
-            uint32_t X[8][4], Y[8][4], Z[8][4];
-            uint2 bp[8], bq[8];
-            float a0[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, a1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-            for (int s = 0; s < 8; ++s) ldmatrix_x4(X[s][0], X[s][1], X[s][2], X[s][3], ta0 + s * 512);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) bp[s] = xp0[s * 8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) ldmatrix_x4(Y[s][0], Y[s][1], Y[s][2], Y[s][3], ta1 + s * 512);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) bq[s] = xp1[s * 8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) mma_bf16_16816(a0[s & 1], X[s], bp[s].x, bp[s].y);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) ldmatrix_x4(Z[s][0], Z[s][1], Z[s][2], Z[s][3], ta0 + (s + 8) * 512);
-            cur_slot = sl;
-            release();
-#pragma unroll
-            for (int s = 0; s < 8; ++s) bp[s] = xp0[(s + 8) * 8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) mma_bf16_16816(a1[s & 1], Y[s], bq[s].x, bq[s].y);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) ldmatrix_x4(X[s][0], X[s][1], X[s][2], X[s][3], ta1 + (s + 8) * 512);
-            cur_slot = slB;
-            release();
-#pragma unroll
-            for (int s = 0; s < 8; ++s) bq[s] = xp1[(s + 8) * 8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) mma_bf16_16816(a0[s & 1], Z[s], bp[s].x, bp[s].y);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) mma_bf16_16816(a1[s & 1], X[s], bq[s].x, bq[s].y);
-            rA0 = (a0[0][0] + a0[1][0]) + (a0[0][1] + a0[1][1]);
-            rA2 = (a0[0][2] + a0[1][2]) + (a0[0][3] + a0[1][3]);
-            rB0 = (a1[0][0] + a1[1][0]) + (a1[0][1] + a1[1][1]);
-            rB2 = (a1[0][2] + a1[1][2]) + (a1[0][3] + a1[1][3]);
-          } else {
+          float rA0, rA2;
+          {
             cur_slot = sl;
             float acc[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
             const uint32_t ta = ring_u32 + sl * TILE_BYTES + lane * 16;
@@ -854,44 +768,31 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             rA0 = (acc[0] + c1[0]) + (acc[1] + c1[1]);
             rA2 = (acc[2] + c1[2]) + (acc[3] + c1[3]);
           }
-          const uint32_t gsA = (gb0 + k) % NG, gsB = (gb0 + kB) % NG;
-          if ((ph == PH_O || ph == PH_DOWN) && lane < 16) {
+          const uint32_t gsA = (gb0 + k) % NG;
+          if ((ph == PH_O || ph == PH_DOWN) && lane < 16 && ks == 0) {
             // residual of row (group, lane), fetched at the group's FIRST tile so that its L2 latency is off the
             // critical path of the group's epilogue (the value was published two or more phases ago)
-#pragma unroll 1
-            for (int t = 0; t < (two ? 2 : 1); ++t) {
-              if ((t ? ksB : ks) != 0) continue;
-              const int row = (g0 + (int)(t ? kB : k)) * 16 + lane;
-              float bres = 0.f;
-              if (row < p.H)
-                bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
-                                              : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
-              rbuf[(t ? gsB : gsA) * 16 + lane] = bres;
-            }
+            const int row = (g0 + (int)k) * 16 + lane;
+            float bres = 0.f;
+            if (row < p.H)
+              bres = (ph == PH_O && l == 0) ? __bfloat162float(p.embed[(int64_t)tok * p.H + row])
+                                            : settle1(ld_weak1(res_src + row), res_src + row, res_tag, nowait);
+            rbuf[gsA * 16 + lane] = bres;
           }
           if ((lane & 3) == 0) {
             float* tp = tpart + ((nb0 + j) % NT) * 16;
             tp[lane >> 2] = rA0;
             tp[(lane >> 2) + 8] = rA2;
-            if (two) {
-              float* tq = tpart + ((nb0 + j + NCW) % NT) * 16;
-              tq[lane >> 2] = rB0;
-              tq[(lane >> 2) + 8] = rB2;
-            }
           }
           __syncwarp();
-          int oldA = -1, oldB = -1;
+          int oldA = -1;
           if (lane == 0) {
             __threadfence_block();
             oldA = atomicAdd(&gcnt[gsA], 1);
-            if (two) oldB = atomicAdd(&gcnt[gsB], 1);   // same group as A (tpg > 8): only this one can come last
           }
           const int lastA = __shfl_sync(0xffffffffu, oldA == tpg - 1, 0);
-          const int lastB = PAIR ? __shfl_sync(0xffffffffu, oldB == tpg - 1, 0) : 0;
-#pragma unroll 1
-          for (int t = 0; t < (PAIR ? 2 : 1); ++t) {
-            if (!(t ? lastB : lastA)) continue;
-            const uint32_t ek = t ? kB : k, egs = t ? gsB : gsA;
+          if (lastA) {
+            const uint32_t ek = k, egs = gsA;
               __threadfence_block();
               // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
               const uint32_t n0 = nb0 + ek * tpg;
@@ -900,6 +801,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
                 for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
               const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
               if (lane == 0) gcnt[egs] = 0;
+              if (nw && rn == 0.f) rn = slices_rn(slice_ss, tpg, K, p.eps);   // (every slice of the vector is staged: the group is complete)
               if (lane < 8) {
                 const int gi = g0 + (int)ek, r = lane;
                 if (ph == PH_QKV) {
@@ -950,11 +852,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
               }
           }
           if (DBG && trow && lane == 0) trow[2] = clock64();
-          const int adv = two ? 2 * NCW : NCW;   // (a lone last tile: the loop ends anyway)
-          j += PAIR ? 2 * NCW : NCW;
-          sl += adv;
-          while (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
-          ks += adv;
+          j += NCW;
+          sl += NCW;
+          if (sl >= (uint32_t)nslots) { sl -= nslots; ++use; }
+          ks += NCW;
           while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
         }
       }
@@ -963,14 +864,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
       stamp(2);
     }
-    // phase boundary (none after qkv: the attention phase polls its head's q itself; none after lm_head)
-    if (ph != PH_QKV && ph != PH_LM) {
-      // No grid-wide arrival counter by default: the next phase's staging polls the tagged words it needs (weak load,
-      // then coherent re-reads with a short back-off) — measured 0.80 vs 0.91 ms per token with the counter in front
-      // (profiles/r2_decode_variants.txt). variant bit 1 restores the counter for A/B runs.
-      if (p.variant & 2) { bar_target += G; hint_barrier(p.bar_count, bar_target, dflags); }
-      else consumer_sync();
-    }
+    // Phase boundary: a CTA-wide barrier only (none after qkv: the attention phase meets after polling its head's q; none
+    // after lm_head). No grid-wide arrival counter: the next phase's warps poll the tagged words of their own slices
+    // (0.80 vs 0.91 ms per token with a counter, profiles/r2_decode_variants.txt). The CTA barrier is what allows the single
+    // vector buffer (slices are overwritten by the next phase; the attention merge scratch aliases it), and it is also FASTER
+    // than letting the warps drift (0.788 vs 0.809 ms per token, profiles/r2_decode_ab.txt).
+    if (ph != PH_QKV && ph != PH_LM) consumer_sync();
     stamp(3);
     if (++ph == 5) { ph = 0; ++l; }
   }
@@ -1059,7 +958,7 @@ cudaError_t launch_retile(const bf16* src, int N, int K, int mode, bf16* dst, cu
 }
 
 int mega_smem_bytes(const MegaArgs& a) {
-  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4;
+  return a.nslots * TILE_BYTES + a.act_floats * 4 + 2 * a.nslots * 8 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4 + NS * 8;
 }
 
 cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_optin, int num_sms, int* grid_out) {
@@ -1071,8 +970,8 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
   a.act_floats = actf;
   a.tg_H = pad(H);
   a.tg_I = pad(I);
-  if ((I + 255) / 256 > NT - 44) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight
-  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4 + 64;
+  if ((I + 255) / 256 > NT - 44 || (I + 255) / 256 > NS || (H + 255) / 256 > NS) return cudaErrorInvalidValue;  // partial-sum window must cover a group + tiles in flight; slice table
+  const int fixed = actf * 4 + (16 + 128 + NT * 16) * 4 + NG * 4 + NG * 16 * 4 + 384 * 4 + NS * 8 + 64;
   int nslots = (max_smem_optin - fixed) / (TILE_BYTES + 16);
   if (nslots > 32) nslots = 32;
   // every ring slot must always be filled by the same producer warp and drained by the same consumer warp
@@ -1089,9 +988,7 @@ cudaError_t mega_configure(MegaArgs& a, int H, int I, int heads, int max_smem_op
 cudaError_t launch_decode_mega(const MegaArgs& a, int grid, cudaStream_t s, uint64_t* counter) {
   const int smem = mega_smem_bytes(a);
   const bool dbgk = a.dbg != nullptr || a.dbg2 != nullptr || a.dbg_flags != 0;
-  const bool pair = (a.variant & 4) != 0;   // two tiles per consumer-warp iteration
-  const void* fn = dbgk ? (pair ? (const void*)decode_mega_kernel<true, true> : (const void*)decode_mega_kernel<true, false>)
-                        : (pair ? (const void*)decode_mega_kernel<false, true> : (const void*)decode_mega_kernel<false, false>);
+  const void* fn = dbgk ? (const void*)decode_mega_kernel<true> : (const void*)decode_mega_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&a};

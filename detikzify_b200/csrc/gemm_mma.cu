@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_tn_kernel(const GemmArgs p)
 
 }  // namespace
 
-static int g_gemm_impl = 1;  // 0 = mma.sync everywhere, 1 = tcgen05 one-tile-per-CTA 128 x 128 kernel, 2 = persistent 128 x 256 tcgen05 kernel (dtk_set_option "gemm_impl")
+static int g_gemm_impl = 2;  // 0 = mma.sync everywhere, 1 = tcgen05 one-tile-per-CTA 128 x 128 kernel, 2 (default) = persistent 128 x 256 tcgen05 kernel, 3 = CTA-pair 256 x 256 kernel (dtk_set_option "gemm_impl")
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 int get_gemm_impl() { return g_gemm_impl; }
 

@@ -8,7 +8,7 @@ from detikzify_b200.model import load
 
 name = "nllg/detikzify-ds-7b"
 t0 = time.time()
-model, _ = load(name, device_map=0, max_seqs=33, max_batch=32)
+model, _ = load(name, device_map=0, max_seqs=40, max_batch=32)
 eng, cfg = model.engine, model.config
 print(f"load {time.time() - t0:.1f}s; persistent={eng.get_option('decode_persistent')}", flush=True)
 ctx = 512
