@@ -7,29 +7,30 @@
 //
 //   * grid = one CTA per SM, resident for the whole token (cooperative launch);
 //   * 4 PRODUCER warps per CTA (one issuing lane each, registers handed back with setmaxnreg.dec) walk the
-//     CTA's statically known list of weight tiles for ALL layers and phases and stream them with 1-D TMA bulk
-//     copies (cp.async.bulk + mbarrier complete_tx) into a ~190 KB shared-memory ring of 8 KB slots, never
-//     waiting for activations — weights do not depend on them — so HBM stays busy across phase boundaries
-//     (measured: the ring sustains 7.2 TB/s);
-//   * 8 CONSUMER warps (setmaxnreg.inc 232: no spills, a whole tile in flight) take tiles in order. A tile is
-//     16 output rows x 256 k, pre-arranged in HBM (launch_retile, once at load) so that it lands in shared
-//     memory exactly in ldmatrix.x4 order; the dot products run on the tensor pipe (mma.sync m16n8k16, fp32
-//     accumulate) with the activation vector split into bf16 hi + lo parts (x = hi + lo to 2^-17) that occupy
-//     alternating columns of the B operand: one HMMA per k-step, fp32-grade GEMV; the ring slot is handed back
-//     as soon as its shared-memory reads are issued;
+//     CTA's statically known list of weight tiles AND cached key/value items for ALL layers and phases and stream
+//     them with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a ~190 KB shared-memory ring of
+//     8 KB slots, never waiting for activations — neither weights nor the cache depend on this token — so HBM
+//     stays busy across phase boundaries (the ring alone sustains 7.2 TB/s, profiles/r2_stream_per_sm.txt);
+//   * 8 CONSUMER warps (setmaxnreg.inc: the kernel calls no function, or ptxas would ignore setmaxnreg) take
+//     tiles in order. A tile is 16 output rows x 256 k, pre-arranged in HBM (launch_retile, once at load) so that
+//     it lands in shared memory exactly in ldmatrix.x4 order; the dot products run on the tensor pipe (mma.sync
+//     m16n8k16, fp32 accumulate) with the activation vector split into bf16 hi + lo parts (x = hi + lo to 2^-17)
+//     that occupy alternating columns of the B operand: one HMMA per k-step, fp32-grade GEMV; the ring slot is
+//     handed back as soon as its shared-memory reads are issued;
 //   * rows are grouped so that one thread's two accumulator rows (g, g+8) are a RoPE pair (i, i+64) or a
-//     SwiGLU pair (gate_i, up_i): RMSNorm prologue, RoPE + KV-cache write, SiLU*mul and residual add are
-//     all fused; partial sums of a group's k-tiles are combined in a fixed order (deterministic);
-//   * phases are separated by a hand-rolled grid barrier (release-reduction + acquire poll) among the
-//     consumer threads; the ring depth (~4 us of streaming per SM) covers part of the barrier + activation
-//     re-staging bubble;
+//     SwiGLU pair (gate_i, up_i): RMSNorm scale, RoPE + KV-cache write, SiLU*mul and residual add are all fused
+//     into the group epilogue; partial sums of a group's k-tiles are combined in a fixed order (deterministic);
+//   * values that cross CTAs travel as 8-byte TAGGED words {fp32, phase tag} (see below): no grid-wide barrier or
+//     counter anywhere, readers poll the words they need;
+//   * the input vector of a phase is staged per 256-element SLICE by the warp whose tile needs it (stage_slice):
+//     one coalesced L2 round trip per warp, no CTA-wide two-pass staging; phases end with a CTA barrier only;
 //   * a phase's 16-row groups are cut into equal blocks over as many CTAs as needed (the participating set
 //     rotates from phase to phase), so participants finish together and idle CTAs' producers run ahead.
 //
-// Per layer: P1 qkv(+RMSNorm, RoPE, KV write) | P2 split-KV attention (the CTA's KV rows are L2-prefetched at
-// the start of the layer and read with plain loads; the last CTA of a head to arrive merges the partials) |
-// P3 o-proj + residual | P4 gate/up + SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final
-// RMSNorm). DESIGN.md section 4 lists the measured alternatives that were rejected.
+// Per layer: P1 qkv(+RMSNorm, RoPE, KV write) | P2 split-KV attention (the CTA's share of the cached keys/values
+// arrives through the ring; a fixed owner CTA per head merges the partials) | P3 o-proj + residual | P4 gate/up +
+// SiLU*mul (+RMSNorm) | P5 down + residual; finally lm_head (+final RMSNorm, + greedy argmax and token publication
+// in the kernel tail). DESIGN.md section 4 lists the measured alternatives that were rejected.
 //
 // Replaces the per-token HF eager path (modeling_llama.py:303-333, ~900 launches per token).
 #include "common.cuh"
@@ -70,8 +71,8 @@ DTK_DEV uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
-// slow path of a wait, out of line (the hot loop stays small): bounded spin, trap instead of hanging the GPU
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+// slow path of a wait: bounded spin, trap instead of hanging the GPU
+DTK_DEV void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
   while (!mbar_try(bar, parity)) {
@@ -142,7 +143,7 @@ struct Spin {   // bounded polling with a short back-off: trap instead of hangin
   }
 };
 // make a (weakly loaded) pair valid: re-read with coherent loads until both tags match (slow path out of line)
-__device__ __noinline__ ulonglong2 poll2(const u64* p, uint32_t tag) {
+DTK_DEV ulonglong2 poll2(const u64* p, uint32_t tag) {
   Spin sp;
   for (;;) {
     const ulonglong2 w = ld_strong2(p);
@@ -150,7 +151,7 @@ __device__ __noinline__ ulonglong2 poll2(const u64* p, uint32_t tag) {
     sp.tick();
   }
 }
-__device__ __noinline__ u64 poll1(const u64* p, uint32_t tag) {
+DTK_DEV u64 poll1(const u64* p, uint32_t tag) {
   Spin sp;
   for (;;) {
     const u64 w = ld_strong1(p);
@@ -235,8 +236,8 @@ DTK_DEV AttnSplit attn_split(const MegaArgs& p, int c, int G, int pos) {
 // r = rsqrt(sum over slices / K + eps) is formed by the epilogue warp (same order in every CTA: identical r everywhere).
 // The vector buffer is single: a slice may only be overwritten when every warp of the CTA is past the previous weight
 // phase (phase_done counts warps x phases); the L2 round trip comes first, so that wait is normally free.
-// Deliberately NOT inlined: one copy keeps the per-token loop inside the instruction cache.
-__device__ __noinline__ void stage_slice(const u64* src, uint32_t in_tag, bool nowait, const bf16* src_bf16, int K, int ks,
+// Inlined (one call site): ptxas ignores setmaxnreg in a kernel that calls functions (C7507); fully inlined measured 0.8 % faster.
+DTK_DEV void stage_slice(const u64* src, uint32_t in_tag, bool nowait, const bf16* src_bf16, int K, int ks,
                                          const bf16* norm_w, uint4* xb, float* slice_ss, volatile uint32_t* slice_tag,
                                          uint32_t my_tag) {
   const int lane = threadIdx.x & 31;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
 
   if (warp >= NCW) {
     // =============================================================== PRODUCERS
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       Walk w;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   }
 
   // ================================================================= CONSUMERS
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
   const int dflags = DBG ? p.dbg_flags : 0;
   const bool nowait = (dflags & 2) != 0;
   unsigned long long bar_target = p.bar_base[0];   // arrivals counted before this launch
