@@ -167,6 +167,7 @@ struct dtk_engine {
   int mega_debug = 0;
   int mega_flags = 0;
   int mega_variant = 0;
+  int mega_nslots = 0;       // dev option "mega_nslots": cap on the ring depth of the persistent kernel (0 = as configured)
   int fuse_greedy = 1;
   int cascade_attn = 1;      // batched decode: rows that share one prefix reduce it with ONE tensor-core pass (option "cascade_attn")
   int cas_slot = -1, cas_len = 0;   // set per step by dtk_decode / dtk_gen_begin: uniform shared prefix of the current batch
@@ -417,6 +418,7 @@ int decode_launches(dtk_engine* eng, int B, const int64_t* tok64, float* logits,
     m.dbg = eng->mega_debug ? eng->d_dbg : nullptr;
     m.dbg_flags = eng->mega_flags;
     m.variant = eng->mega_variant;
+    if (eng->mega_nslots >= 8 && eng->mega_nslots < m.nslots) m.nslots = eng->mega_nslots & ~7;
     m.fuse_greedy = 0;
     if (eng->gen_fused && logits == eng->d_logits) {   // inside the greedy generation loop
       m.fuse_greedy = 1; m.bad_token = eng->gen_sample.bad_token; m.ring = eng->ring; m.max_pos = eng->cfg.max_len - 1;
@@ -1251,6 +1253,10 @@ int dtk_set_option(dtk_engine* eng, const char* key, int64_t value) {
     eng->mega_variant = (int)value;
     return DTK_OK;
   }
+  if (std::strcmp(key, "mega_nslots") == 0) {  // dev: smaller ring (8 / 16) for A/B runs of the stream's depth
+    eng->mega_nslots = (int)value;
+    return DTK_OK;
+  }
   if (std::strcmp(key, "mega_trace_layer") == 0) {  // dev: per-tile clock trace of this layer (-1 = off); needs mega_debug
     eng->mega_trace_layer = (int)value;
     return DTK_OK;
@@ -1308,7 +1314,10 @@ int dtk_dbg_gemm(const void* A, const void* Wm, const void* bias, const float* r
   g.A = (const bf16*)A; g.lda = K; g.W = (const bf16*)Wm; g.ldw = K; g.M = M; g.N = N; g.K = K;
   g.bias = (const bf16*)bias; g.resid = resid; g.ldr = glu ? N / 2 : N; g.act = act; g.glu = glu;
   g.out_f32 = out_f32; g.out_bf16 = (bf16*)out_bf16; g.ldo = glu ? N / 2 : N;
-  return launch_gemm(g, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+  set_gemm_small_fallback(0);   // the hook tests the kernel that gemm_impl names
+  const cudaError_t e = launch_gemm(g, (cudaStream_t)stream, nullptr);
+  set_gemm_small_fallback(1);
+  return e == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
 }
 
 int dtk_dbg_flash_attn(const void* q, const void* k, const void* v, void* o, int B, int heads, int Tq, int Tk,

@@ -14,7 +14,7 @@ from detikzify_b200.model import load
 name = sys.argv[1] if len(sys.argv) > 1 else "nllg/detikzify-ds-1.3b"
 ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 groups = sys.argv[3].split(";") if len(sys.argv) > 3 else [""]
-KEYS = ["mega_variant"]
+KEYS = ["mega_variant", "mega_nslots"]
 DEFAULTS = {}
 
 model, _ = load(name, device_map=0)
