@@ -1314,10 +1314,7 @@ int dtk_dbg_gemm(const void* A, const void* Wm, const void* bias, const float* r
   g.A = (const bf16*)A; g.lda = K; g.W = (const bf16*)Wm; g.ldw = K; g.M = M; g.N = N; g.K = K;
   g.bias = (const bf16*)bias; g.resid = resid; g.ldr = glu ? N / 2 : N; g.act = act; g.glu = glu;
   g.out_f32 = out_f32; g.out_bf16 = (bf16*)out_bf16; g.ldo = glu ? N / 2 : N;
-  set_gemm_small_fallback(0);   // the hook tests the kernel that gemm_impl names
-  const cudaError_t e = launch_gemm(g, (cudaStream_t)stream, nullptr);
-  set_gemm_small_fallback(1);
-  return e == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
+  return launch_gemm(g, (cudaStream_t)stream, nullptr) == cudaSuccess ? DTK_OK : DTK_ERR_CUDA;
 }
 
 int dtk_dbg_flash_attn(const void* q, const void* k, const void* v, void* o, int B, int heads, int Tq, int Tk,

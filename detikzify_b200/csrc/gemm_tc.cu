@@ -879,8 +879,6 @@ static cudaError_t launch_tc_pair(const GemmArgs& a, cudaStream_t s, uint64_t* c
   return e;
 }
 
-static int g_small_fallback = 1;   // 0 inside the kernel-level test hook: gemm_impl 2 then always means the persistent kernel
-void set_gemm_small_fallback(int v) { g_small_fallback = v; }
 static int g_skinny_swap = 1;   // dev switch (dtk_set_option "gemm_skinny_swap"): 1 = swapped-operand tile for M < 64
 void set_gemm_skinny_swap(int v) { g_skinny_swap = v; }
 
@@ -890,13 +888,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t s, uint64_t* counter)
     return a.M <= 32 ? launch_tc_swap<32, 5>(a, s, counter) : launch_tc_swap<64, 4>(a, s, counter);
   }
   if (a.M < 64) return launch_tc_variant<32, 8, 1>(a, s, counter);   // skinny: batched decode
-  if (get_gemm_impl() == 2) {   // persistent 128 x 256, overlapped epilogue
-    // few output tiles (ViT out/fc2 at batch 1: 30, prefill down-projection at T = 243: 16): the one-tile 128 x 128 kernel puts
-    // twice as many CTAs on the chip (35 vs 39 us, profiles/r2_gemm_bench.txt)
-    const int tiles256 = ((a.M + TBM - 1) / TBM) * ((a.N + PBN - 1) / PBN);
-    if (g_small_fallback && tiles256 < 48) return launch_tc_variant<128, 3, 2>(a, s, counter);
-    return launch_tc_persist(a, s, counter);
-  }
+  if (get_gemm_impl() == 2) return launch_tc_persist(a, s, counter);   // persistent 128 x 256, overlapped epilogue (handing the few-tile
+  // products of the batch-1 ViT to the 128 x 128 kernel was measured: 5.47 vs 4.72 ms per image, rejected)
   if (get_gemm_impl() == 3) return launch_tc_pair(a, s, counter);      // CTA pairs, 256 x 256, cta_group::2
   return launch_tc_variant<128, 3, 2>(a, s, counter);
 }

@@ -40,7 +40,6 @@ void set_gemm_swap_split(int v);    // dev: 0 (default) = heuristic split-K fact
 void set_gemm_skinny_swap(int v);   // dev: 1 (default) = swapped-operand tcgen05 tile for M < 64, 0 = 128 x 32 tile
 void set_gemm_impl(int impl);   // 0 = mma.sync everywhere, 1 = tcgen05 where supported (process-wide dev switch)
 int get_gemm_impl();
-void set_gemm_small_fallback(int v);   // 1 (default): gemm_impl 2 hands products with < 48 output tiles to the 128 x 128 kernel
 
 // ---------------------------------------------------------------- flash attention (mma.sync)
 struct AttnArgs {
