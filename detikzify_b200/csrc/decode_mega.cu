@@ -20,6 +20,8 @@
 //   * rows are grouped so that one thread's two accumulator rows (g, g+8) are a RoPE pair (i, i+64) or a
 //     SwiGLU pair (gate_i, up_i): RMSNorm scale, RoPE + KV-cache write, SiLU*mul and residual add are all fused
 //     into the group epilogue; partial sums of a group's k-tiles are combined in a fixed order (deterministic);
+//     the epilogues of a phase run in PARALLEL behind a CTA barrier (warp w takes groups w, w + 8, ...), not on whichever
+//     warp finishes a group last;
 //   * values that cross CTAs travel as 8-byte TAGGED words {fp32, phase tag} (see below): no grid-wide barrier or
 //     counter anywhere, readers poll the words they need;
 //   * the input vector of a phase is staged per 256-element SLICE by the warp whose tile needs it (stage_slice):
@@ -143,14 +145,6 @@ struct Spin {   // bounded polling with a short back-off: trap instead of hangin
   }
 };
 // make a (weakly loaded) pair valid: re-read with coherent loads until both tags match (slow path out of line)
-DTK_DEV ulonglong2 poll2(const u64* p, uint32_t tag) {
-  Spin sp;
-  for (;;) {
-    const ulonglong2 w = ld_strong2(p);
-    if (tag_ok(w.x, tag) && tag_ok(w.y, tag)) return w;
-    sp.tick();
-  }
-}
 DTK_DEV u64 poll1(const u64* p, uint32_t tag) {
   Spin sp;
   for (;;) {
@@ -158,10 +152,6 @@ DTK_DEV u64 poll1(const u64* p, uint32_t tag) {
     if (tag_ok(w, tag)) return w;
     sp.tick();
   }
-}
-DTK_DEV float2 settle2(ulonglong2 w, const u64* p, uint32_t tag, bool nowait) {
-  if (!(tag_ok(w.x, tag) && tag_ok(w.y, tag)) && !nowait) w = poll2(p, tag);
-  return make_float2(tag_val(w.x), tag_val(w.y));
 }
 DTK_DEV float settle1(u64 w, const u64* p, uint32_t tag, bool nowait) {
   if (!tag_ok(w, tag) && !nowait) w = poll1(p, tag);
@@ -334,7 +324,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   float* red = reinterpret_cast<float*>(bars + 2 * nslots);  // 16 floats
   float* rope_s = red + 16;                                   // [64][2] cos/sin of this position
   float* tpart = rope_s + 128;                                // [NT][16] per-tile partial sums
-  int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] tiles finished per group
+  int* gcnt = reinterpret_cast<int*>(tpart + NT * 16);        // [NG] (unused since the epilogues run behind a barrier; keeps the layout)
   float* rbuf = reinterpret_cast<float*>(gcnt + NG);          // [NG][16] residuals prefetched at a group's first tile
   float* qkn = rbuf + NG * 16;                                // [3][128] q | new key | new value of the CTA's head
   float* slice_ss = qkn + 384;                                // [NS] sum of squares of each staged slice (normed phases)
@@ -354,7 +344,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   int tok = p.tok[0];
   if (tok < 0 || tok >= p.V) tok = 0;
   const int qd = p.heads * 128, kd = p.kv_heads * 128;
-  if (tid < NG) gcnt[tid] = 0;
   if (tid < NS) slice_tag[tid] = (uint32_t)p.bar_base[1];   // the epoch: never a phase tag of this launch
   if (tid < 128) rope_s[tid] = p.rope_cs[(int64_t)pos * 128 + tid];
   __syncthreads();
@@ -715,12 +704,87 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       const int rounds = (ntiles + NCW - 1) / NCW;
       const int sync_every = max(1, min((NT - tpg - 2 * NCW) / NCW, NG * tpg / (2 * NCW)));
       int since_sync = 0;
+      // ---- group epilogues. They do NOT run inside the tile loop: with "the warp that finishes a group's last tile runs its
+      // epilogue" the warp that is last in one round starts its next tile late, is last again, and ends up with ALL epilogues of
+      // the phase in series (gate/up: it finished 2 us after the other seven warps, profiles/r2_decode_trace_own_cost.txt). The
+      // tiles only leave their partial sums in shared memory; after a CTA barrier the complete groups are dealt to the warps
+      // (warp w: groups k_ep + w, + 8, ...) and run in parallel — no per-tile counter, atomic or fence either. Partials are
+      // summed in k order (deterministic).
+      uint32_t k_ep = 0;   // groups of this phase whose epilogue has run
+      auto run_epilogues = [&](uint32_t k_hi) {
+        for (uint32_t ek = k_ep + (uint32_t)warp; ek < k_hi; ek += NCW) {
+          const uint32_t egs = (gb0 + ek) % NG;
+              const uint32_t n0 = nb0 + ek * tpg;
+              float v = 0.f;
+              if (lane < 16)
+                for (int t = 0; t < tpg; ++t) v += tpart[((n0 + t) % NT) * 16 + lane];
+              const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
+              if (nw && rn == 0.f) rn = slices_rn(slice_ss, tpg, K, p.eps);   // (every slice of the vector is staged: the group is complete)
+              if (lane < 8) {
+                const int gi = g0 + (int)ek, r = lane;
+                if (ph == PH_QKV) {
+                  const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
+                  const int row0 = hb * 128 + i;
+                  const float a0 = v * rn, a1 = v1 * rn;
+                  if (row0 < qd + kd) {
+                    const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
+                    const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
+                    if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
+                    else {
+                      const int kh = (row0 - qd) >> 7;
+                      bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
+                      const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
+                      dd[i] = z0;
+                      dd[i + 64] = z1;
+                      st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
+                      st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                    }
+                  } else {
+                    const int kh = (row0 - qd - kd) >> 7;
+                    bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
+                    const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
+                    dd[i] = z0;
+                    dd[i + 64] = z1;
+                    st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
+                    st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
+                  }
+                } else if (ph == PH_O || ph == PH_DOWN) {
+                  u64* dst = (ph == PH_O) ? t_xa : t_xb;
+                  const int r0 = gi * 16 + r, r1 = r0 + 8;
+                  const float b0 = rbuf[egs * 16 + r], b1 = rbuf[egs * 16 + r + 8];
+                  if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
+                  if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
+                } else if (ph == PH_GU) {
+                  const int i = gi * 8 + r;
+                  if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
+                } else {
+                  const int r0 = gi * 16 + r, r1 = r0 + 8;
+                  const float l0 = v * rn, l1 = v1 * rn;
+                  if (r0 < p.V) p.logits[r0] = l0;
+                  if (r1 < p.V) p.logits[r1] = l1;
+                  if (p.fuse_greedy) {   // rows are visited in increasing order per thread: '>' keeps the lowest index on ties
+                    if (r0 < p.V && r0 != p.bad_token && l0 > best_v) { best_v = l0; best_i = r0; }
+                    if (r1 < p.V && r1 != p.bad_token && l1 > best_v) { best_v = l1; best_i = r1; }
+                  }
+                }
+              }
+        }
+        k_ep = k_hi;
+      };
       {
         const uint32_t n00 = nb0 + j;
         uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
         uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
-        for (int rd = 0; rd < rounds; ++rd) {
-          if (++since_sync > sync_every) { consumer_sync(); since_sync = 1; }
+        for (int rd = 0; rd <= rounds; ++rd) {
+          // a meeting point: every sync_every rounds (partial-sum window) and once after the last round (rd == rounds). All tiles
+          // j < 8 rd are done: the groups they complete get their epilogues (ONE call site: the epilogue code exists once).
+          const bool at_end = rd == rounds;
+          if (at_end || ++since_sync > sync_every) {
+            consumer_sync();
+            run_epilogues(at_end ? (uint32_t)cnt : (uint32_t)(NCW * rd) / (uint32_t)tpg);
+            since_sync = 1;
+          }
+          if (at_end) break;
           if ((int)j >= ntiles) { j += NCW; continue; }
           long long* trow = nullptr;
           if (DBG && ctr) {
@@ -784,73 +848,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
             float* tp = tpart + ((nb0 + j) % NT) * 16;
             tp[lane >> 2] = rA0;
             tp[(lane >> 2) + 8] = rA2;
-          }
-          __syncwarp();
-          int oldA = -1;
-          if (lane == 0) {
-            __threadfence_block();
-            oldA = atomicAdd(&gcnt[gsA], 1);
-          }
-          const int lastA = __shfl_sync(0xffffffffu, oldA == tpg - 1, 0);
-          if (lastA) {
-            const uint32_t ek = k, egs = gsA;
-              __threadfence_block();
-              // ---- group epilogue (this warp saw the last tile of group k): partials summed in k order (deterministic)
-              const uint32_t n0 = nb0 + ek * tpg;
-              float v = 0.f;
-              if (lane < 16)
-                for (int t = 0; t < tpg; ++t) v += *reinterpret_cast<volatile float*>(tpart + ((n0 + t) % NT) * 16 + lane);
-              const float v1 = __shfl_down_sync(0xffffffffu, v, 8);
-              if (lane == 0) gcnt[egs] = 0;
-              if (nw && rn == 0.f) rn = slices_rn(slice_ss, tpg, K, p.eps);   // (every slice of the vector is staged: the group is complete)
-              if (lane < 8) {
-                const int gi = g0 + (int)ek, r = lane;
-                if (ph == PH_QKV) {
-                  const int hb = gi >> 3, i = ((gi & 7) << 3) + r;      // 128-row block, index inside the half
-                  const int row0 = hb * 128 + i;
-                  const float a0 = v * rn, a1 = v1 * rn;
-                  if (row0 < qd + kd) {
-                    const float2 csn = *reinterpret_cast<const float2*>(rope_s + i * 2);
-                    const float y0 = a0 * csn.x - a1 * csn.y, y1 = a1 * csn.x + a0 * csn.y;
-                    if (row0 < qd) { st_tag(t_q + row0, y0, tag); st_tag(t_q + row0 + 64, y1, tag); }
-                    else {
-                      const int kh = (row0 - qd) >> 7;
-                      bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + ((int64_t)kh * p.max_len + pos) * 128;
-                      const bf16 z0 = __float2bfloat16_rn(y0), z1 = __float2bfloat16_rn(y1);
-                      dd[i] = z0;
-                      dd[i + 64] = z1;
-                      st_tag(t_kn + kh * 128 + i, __bfloat162float(z0), tag);      // the cache row as this launch's attention reads it
-                      st_tag(t_kn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-                    }
-                  } else {
-                    const int kh = (row0 - qd - kd) >> 7;
-                    bf16* dd = p.kv + (int64_t)slot * p.kv_slot_stride + (int64_t)l * p.kv_layer_stride + p.kv_v_offset + ((int64_t)kh * p.max_len + pos) * 128;
-                    const bf16 z0 = __float2bfloat16_rn(a0), z1 = __float2bfloat16_rn(a1);
-                    dd[i] = z0;
-                    dd[i + 64] = z1;
-                    st_tag(t_vn + kh * 128 + i, __bfloat162float(z0), tag);
-                    st_tag(t_vn + kh * 128 + i + 64, __bfloat162float(z1), tag);
-                  }
-                } else if (ph == PH_O || ph == PH_DOWN) {
-                  u64* dst = (ph == PH_O) ? t_xa : t_xb;
-                  const int r0 = gi * 16 + r, r1 = r0 + 8;
-                  const float b0 = *reinterpret_cast<volatile float*>(rbuf + egs * 16 + r), b1 = *reinterpret_cast<volatile float*>(rbuf + egs * 16 + r + 8);
-                  if (r0 < p.H) st_tag(dst + r0, b0 + v, tag);
-                  if (r1 < p.H) st_tag(dst + r1, b1 + v1, tag);
-                } else if (ph == PH_GU) {
-                  const int i = gi * 8 + r;
-                  if (i < p.I) st_tag(t_h + i, silu(v * rn) * (v1 * rn), tag);
-                } else {
-                  const int r0 = gi * 16 + r, r1 = r0 + 8;
-                  const float l0 = v * rn, l1 = v1 * rn;
-                  if (r0 < p.V) p.logits[r0] = l0;
-                  if (r1 < p.V) p.logits[r1] = l1;
-                  if (p.fuse_greedy) {   // rows are visited in increasing order per thread: '>' keeps the lowest index on ties
-                    if (r0 < p.V && r0 != p.bad_token && l0 > best_v) { best_v = l0; best_i = r0; }
-                    if (r1 < p.V && r1 != p.bad_token && l1 > best_v) { best_v = l1; best_i = r1; }
-                  }
-                }
-              }
           }
           if (DBG && trow && lane == 0) trow[2] = clock64();
           j += NCW;
