@@ -366,12 +366,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   // A weight phase with `groups` 16-row groups is cut into equal blocks of per = ceil(groups / G) groups; only
   // ceil(groups / per) CTAs take part (same amount of work each, so they finish together), the others idle for that
   // phase. The participating set rotates from phase to phase.
-  auto phase_span = [&](const Walk& w, int groups, int& g0, int& cnt, int& nact) {
-    const int per = (groups + G - 1) / G;
-    nact = (groups + per - 1) / per;
-    const int ci = (int)(((uint32_t)c + (uint32_t)G - w.rot) % (uint32_t)G);
-    g0 = ci * per;
-    cnt = (ci < nact) ? min(per, groups - g0) : 0;
+  // (per / nact come from the host and every modulo below is a conditional subtraction: no division on the per-phase path)
+  auto phase_span = [&](const Walk& w, const MegaMat& m, int& g0, int& cnt, int& nact) {
+    nact = m.nact;
+    int ci = c + G - (int)w.rot;   // rot < G
+    if (ci >= G) ci -= G;
+    g0 = ci * m.per;
+    cnt = (ci < nact) ? min(m.per, m.groups - g0) : 0;
   };
   // phase it -> (layer, kind, matrix index into p.mat)
   auto mat_of = [](int ph) { return ph == PH_QKV ? 0 : ph == PH_O ? 1 : ph == PH_GU ? 2 : ph == PH_DOWN ? 3 : 4; };
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
     const uint32_t pw = (uint32_t)(warp - NCW);
     if (lane == 0) {
       Walk w;
+      uint32_t sl = pw, use = 0;   // ring slot / use count of this lane's next tile: its tiles are n = pw, pw + NPW, ... across ALL phases
       long long* tr = nullptr;   // dev trace: row (local tile index within the traced layer), column 0 = issue clock
       uint32_t tr_nb0 = 0;
       int l = 0, ph = 0;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         const bool attn = ph == PH_ATTN;
         const MegaMat& m = p.mat[mat_of(ph)];
         int g0 = 0, cnt = 0, nact = 0;
-        if (!attn) phase_span(w, m.groups, g0, cnt, nact);
+        if (!attn) phase_span(w, m, g0, cnt, nact);
         const int tpg = attn ? 1 : m.tpg;
         const int ntiles = attn ? as.n_items : cnt * tpg;
         const int64_t kvo = (int64_t)l * p.kv_layer_stride + (int64_t)kvh * p.max_len * 128;
@@ -407,8 +409,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         // own tiles j = j0, j0 + NPW, ...
         uint32_t j = (pw + NPW - (w.nb & (NPW - 1))) & (NPW - 1);
         if ((int)j < ntiles) {
-          const uint32_t n0 = w.nb + j;
-          uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
           for (; (int)j < ntiles; j += NPW) {
             if (use > 0) mbar_wait(empty0 + 8 * sl, (use - 1) & 1);
             const uint32_t dst = ring_u32 + sl * TILE_BYTES, fb = full0 + 8 * sl;
@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         w.nb += ntiles;
         if (!attn) {
           w.gb += cnt;
-          w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
+          w.rot += (uint32_t)nact;
+          if (w.rot >= (uint32_t)G) w.rot -= G;
         }
         if (++ph == 5) { ph = 0; ++l; }
       }
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
   unsigned long long bar_target = p.bar_base[0];   // arrivals counted before this launch
   const uint32_t epoch = (uint32_t)p.bar_base[1];  // tag of phase it = epoch + it + 1
   Walk w;
+  uint32_t sl = (uint32_t)warp, use = 0;   // ring slot / use count of this warp's next tile or item: n = warp, warp + NCW, ... across ALL phases
   uint32_t cur_slot = 0;
   auto release = [&]() {   // hand the ring slot back: every lane's shared-memory reads of it are issued, the arrive is ordered after them
     __syncwarp();
@@ -563,8 +565,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         {
           uint32_t j = ((uint32_t)warp + NCW - (w.nb & (NCW - 1))) & (NCW - 1);
           if ((int)j < as.n_items) {
-            const uint32_t n0 = w.nb + j;
-            uint32_t sl = n0 % (uint32_t)nslots, use = n0 / (uint32_t)nslots;
             for (; (int)j < as.n_items; j += NCW) {
               long long* trow = nullptr;
               if (DBG && ctr) {
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       // ---------------- weight phase: multiply the CTA's row groups (each warp stages the input slices of its own tiles), fused epilogue
       const MegaMat& m = p.mat[mat_of(ph)];
       int g0, cnt, nact;
-      phase_span(w, m.groups, g0, cnt, nact);
+      phase_span(w, m, g0, cnt, nact);
       const int tpg = m.tpg;
       const int64_t no = (int64_t)l * p.norm_stride;
       const u64* src = ph == PH_QKV ? (l == 0 ? nullptr : t_xb) : ph == PH_O ? t_att : ph == PH_GU ? t_xa : ph == PH_DOWN ? t_h : t_xb;
@@ -772,9 +772,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
         k_ep = k_hi;
       };
       {
-        const uint32_t n00 = nb0 + j;
-        uint32_t sl = n00 % (uint32_t)nslots, use = n00 / (uint32_t)nslots;
-        uint32_t k = j / (uint32_t)tpg, ks = j - k * (uint32_t)tpg;
+        uint32_t k = 0, ks = j;
+        while (ks >= (uint32_t)tpg) { ks -= tpg; ++k; }
         for (int rd = 0; rd <= rounds; ++rd) {
           // a meeting point: every sync_every rounds (partial-sum window) and once after the last round (rd == rounds). All tiles
           // j < 8 rd are done: the groups they complete get their epilogues (ONE call site: the epilogue code exists once).
@@ -859,7 +858,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const Mega
       }
       w.nb += ntiles;
       w.gb += cnt;
-      w.rot = (w.rot + (uint32_t)nact) % (uint32_t)G;
+      w.rot += (uint32_t)nact;
+      if (w.rot >= (uint32_t)G) w.rot -= G;
       stamp(2);
     }
     // Phase boundary: a CTA-wide barrier only (none after qkv: the attention phase meets after polling its head's q; none

@@ -702,6 +702,10 @@ int dtk_create(const dtk_config* cfg, const void* weight_arena, uint64_t arena_b
           DTK_CK(launch_retile(W(eng, LN("dec.L", l, specs[i].name)), specs[i].N, specs[i].K, specs[i].mode,
                                eng->d_tiled + (int64_t)l * per_layer + off[i], 0));
       }
+      for (int i = 0; i < 5; ++i) {
+        m.mat[i].per = (m.mat[i].groups + grid - 1) / grid;
+        m.mat[i].nact = (m.mat[i].groups + m.mat[i].per - 1) / m.mat[i].per;
+      }
       m.mat[4].base = eng->d_tiled + per_layer * c.layers; m.mat[4].layer_stride = 0; m.mat[4].N = c.vocab; m.mat[4].K = c.hidden; m.mat[4].mode = TILE_SEQ;
       DTK_CK(launch_retile(W(eng, "dec.lm_head"), c.vocab, c.hidden, TILE_SEQ, eng->d_tiled + per_layer * c.layers, 0));
       m.tok = eng->d_tok; m.pos = eng->d_pos; m.slots = eng->d_slots; m.share_slot = eng->d_share_slot; m.share_len = eng->d_share_len;

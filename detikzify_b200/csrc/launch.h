@@ -194,6 +194,7 @@ struct MegaMat {
   int64_t layer_stride;   // elements between layers
   int N, K;               // logical rows / cols of the matrix (GLU: N = 2I interleaved source rows)
   int groups, tpg;        // 16-row groups, 256-column tiles per group
+  int per, nact;          // work split over the grid (host-computed: no division in the kernel): per = ceil(groups / grid) groups per participating CTA, nact = ceil(groups / per) participants
   int mode;
 };
 struct MegaArgs {
