@@ -178,7 +178,11 @@ DTK_API int dtk_gen_wait(dtk_engine* eng, int64_t step, int32_t* tokens_out_host
 DTK_API int dtk_gen_end(dtk_engine* eng);
 
 /* ---- engine options. "decode_impl": 1 = persistent weight-streaming decode kernel (default for
- *      B = 1), 0 = per-op kernels replayed from a CUDA graph (always used for B > 1). ----------- */
+ *      B = 1), 0 = per-op kernels replayed from a CUDA graph (always used for B > 1). Others (all with
+ *      working defaults): "gemm_impl" (see dtk_dbg_gemm_impl), "attn_impl" (ViT attention: 1 = tcgen05, 0 =
+ *      mma.sync), "cascade_attn" (shared-prefix attention of batched decode), "decode_gemm_min_batch",
+ *      "fuse_greedy", "vit_graph", and dev switches "mega_debug", "mega_flags", "mega_trace_layer",
+ *      "mega_nslots", "mega_variant". Unknown keys return DTK_ERR_INVALID. ------------------------- */
 DTK_API int dtk_set_option(dtk_engine* eng, const char* key, int64_t value);
 /*      Read back an option; the extra key "decode_persistent" reports whether B = 1 decode steps
  *      actually run on the persistent kernel (option set AND the device can co-schedule its grid). */
@@ -199,7 +203,8 @@ DTK_API int dtk_dbg_mega_times(dtk_engine* eng, long long* out_host, int max_val
  * rows 160..164 = the layer's five phases {start, staged, items done, barrier done}; returns the value count */
 DTK_API int dtk_dbg_mega_trace(dtk_engine* eng, long long* out_host, int max_values);
 /* select the dense GEMM implementation used by dtk_dbg_gemm and the engines of this process:
- * 0 = mma.sync, 1 = tcgen05/TMEM where supported, -1 = query only; returns the current setting. Bits 8..11 of a
+ * 0 = mma.sync, 1 = tcgen05 one 128 x 128 tile per CTA, 2 (default) = persistent 128 x 256 tcgen05 kernel with two TMEM
+ * accumulators, 3 = CTA-pair (cta_group::2) 256 x 256 kernel, -1 = query only; returns the current setting. Bits 8..11 of a
  * non-negative value force the split-K factor (cluster size 1..8) of the batched-decode tile; 0 = heuristic. */
 DTK_API int dtk_dbg_gemm_impl(int impl);
 /* C = act(A[M,K] * W[N,K]^T + bias) (+resid); glu: out[m, n/2] = silu(c[m,n]) * c[m,n+1] */
