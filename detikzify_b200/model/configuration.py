@@ -82,7 +82,9 @@ class DetikzifyConfig:
 
     @property
     def pooling_mode(self) -> str:
-        return "cos"
+        # v1 configs pool with "cos" (v1/configuration_detikzify.py:11-13); the v2 config has no such attribute and
+        # ImageSim.from_detikzify then defaults to "emd" (evaluate/imagesim.py:64)
+        return "cos" if self.projector_bias else "emd"
 
     @property
     def text_config(self) -> "DetikzifyConfig":

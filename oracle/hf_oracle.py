@@ -238,6 +238,33 @@ class Oracle:
         return F.cosine_similarity(p1.squeeze().double(), p2.squeeze().double(), dim=0).item()
 
 
+    # ---- a13: SelfSim "emd" (detikzify/evaluate/imagesim.py:105-107,121-123): patch tokens of both images, cost 1 - cosine in
+    # fp64, earth mover's distance between the UNIFORM distributions over the patches (ot.lp.emd2(M, a=[], b=[]): POT 0.9.x
+    # network simplex, absent offline). Restated here as the transport LP itself (scipy HiGHS): min <P, M> s.t. P 1 = 1/n,
+    # P^T 1 = 1/m, P >= 0 - independent of the assignment solver the product uses.
+    @torch.no_grad()
+    def selfsim_emd(self, pix1: torch.Tensor, pix2: torch.Tensor) -> float:
+        import math
+        import numpy as np
+        from scipy.optimize import linprog
+        t1, _ = self.vision(pix1)
+        t2, _ = self.vision(pix2)
+        a, b = t1.squeeze(0).double(), t2.squeeze(0).double()
+        a = a / a.norm(dim=1, keepdim=True)
+        b = b / b.norm(dim=1, keepdim=True)
+        M = (1.0 - a @ b.T).numpy()
+        n, m = M.shape
+        A_eq = np.zeros((n + m, n * m))
+        for i in range(n):
+            A_eq[i, i * m:(i + 1) * m] = 1.0
+        for j in range(m):
+            A_eq[n + j, j::m] = 1.0
+        b_eq = np.concatenate([np.full(n, 1.0 / n), np.full(m, 1.0 / m)])
+        res = linprog(M.reshape(-1), A_eq=A_eq, b_eq=b_eq, bounds=(0, None), method="highs")
+        assert res.status == 0, res.message
+        return 2 * math.tanh(-float(res.fun)) + 1
+
+
 def config_to_dict(cfg) -> dict:
     """Accept the product's DetikzifyConfig dataclass (duck-typed) or a plain dict."""
     if isinstance(cfg, dict):

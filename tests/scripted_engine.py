@@ -55,8 +55,15 @@ class ScriptedEngine:
         self.calls.append(("vit_encode", tuple(pix.shape)))
         B = pix.shape[0]
         feat = pix.reshape(B, -1)[:, : self.cfg.vision_config.hidden_size].float()
-        return (torch.zeros(B, self.cfg.vision_config.num_positions, self.cfg.vision_config.hidden_size) if want_tokens else None,
-                feat if want_pooled else None)
+        # patch "tokens": the first hidden_size values of every position's share of the pixels (+2: pixels lie in [-1, 1], never a zero row), so that the
+        # patch-token similarity modes (cos_avg, emd) see something image-dependent
+        P, D = self.cfg.vision_config.num_positions, self.cfg.vision_config.hidden_size
+        flat = pix.reshape(B, -1).float()
+        per = flat.shape[1] // P
+        tokens = flat[:, : P * per].reshape(B, P, per)[:, :, :D]
+        if tokens.shape[2] < D:
+            tokens = torch.nn.functional.pad(tokens, (0, D - tokens.shape[2]))
+        return ((tokens + 2.0) if want_tokens else None, feat if want_pooled else None)
 
     def prefill(self, slot, ids, start_pos=0, img_embeds=None, img_start=0, want_all_logits=False):
         ids = ids.tolist()

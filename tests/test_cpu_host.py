@@ -276,7 +276,48 @@ def test_imagesim_protocol():
     sim.update(img1=_figure(), img2=other)
     assert sim.compute() < 1.0
     with pytest.raises(NotImplementedError):
-        ImageSim(mode="emd")
+        ImageSim(mode="ssim")
+
+
+def test_imagesim_emd_mode():
+    """The v2 models' default SelfSim: 2 tanh(-EMD) + 1 over the patch tokens (reference evaluate/imagesim.py:105-107,121-123).
+    The product solves the uniform equal-size transport problem as an assignment problem; here it is held to the transport LP
+    itself (what POT's emd2 solves) on random token sets, and run through the public protocol on the scripted tower."""
+    import math
+    import numpy as np
+    from scipy.optimize import linprog
+    from detikzify_b200.evaluate import ImageSim
+    g = torch.Generator().manual_seed(7)
+    for n, d in ((5, 8), (12, 16), (16, 6)):
+        f1, f2 = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+        a, b = f1.double() / f1.double().norm(dim=1, keepdim=True), f2.double() / f2.double().norm(dim=1, keepdim=True)
+        M = (1.0 - a @ b.T).numpy()
+        A_eq = np.zeros((2 * n, n * n))
+        for i in range(n):
+            A_eq[i, i * n:(i + 1) * n] = 1.0
+            A_eq[n + i, i::n] = 1.0
+        res = linprog(M.reshape(-1), A_eq=A_eq, b_eq=np.full(2 * n, 1.0 / n), bounds=(0, None), method="highs")
+        assert res.status == 0
+        assert ImageSim._emd_similarity(f1, f2) == pytest.approx(2 * math.tanh(-res.fun) + 1, abs=1e-9)
+    assert ImageSim._emd_similarity(f1, f1) == pytest.approx(1.0, abs=1e-12)
+    with pytest.raises(ValueError):
+        ImageSim._emd_similarity(f1, f2[:3])
+    model, proc, eng = _model()
+    sim = ImageSim.from_detikzify(model, proc, mode="emd")
+    assert str(sim) == "ImageSim (EMD)"
+    other = Image.new("RGB", (80, 80), "white")
+    ImageDraw.Draw(other).rectangle((5, 5, 70, 70), fill="black")
+    same, diff = sim.get_similarity(_figure(), _figure()), sim.get_similarity(_figure(), other)
+    assert same == pytest.approx(1.0) and -1.0 < diff < 1.0
+    assert sim.get_similarities([_figure(), other], _figure()) == pytest.approx([same, diff])
+
+
+def test_pooling_mode_follows_the_model_generation():
+    """v1 configs pool with "cos" (v1/configuration_detikzify.py:11-13); the v2 config has no pooling_mode, so the reference's
+    ImageSim.from_detikzify falls back to "emd" (evaluate/imagesim.py:64)."""
+    from detikzify_b200.model.configuration import preset
+    assert preset("tiny").pooling_mode == "cos" and preset("nllg/detikzify-ds-1.3b").pooling_mode == "cos"
+    assert preset("tiny-v2").pooling_mode == "emd" and preset("nllg/detikzify-v2-8b").pooling_mode == "emd"
 
 
 def test_shard_and_interleave():

@@ -177,3 +177,20 @@ def test_oracle_matches_reference_v2_golden():
     assert (dec[0, -1] - gold["decode_logits"]).abs().max() < 2e-5
     out = oracle.generate(gold["generate_prompt"][None], pix, max_length=gold["generate_ids"].numel())
     assert torch.equal(out[0], gold["generate_ids"])
+
+
+def test_oracle_emd_selfsim_equals_assignment_formulation():
+    """oracle.selfsim_emd restates the reference's "emd" SelfSim as the transport LP between uniform marginals (what POT's
+    emd2(M, [], []) solves, evaluate/imagesim.py:121-123); with equally many patches the optimum is a permutation, so the
+    assignment solver the product uses must give the same value on the same (oracle) patch tokens."""
+    from conftest import model_bundle
+    from detikzify_b200.evaluate.imagesim import ImageSim
+    from oracle.hf_oracle import synthetic_pixels
+    for name in ("tiny", "tiny-v2"):
+        cfg, sd, oracle = model_bundle(name)
+        p1 = synthetic_pixels(1, cfg.vision_config.image_size, seed=11)
+        p2 = synthetic_pixels(1, cfg.vision_config.image_size, seed=12)
+        t1, _ = oracle.vision(p1)
+        t2, _ = oracle.vision(p2)
+        assert ImageSim._emd_similarity(t1.squeeze(0), t2.squeeze(0)) == pytest.approx(oracle.selfsim_emd(p1, p2), abs=1e-9)
+        assert oracle.selfsim_emd(p1, p1) == pytest.approx(1.0, abs=1e-9)

@@ -127,6 +127,38 @@ def test_imagesim_on_cuda_tower_matches_oracle(mode):
         assert abs(oracle.selfsim_cos(p0, p1) - ref) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["tiny2", "tiny-v2"])
+def test_imagesim_emd_on_cuda_tower_matches_oracle(name):
+    """The v2 models' SelfSim ("emd": 2 tanh(-EMD) + 1 over the patch tokens, evaluate/imagesim.py:105-107,121-123) on the CUDA
+    vision tower (assignment solver on the host) vs the oracle (HF SigLIP tokens, the transport LP itself)."""
+    from PIL import Image, ImageDraw
+    from detikzify_b200.evaluate.imagesim import ImageSim
+    from detikzify_b200.model.modeling import DetikzifyForCausalLM
+    from detikzify_b200.model import build_processor
+    from detikzify_b200.util.image import expand, load
+    cfg, sd, oracle = model_bundle(name)
+    model = DetikzifyForCausalLM(cfg, engine=engine_for(name))
+    proc = build_processor(cfg)
+    ims = []
+    for k in range(2):
+        im = Image.new("RGB", (200, 160), "white")
+        d = ImageDraw.Draw(im)
+        for j in range(6):
+            d.line([(10 + 25 * j, 20 + 9 * k * j), (180 - 20 * j, 140 - 15 * k)], fill="black", width=2 + k)
+        d.ellipse([60, 40 + 30 * k, 140, 120], outline="black", width=3)
+        ims.append(im)
+    sim = ImageSim.from_detikzify(model, proc, mode="emd")
+    if name == "tiny-v2":
+        assert ImageSim.from_detikzify(model, proc).mode == "emd"   # the v2 default
+    got = sim.get_similarity(ims[0], ims[1])
+    pix = [proc.image_processor(images=expand(load(im), max(im.size), do_trim=True), return_tensors="pt")["pixel_values"] for im in ims]
+    ref = oracle.selfsim_emd(pix[0], pix[1])
+    assert abs(got - ref) < 5e-3, (got, ref)
+    assert abs(sim.get_similarity(ims[0], ims[0]) - 1.0) < 1e-6
+    both = sim.get_similarities([ims[1], ims[0]], ims[0])
+    assert abs(both[0] - got) < 2e-3 and abs(both[1] - 1.0) < 1e-6
+
+
 def test_shared_prefix_rollouts_against_oracle():
     """dtk_seq_share: four rollouts READ the first 41 positions (image span + path prefix) from one base slot — whole
     16-position blocks shared, the 9-position remainder copied — then prefill their own suffixes and decode. Every logits
