@@ -96,7 +96,22 @@ def reference_infer():
         tmf.pairwise_cosine_similarity = lambda a, b: torch.nn.functional.normalize(a, dim=-1) @ torch.nn.functional.normalize(b, dim=-1).T
         sys.modules["torchmetrics.functional"] = tmf
         ot, otlp = types.ModuleType("ot"), types.ModuleType("ot.lp")
-        otlp.emd2 = lambda **kw: (_ for _ in ()).throw(NotImplementedError("emd mode needs POT"))   # v1 models pool with "cos"
+        def emd2(M, a, b):   # POT's ot.lp.emd2 (absent offline) restated: the transport LP, empty marginals = uniform
+            import numpy as np
+            from scipy.optimize import linprog
+            M = np.asarray(M, dtype=np.float64)
+            n, m = M.shape
+            a = np.full(n, 1.0 / n) if len(a) == 0 else np.asarray(a, dtype=np.float64)
+            b = np.full(m, 1.0 / m) if len(b) == 0 else np.asarray(b, dtype=np.float64)
+            A_eq = np.zeros((n + m, n * m))
+            for i in range(n):
+                A_eq[i, i * m:(i + 1) * m] = 1.0
+            for j in range(m):
+                A_eq[n + j, j::m] = 1.0
+            res = linprog(M.reshape(-1), A_eq=A_eq, b_eq=np.concatenate([a, b]), bounds=(0, None), method="highs")
+            assert res.status == 0, res.message
+            return float(res.fun)
+        otlp.emd2 = emd2
         sys.modules["ot"], sys.modules["ot.lp"] = ot, otlp
         _load("detikzify.evaluate.imagesim", f"{REF}/evaluate/imagesim.py")
         tikz = types.ModuleType("detikzify.infer.tikz")
@@ -184,6 +199,26 @@ def test_reference_selfsim_metric_runs_on_our_vision_model(reference_infer):
     results = list(pipe.simulate(image=_figure(), expansions=3))
     assert len(results) == 3 and all(-1.0 <= score <= 1.0 + 1e-9 for score, _ in results)
     assert any(c[0] == "vit_encode" for c in eng.calls)
+
+
+def test_reference_emd_selfsim_agrees_with_ours(reference_infer):
+    """The v2 default reward: the reference's own ImageSim in "emd" mode (evaluate/imagesim.py:105-107,121-123; POT's emd2
+    restated as the transport LP) and ours (assignment solver) on the same vision model object and image processor."""
+    from PIL import ImageDraw
+    from detikzify_b200.evaluate.imagesim import ImageSim as Ours
+    RefImageSim = sys.modules["detikzify.evaluate.imagesim"].ImageSim
+    model, proc, eng = _ours(eos_at=36)
+    ref = RefImageSim.from_detikzify(model, proc, mode="emd")
+    ours = Ours.from_detikzify(model, proc, mode="emd")
+    other = Image.new("RGB", (80, 80), "white")
+    ImageDraw.Draw(other).ellipse((10, 10, 60, 70), outline="black", width=4)
+    # the reference object feeds bf16 pixels (its .to(device, dtype)), ours fp32: compare the solvers on the SAME patch tokens ...
+    f1, f2 = ref.get_vision_features(_figure()), ref.get_vision_features(other)
+    a = ref.get_similarity(_figure(), other)
+    assert f1.ndim == 2 and a == pytest.approx(Ours._emd_similarity(f1, f2), abs=1e-9) and -1.0 < a < 1.0
+    # ... and the two end-to-end paths within the bf16 rounding of the inputs
+    assert a == pytest.approx(ours.get_similarity(_figure(), other), abs=5e-2)
+    assert ref.get_similarity(_figure(), _figure()) == pytest.approx(1.0, abs=1e-9)
 
 
 def test_image_processor_matches_reference_preprocess():
